@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds transcribed per second (log-mel + paper-size hFT forward) on N B200s.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference            # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1] -- paper-size hFT
+(hid 256, ff 512, 3+3 layers, 4 heads, 128-frame window, margins 32) on 1 hour of synthetic 16 kHz audio per GPU:
+57.6 M samples -> 225 001 log-mel frames -> 1 758 segments.  Weak scaling: every rank processes its own hour
+(files/segments shard with no data-path collective).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEG_SECONDS = 128 * 256 / 16000.0            # 2.048 s of audio per segment
+GFLOP_PER_SEGMENT = 249.44                   # algorithmic, paper size, reference formulation
+LOGMEL_BYTES_PER_FRAME = 2048                # 1 KB in + 1 KB out (fp32)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops_sustained"], "src": "MEASURED_PEAKS.json (sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = []
+        for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_arm(n_segments, threads=None):
+    """The reference's CPU path for the same workload, via the oracle port (the reference is Python and cannot travel
+    to the GPU box): C log-mel restatement + torch-CPU forward restatement, paper size, on a bounded sample."""
+    import numpy as np
+    import torch
+    import nylon_amt_b200 as hft
+    from oracle import c_logmel, hft_oracle
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    cfg = hft.default_config()
+    model = hft.build_model(cfg, 256, 512, 3, 4, seed=1234, device="cpu")
+    orc = hft_oracle.Oracle(model.state_dict(), 4)
+    from nylon_amt_b200 import melfb
+    fb, win = melfb.melscale_fbanks().numpy(), melfb.hann_window().numpy()
+    n_samples = int(n_segments * 128 * 256)
+    rng = np.random.default_rng(1000)
+    wav = (0.1 * rng.standard_normal(n_samples)).astype(np.float32)
+    t0 = time.perf_counter()
+    feat = c_logmel.logmel(wav, win, fb, n_threads=cores)
+    t_mel = time.perf_counter() - t0
+    spec = hft_oracle.segment_feature(feat[:n_segments * 128])
+    t0 = time.perf_counter()
+    orc(spec)
+    t_fwd = time.perf_counter() - t0
+    audio = n_segments * SEG_SECONDS
+    return {"value": audio / (t_mel + t_fwd), "seconds": t_mel + t_fwd, "cores": cores, "audio_s": audio,
+            "logmel_s": t_mel, "forward_s": t_fwd}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("HFT_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--hours", type=float, default=1.0, help="audio per GPU per step (configs[1] = 1 hour)")
+    ap.add_argument("--chunk", type=int, default=16, help="segments per forward call")
+    ap.add_argument("--cpu-segments", type=int, default=8, help="bounded CPU-baseline sample (segments of 2.048 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "audio-sec/sec transcribed (log-mel+hFT fwd)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_arm(args.cpu_segments)
+            if i >= args.warmup:
+                vals.append(r)
+        sec = sum(v["seconds"] for v in vals) / len(vals)
+        value = vals[0]["audio_s"] / sec
+        sample = "%d segments (%.1f s of audio) per step: C log-mel oracle + torch-CPU forward oracle, paper size" % (args.cpu_segments, vals[0]["audio_s"])
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: paper-size hFT (hid 256, ff 512, 3+3 layers, 4 heads) + log-mel, bounded sample of the 1 h clip", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": vals[0]["cores"], "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import nylon_amt_b200 as hft
+    from nylon_amt_b200 import _lib
+    L = _lib.lib()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = hft.default_config()
+    amt = hft.AMT(cfg, None, batch_size=args.chunk)
+    model = hft.build_model(cfg, 256, 512, 3, 4, seed=1234, device=dev)
+    model.precision = args.precision
+    model.max_batch = args.chunk
+    amt.model = model
+
+    n_samples = int(round(args.hours * 3600 * 16000))
+    T = 1 + n_samples // 256
+    n_seg = (T + 127) // 128
+    audio_s = n_samples / 16000.0
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    wav_dev = 0.1 * torch.randn(n_samples, device=dev, generator=gen)         # inputs resident in HBM (230 MB > L2)
+    wav_host = wav_dev.cpu().pin_memory()
+    # padded feature buffer: 32 rows of min_value, T log-mel rows written in place by the kernel, ragged tail + 32 rows
+    rows = 32 + n_seg * 128 + 32
+    a_input = torch.full((rows, 256), cfg["input"]["min_value"], device=dev)
+    feat_view = a_input[32:32 + T]
+    spec_all = torch.as_strided(a_input, (n_seg, 256, 192), (128 * 256, 1, 256))
+    nb = min(args.chunk, n_seg)
+    opt = dict(device=dev, dtype=torch.float32)
+    outs = [torch.empty((nb, 128, 88), **opt) for _ in range(3)] + [torch.empty((nb, 128, 88, 128), **opt), torch.empty((nb, 128, 4, 88, 256), **opt)] + \
+           [torch.empty((nb, 128, 88), **opt) for _ in range(3)] + [torch.empty((nb, 128, 88, 128), **opt)]
+    plan = amt._logmel_plan()
+    stream = torch.cuda.current_stream(dev)
+    launches = [0]
+
+    def logmel_dev(src):
+        _lib.check(L.hft_logmel_f32(plan.ptr, ctypes.c_void_p(src.data_ptr()), n_samples, ctypes.c_void_p(feat_view.data_ptr()), T,
+                                    ctypes.c_void_p(stream.cuda_stream)), "hft_logmel_f32")
+        launches[0] += L.hft_last_launch_count()
+
+    def step_device():
+        """value: inputs already in HBM; full 9-output forward (attention probabilities included) per chunk."""
+        logmel_dev(wav_dev)
+        for s0 in range(0, n_seg, nb):
+            b = min(nb, n_seg - s0)
+            model.forward_into(spec_all[s0:s0 + b], [t[:b] for t in outs])
+            launches[0] += L.hft_last_launch_count()
+
+    # e2e: host waveform in, host transcript arrays out (what AMT.wav2feature + AMT.transcript hand back: 6 fp32 + 2 int8
+    # [T,88] arrays), H2D and D2H inside the timed region.
+    res_f = [torch.empty((n_seg * 128, 88), dtype=torch.float32).pin_memory() for _ in range(6)]
+    res_v = [torch.empty((n_seg * 128, 88), dtype=torch.int8).pin_memory() for _ in range(2)]
+    wav_stage = torch.empty_like(wav_dev)
+
+    def step_e2e():
+        wav_stage.copy_(wav_host, non_blocking=True)
+        logmel_dev(wav_stage)
+        for s0 in range(0, n_seg, nb):
+            b = min(nb, n_seg - s0)
+            o = [t[:b] for t in outs]
+            model.forward_into(spec_all[s0:s0 + b], o, want_attention=False)
+            r0, r1 = s0 * 128, (s0 + b) * 128
+            for dst, i in zip(res_f, (0, 1, 2, 5, 6, 7)):
+                dst[r0:r1].copy_(o[i].reshape(b * 128, 88), non_blocking=True)
+            for dst, i in zip(res_v, (3, 8)):
+                dst[r0:r1].copy_(o[i].argmax(3).reshape(b * 128, 88).to(torch.int8), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches[0] = 0
+    ms = timed(step_device, args.steps)
+    n_launch = launches[0]
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    value = world * audio_s / (ms_step / 1e3)
+
+    step_e2e()                                                                 # warm the e2e path (pinned buffers, argmax)
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 2))) / max(1, min(args.steps, 2))
+    e2e_value = world * audio_s / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel class, measured live with CUDA events around every launch of one extra step
+    L.hft_profile_enable(1)
+    step_device()
+    torch.cuda.synchronize(dev)
+    L.hft_profile_enable(0)
+    prof = {}
+    names = ["logmel", "front", "gemm", "attention", "norm", "heads"]
+    for k, n in enumerate(names):
+        t, c = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(L.hft_profile_read(k, ctypes.byref(t), ctypes.byref(c)), "hft_profile_read")
+        prof[n] = {"ms": t.value, "launches": c.value}
+    pk = peaks()
+    total_prof = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda n: prof[n]["ms"])
+    fwd_ms = total_prof - prof["logmel"]["ms"]
+    achieved_tf = n_seg * GFLOP_PER_SEGMENT / max(fwd_ms, 1e-9)                 # GFLOP / ms = TFLOP/s
+    roofline = {"bound": "tensor", "kernel": "hFT forward (all classes; dominant: %s, %.0f%% of step)" % (dom, 100 * prof[dom]["ms"] / total_prof),
+                "achieved": achieved_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops"], "traffic": None,
+                "peak_source": pk["src"], "algorithmic_gflop_per_segment": GFLOP_PER_SEGMENT,
+                "classes_ms": {n: round(v["ms"], 3) for n, v in prof.items()},
+                "logmel": {"bound": "hbm", "achieved": T * LOGMEL_BYTES_PER_FRAME / max(prof["logmel"]["ms"], 1e-9) / 1e6,
+                           "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": T * LOGMEL_BYTES_PER_FRAME / max(prof["logmel"]["ms"], 1e-9) / 1e6 / pk["hbm_gbs"]}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(args.cpu_segments)
+        cpu = {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port",
+               "sample": "%d segments (%.1f s of audio): C log-mel oracle %.3f s + torch-CPU forward oracle %.2f s, paper size" %
+                         (args.cpu_segments, r["audio_s"], r["logmel_s"], r["forward_s"])}
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic",
+                "config": {"workload": "configs[1]: paper-size hFT (hid 256, ff 512, 3+3 layers, 4 heads, 128-frame window, margins 32) + fused log-mel on "
+                                       "%.2f h of synthetic 16 kHz audio per GPU (%d frames, %d segments)" % (args.hours, T, n_seg),
+                           "precision": args.precision, "chunk_segments": nb, "l2_policy": "inputs and activations per step (>= 230 MB) exceed the 126 MB L2",
+                           "sharding": "one hour per rank, no data-path collective"},
+                "x_realtime_per_gpu": value / world,
+                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(wav_host.numel() * 4),
+                        "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in res_f + res_v)), "ms_per_step": ms_e2e},
+                "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,156 @@
+/* libhft_sm100.so -- C ABI of the B200 (sm_100a) implementation of nylon-amt's hFT-Transformer hot path.
+ *
+ * The reference (d-f/nylon-amt) is 100 % Python and has no FFI layer; its "operator API" for this path is two
+ * Python call signatures.  Each entry point below names the reference interface it replaces; the host-side mirror
+ * of those signatures lives in nylon_amt_b200/{amt.py,model_spec2midi.py} and INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t or an HFT_ERR_* code otherwise; hft_last_error() gives
+ *     the message of the last failure on the calling thread.  Nothing throws across the ABI.
+ *   - POD arguments only.  `*_dev` pointers are CUDA device pointers owned by the caller (PyTorch in the mirror);
+ *     `*_host` pointers are host memory.  `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream).  Launches are asynchronous on that stream unless stated otherwise.
+ *   - no CPU fallback and no silent shape fallback: an unsupported configuration is an error.
+ *   - handles are not thread-safe; use one handle per device per thread (the reference is single-device too:
+ *     hftt_code/training/m_training.py:113, hftt_code/model/amt.py:14-17).
+ */
+#ifndef HFT_SM100_H
+#define HFT_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFT_ERR_ARG 10001
+#define HFT_ERR_UNSUPPORTED 10002
+#define HFT_ERR_STATE 10003
+
+/* ABI version of this header (bumped on incompatible change). */
+int hft_version(void);
+/* Message of the last error raised on this thread ("" if none). */
+const char* hft_last_error(void);
+/* Device facts the host side uses for sharding and bench bookkeeping. */
+int hft_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Log-mel front end.
+ * Replaces: torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=2048, win_length=2048, hop_length=256,
+ *           pad_mode='constant', n_mels=256, norm='slaney') followed by torch.log(mel + log_offset).T in
+ *           AMT.wav2feature  -- reference hftt_code/model/amt.py:59-61 (parameters hftt_code/corpus/config.json:2-12;
+ *           second call site dataset_creation.py:45-53,24).
+ * Fixed geometry: n_fft 2048, hop 256, 1025 FFT bins, 256 mel bins.  T = 1 + n_samples / 256 frames.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hft_logmel_plan hft_logmel_plan;
+
+/* window_host: 2048 floats (torch.hann_window(2048)) or NULL for the built-in periodic Hann.
+ * fb_host: dense filterbank [1025][256] row-major exactly as torchaudio's MelScale.fb, or NULL for the built-in
+ *          HTK/slaney 0..8 kHz table.  Each mel column must be a band of <= 31 consecutive FFT bins. */
+int hft_logmel_create(hft_logmel_plan** plan, const float* window_host, const float* fb_host, float log_offset);
+int hft_logmel_destroy(hft_logmel_plan* plan);
+int64_t hft_logmel_num_frames(int64_t n_samples);
+
+/* One clip resident in HBM: wav_dev [n_samples] fp32 mono 16 kHz -> out_dev [n_frames][256] fp32 (amt.py:61 layout). */
+int hft_logmel_f32(hft_logmel_plan* plan, const float* wav_dev, int64_t n_samples, float* out_dev, int64_t n_frames, void* stream);
+
+/* A ragged batch of clips in ONE launch (the file loop of hftt_code/corpus/conv_wav2fe.py:41-48): clip c is
+ * wav_dev[clip_start_host[c] .. clip_start_host[c] + clip_len_host[c]); its T_c rows follow those of clip c-1 in
+ * out_dev.  Clips whose start is a multiple of 4 samples (16 bytes) are staged by TMA. */
+int hft_logmel_batch_f32(hft_logmel_plan* plan, const float* wav_dev, const int64_t* clip_start_host, const int64_t* clip_len_host,
+                         int n_clips, float* out_dev, void* stream);
+
+/* Host-buffer form of AMT.wav2feature's arithmetic (amt.py:59-63 returns a CPU tensor): H2D copy, kernel, D2H copy,
+ * stream synchronised on return. */
+int hft_logmel_host_f32(hft_logmel_plan* plan, const float* wav_host, int64_t n_samples, float* out_host, int64_t n_frames,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hFT-Transformer forward.
+ * Replaces: Model_SPEC2MIDI.forward(input_spec) -- reference hftt_code/model/model_spec2midi.py:15-35
+ *           (Encoder_SPEC2MIDI.forward :60-106, Decoder_SPEC2MIDI.forward :145-216, EncoderLayer :230-245,
+ *           DecoderLayer_Zero :255-272, DecoderLayer :283-306, MultiHeadAttentionLayer :322-360,
+ *           PositionwiseFeedforwardLayer :369-378).  Eval semantics (dropout = identity).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hft_model hft_model;
+
+/* Constructor arguments of Encoder_SPEC2MIDI / Decoder_SPEC2MIDI (model_spec2midi.py:42,113). */
+typedef struct hft_dims {
+  int32_t n_margin;      /* 32  */
+  int32_t n_frame;       /* 128 */
+  int32_t n_bin;         /* 256 */
+  int32_t cnn_channel;   /* 4   */
+  int32_t cnn_kernel;    /* 5   */
+  int32_t hid_dim;       /* 256 paper / 64 reduced */
+  int32_t pf_dim;        /* 512 / 128 */
+  int32_t n_enc_layers;  /* 3 / 2 */
+  int32_t n_dec_layers;  /* 3 / 2 */
+  int32_t n_heads;       /* 4 / 2 (encoder and decoder use the same count) */
+  int32_t n_note;        /* 88  */
+  int32_t n_velocity;    /* 128 */
+} hft_dims;
+
+/* Arithmetic the forward runs in. */
+#define HFT_PREC_F32 0      /* fp32 CUDA-core kernels: the 2e-3 parity path */
+#define HFT_PREC_BF16 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 softmax/LayerNorm/sigmoid */
+#define HFT_PREC_F16 2      /* fp16 operands on tcgen05 tensor cores (3 more mantissa bits than bf16) */
+
+int hft_model_create(hft_model** model, const hft_dims* dims);
+int hft_model_destroy(hft_model* model);
+
+/* The state_dict schema (reference Appendix: every key of Model_SPEC2MIDI.state_dict()).  The host passes one fp32
+ * device pointer per tensor in this order. */
+int hft_model_num_weights(const hft_model* model);
+const char* hft_model_weight_name(const hft_model* model, int index);
+int64_t hft_model_weight_numel(const hft_model* model, int index);
+
+/* Register (or re-register after load_state_dict) the parameters.  The library copies them and derives what the
+ * kernels use (collapsed 65-tap front filter, fused QKV / head matrices, 16-bit operand copies). */
+int hft_model_set_weights(hft_model* model, const float* const* weights_dev, int n_weights, void* stream);
+
+/* The 9-tuple Model_SPEC2MIDI.forward returns (model_spec2midi.py:35).  All fp32, contiguous:
+ *   onset/offset/mpe  [B][n_frame][n_note]  sigmoid probabilities
+ *   velocity          [B][n_frame][n_note][n_velocity]  raw logits
+ *   attention         [B][n_frame][n_heads][n_note][n_bin]  softmax of the last cross-attention
+ * Any pointer may be NULL to skip writing that output. */
+typedef struct hft_outputs {
+  float* onset_A;
+  float* offset_A;
+  float* mpe_A;
+  float* velocity_A;
+  float* attention;
+  float* onset_B;
+  float* offset_B;
+  float* mpe_B;
+  float* velocity_B;
+} hft_outputs;
+
+/* spec_dev: [B][n_bin][n_margin + n_frame + n_margin] fp32 with element strides (the reference calls forward with
+ * a non-contiguous .T view, amt.py:89, so strides are part of the interface). */
+int hft_forward(hft_model* model, int precision, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                int32_t batch, const hft_outputs* outputs, void* stream);
+
+/* Largest batch one hft_forward call processes at once (bigger batches are looped internally). */
+int hft_model_set_max_batch(hft_model* model, int32_t max_batch);
+
+/* Number of kernels the last hft_forward / hft_logmel call on this thread launched (bench bookkeeping). */
+int64_t hft_last_launch_count(void);
+
+/* Per-kernel-class device timing for the roofline report (bench.py).  While enabled, every launch is bracketed by
+ * CUDA events on the launching stream; hft_profile_read synchronises those events and returns the accumulated
+ * milliseconds and launch count of one class, then clears it. */
+#define HFT_KCLASS_LOGMEL 0
+#define HFT_KCLASS_FRONT 1
+#define HFT_KCLASS_GEMM 2
+#define HFT_KCLASS_ATTENTION 3
+#define HFT_KCLASS_NORM 4
+#define HFT_KCLASS_HEADS 5
+#define HFT_KCLASS_COUNT 6
+int hft_profile_enable(int on);
+int hft_profile_read(int kclass, double* ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFT_SM100_H */

@@ -1,0 +1,262 @@
+"""Host-side mirror of the reference's hftt_code/model/amt.py (class AMT) for the hot path.
+
+Same constructor and method signatures as the reference (AMT.__init__ amt.py:10, wav2feature :34, transcript :66,
+transcript_stride :121, mpe2note :179).  The arithmetic runs in libhft_sm100.so (include/hft_sm100.h):
+  * wav2feature  -> fused log-mel kernel (replaces torchaudio MelSpectrogram + log, amt.py:59-61)
+  * transcript   -> windows are gathered on the device as a strided view of the padded feature and run through
+                    Model_SPEC2MIDI.forward in batches (replaces the batch-1 loop with 1 H2D + 8 D2H per segment,
+                    amt.py:88-113)
+There is no CPU fallback: without a CUDA device these methods raise.
+"""
+import ctypes
+import pickle
+import wave as _wave
+
+import numpy as np
+import torch
+
+from . import _lib, melfb
+
+
+def _read_wav(path):
+    """(float32 [C,N] in [-1,1), sample_rate) like torchaudio.load's default normalisation (amt.py:55)."""
+    try:
+        from scipy.io import wavfile
+        sr, data = wavfile.read(path)
+        if data.ndim == 1:
+            data = data[:, None]
+        if data.dtype == np.int16:
+            x = data.astype(np.float32) / np.float32(32768.0)
+        elif data.dtype == np.int32:
+            x = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
+        elif data.dtype == np.uint8:
+            x = (data.astype(np.float32) - np.float32(128.0)) / np.float32(128.0)
+        else:
+            x = data.astype(np.float32)
+        return torch.from_numpy(np.ascontiguousarray(x.T)), int(sr)
+    except ImportError:
+        with _wave.open(path, "rb") as f:
+            n_ch, width, sr, n = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
+            raw = f.readframes(n)
+        if width != 2:
+            raise RuntimeError("only 16-bit PCM wav is readable without scipy")
+        a = np.frombuffer(raw, dtype="<i2").reshape(-1, n_ch).T.astype(np.float32) / np.float32(32768.0)
+        return torch.from_numpy(np.ascontiguousarray(a)), int(sr)
+
+
+class _LogmelPlan:
+    def __init__(self, window, fb, log_offset):
+        self.ptr = ctypes.c_void_p()
+        w = window.contiguous().cpu().float()
+        f = fb.contiguous().cpu().float()
+        _lib.check(_lib.lib().hft_logmel_create(ctypes.byref(self.ptr), ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(f.data_ptr()),
+                                                ctypes.c_float(log_offset)), "hft_logmel_create")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().hft_logmel_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class AMT():
+    def __init__(self, config, model_path, batch_size=1, verbose_flag=False):
+        if verbose_flag is True:
+            print('torch version: ' + torch.__version__)
+            print('torch cuda   : ' + str(torch.cuda.is_available()))
+        # the reference falls back to 'cpu' (amt.py:14-17); this implementation is CUDA-only and fails at first use
+        self.device = 'cuda'
+        self.config = config
+        if model_path is None:
+            self.model = None
+        else:
+            from . import install_reference_aliases
+            install_reference_aliases()
+            with open(model_path, 'rb') as f:
+                self.model = pickle.load(f)
+            self.model = self.model.to(self.device)
+            self.model.eval()
+            if verbose_flag is True:
+                print(self.model)
+        self.batch_size = batch_size
+        self._plan = None
+        self._fb = None
+
+    # ---- feature -----------------------------------------------------------------------------------------
+    def _check_feature_config(self):
+        f = self.config['feature']
+        if not (f['sr'] == 16000 and f['fft_bins'] == 2048 and f['window_length'] == 2048 and f['hop_sample'] == 256 and
+                f['mel_bins'] == 256 and f['pad_mode'] == 'constant'):
+            raise RuntimeError("the fused log-mel kernel implements the reference geometry only "
+                               "(sr 16000, n_fft/win 2048, hop 256, 256 mels, constant padding); got %r" % (f,))
+
+    def mel_fb(self):
+        if self._fb is None:
+            f = self.config['feature']
+            self._fb = melfb.melscale_fbanks(f['fft_bins'] // 2 + 1, 0.0, float(f['sr'] // 2), f['mel_bins'], f['sr'])
+        return self._fb
+
+    def _logmel_plan(self):
+        if self._plan is None:
+            self._check_feature_config()
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the B200 path has no CPU fallback")
+            self._plan = _LogmelPlan(melfb.hann_window(self.config['feature']['fft_bins']), self.mel_fb(),
+                                     float(self.config['feature']['log_offset']))
+        return self._plan
+
+    def wave2feature(self, wave_mono_16k):
+        """Device-resident variant: fp32 CUDA tensor [N] (mono, 16 kHz) -> CUDA tensor [T,256]."""
+        plan = self._logmel_plan()
+        x = wave_mono_16k
+        if not x.is_cuda:
+            raise RuntimeError("wave2feature expects a CUDA tensor (no CPU fallback); use wav2feature for files")
+        x = x.contiguous().float()
+        n = x.numel()
+        T = _lib.lib().hft_logmel_num_frames(n)
+        out = torch.empty((T, self.config['feature']['mel_bins']), device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hft_logmel_f32(plan.ptr, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(out.data_ptr()), T,
+                                                 ctypes.c_void_p(stream)), "hft_logmel_f32")
+        return out
+
+    def waves2features(self, waves):
+        """Ragged batch in one launch (the file loop of conv_wav2fe.py:41-48): list of CUDA [N_i] -> list of [T_i,256]."""
+        plan = self._logmel_plan()
+        if len(waves) == 0:
+            return []
+        dev = waves[0].device
+        lens = [int(w.numel()) for w in waves]
+        starts, pos = [], 0
+        for n in lens:                       # clip starts padded to 4 samples: every clip stays TMA-eligible
+            starts.append(pos)
+            pos += (n + 3) // 4 * 4
+        flat = torch.zeros(max(pos, 1), device=dev, dtype=torch.float32)
+        for w, s, n in zip(waves, starts, lens):
+            flat[s:s + n] = w.reshape(-1).float()
+        Ts = [int(_lib.lib().hft_logmel_num_frames(n)) for n in lens]
+        out = torch.empty((sum(Ts), self.config['feature']['mel_bins']), device=dev, dtype=torch.float32)
+        c_start = (ctypes.c_int64 * len(lens))(*starts)
+        c_len = (ctypes.c_int64 * len(lens))(*lens)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().hft_logmel_batch_f32(plan.ptr, ctypes.c_void_p(flat.data_ptr()), c_start, c_len, len(lens),
+                                                       ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)), "hft_logmel_batch_f32")
+        outs, r = [], 0
+        for T in Ts:
+            outs.append(out[r:r + T])
+            r += T
+        return outs
+
+    def wav2feature(self, f_wav):
+        """amt.py:34-63: wav file -> CPU FloatTensor [T, mel_bins] = log(mel + log_offset).T"""
+        wave, sr = _read_wav(f_wav)
+        wave_mono = torch.mean(wave, dim=0)
+        if sr != self.config['feature']['sr']:
+            raise NotImplementedError("resampling %d -> %d Hz (amt.py:57-58) is not on the B200 hot path yet; "
+                                      "feed %d Hz audio" % (sr, self.config['feature']['sr'], self.config['feature']['sr']))
+        plan = self._logmel_plan()
+        x = wave_mono.contiguous().float()
+        n = x.numel()
+        T = _lib.lib().hft_logmel_num_frames(n)
+        out = torch.empty((T, self.config['feature']['mel_bins']), dtype=torch.float32)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().hft_logmel_host_f32(plan.ptr, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(out.data_ptr()), T,
+                                                  ctypes.c_void_p(stream)), "hft_logmel_host_f32")
+        return out
+
+    # ---- transcription -----------------------------------------------------------------------------------
+    def _run_windows(self, a_input, n_win, hop, n_offset, n_keep, n_out_rows, mode, ablation_flag):
+        """Run the model over windows [i*hop, i*hop+W) of the padded device feature and keep rows
+        [n_offset, n_offset+n_keep) of every window's outputs (amt.py:88-113 / :146-171)."""
+        if self.model is None:
+            raise RuntimeError("AMT was constructed without a model")
+        if mode != 'combination' or ablation_flag:
+            raise NotImplementedError("only mode='combination' of Model_SPEC2MIDI is on the B200 hot path")
+        cfg = self.config
+        n_note, n_bin = cfg['midi']['num_note'], cfg['feature']['n_bins']
+        W = cfg['input']['margin_b'] + cfg['input']['num_frame'] + cfg['input']['margin_f']
+        F = cfg['input']['num_frame']
+        dev = a_input.device
+        chunk = int(self.batch_size) if (self.batch_size is not None and int(self.batch_size) > 1) else 16
+        self.model.eval()
+        res_f = [np.zeros((n_out_rows, n_note), dtype=np.float32) for _ in range(6)]
+        res_v = [np.zeros((n_out_rows, n_note), dtype=np.int8) for _ in range(2)]
+        spec_all = torch.as_strided(a_input, (n_win, n_bin, W), (hop * n_bin, 1, n_bin))
+        nb = min(chunk, n_win)
+        V = cfg['midi']['num_velocity']
+        opt = dict(device=dev, dtype=torch.float32)
+        bufs = [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [torch.empty((nb, F, n_note, V), **opt), None] + \
+               [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [torch.empty((nb, F, n_note, V), **opt)]
+        with torch.no_grad():
+            for w0 in range(0, n_win, chunk):
+                b = min(chunk, n_win - w0)
+                outs = [t[:b] if t is not None else None for t in bufs]
+                self.model.forward_into(spec_all[w0:w0 + b], outs, want_attention=False)
+                sl = slice(n_offset, n_offset + n_keep)
+                host = [outs[i][:, sl].reshape(b * n_keep, n_note).cpu().numpy() for i in (0, 1, 2, 5, 6, 7)]
+                vel = [outs[i][:, sl].argmax(3).reshape(b * n_keep, n_note).to(torch.int8).cpu().numpy() for i in (3, 8)]
+                r0 = w0 * n_keep
+                for dst, src in zip(res_f, host):
+                    dst[r0:r0 + b * n_keep] = src[:max(0, min(b * n_keep, n_out_rows - r0))]
+                for dst, src in zip(res_v, vel):
+                    dst[r0:r0 + b * n_keep] = src[:max(0, min(b * n_keep, n_out_rows - r0))]
+        return res_f[0], res_f[1], res_f[2], res_v[0], res_f[3], res_f[4], res_f[5], res_v[1]
+
+    def _to_device_feature(self, a_feature):
+        if isinstance(a_feature, torch.Tensor):
+            t = a_feature.detach().float()
+        else:
+            t = torch.from_numpy(np.array(a_feature, dtype=np.float32))
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the B200 path has no CPU fallback")
+        return t.to(self.device)
+
+    def transcript(self, a_feature, mode='combination', ablation_flag=False):
+        """amt.py:66-118.  a_feature: [num_frame, n_mels] -> 8 numpy arrays [T+len_s, num_note]."""
+        cfg = self.config
+        feat = self._to_device_feature(a_feature)
+        T, F = feat.shape[0], cfg['input']['num_frame']
+        mb, mf = cfg['input']['margin_b'], cfg['input']['margin_f']
+        len_s = int(np.ceil(T / F) * F) - T
+        a_input = torch.full((mb + T + len_s + mf, cfg['feature']['n_bins']), float(cfg['input']['min_value']), device=feat.device,
+                             dtype=torch.float32)
+        a_input[mb:mb + T] = feat
+        n_win = (T + F - 1) // F
+        return self._run_windows(a_input, n_win, F, 0, F, T + len_s, mode, ablation_flag)
+
+    def transcript_stride(self, a_feature, n_offset, mode='combination', ablation_flag=False):
+        """amt.py:121-176: half-frame stride, keeps rows [n_offset, n_offset+64) of every window."""
+        cfg = self.config
+        feat = self._to_device_feature(a_feature)
+        T, F = feat.shape[0], cfg['input']['num_frame']
+        mb, mf = cfg['input']['margin_b'], cfg['input']['margin_f']
+        half = int(F / 2)
+        tmp_len = T + mb + mf + half
+        len_s = int(np.ceil(tmp_len / half) * half) - tmp_len
+        rows = (mb + n_offset) + T + (len_s + mf + (half - n_offset))
+        a_input = torch.full((rows, cfg['feature']['n_bins']), float(cfg['input']['min_value']), device=feat.device, dtype=torch.float32)
+        a_input[mb + n_offset: mb + n_offset + T] = feat
+        n_win = (T + half - 1) // half
+        return self._run_windows(a_input, n_win, half, n_offset, half, T + len_s, mode, ablation_flag)
+
+    # ---- note decoding (host, amt.py:179-344) ---------------------------------------------------------------
+    def mpe2note(self, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, thred_onset=0.5, thred_offset=0.5, thred_mpe=0.5,
+                 mode_velocity='ignore_zero', mode_offset='shorter'):
+        from .notes import mpe2note as _mpe2note
+        return _mpe2note(self.config, a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe, mode_velocity,
+                         mode_offset)
+
+    def note2midi(self, a_note, f_midi):
+        """amt.py:347-355 (file output; needs pretty_midi like the reference)."""
+        import pretty_midi
+        midi = pretty_midi.PrettyMIDI()
+        instrument = pretty_midi.Instrument(program=0)
+        for note in a_note:
+            instrument.notes.append(pretty_midi.Note(velocity=note['velocity'], pitch=note['pitch'], start=note['onset'], end=note['offset']))
+        midi.instruments.append(instrument)
+        midi.write(f_midi)
+        return

@@ -1,0 +1,107 @@
+// Per-lane building blocks of the fused log-mel kernel (frames -> Hann -> 2048-point real FFT ->
+// |X|^2 -> banded mel sums -> log).  Replaces torchaudio MelSpectrogram + log in AMT.wav2feature
+// (reference hftt_code/model/amt.py:59-61).
+//
+// One warp owns one frame.  The 2048-point real FFT is a 1024-point complex FFT of z[n] = x[2n] + i x[2n+1]
+// done as 32 x 32 (four-step): every lane runs a 32-point FFT in registers, multiplies by W_1024^{n1 k2},
+// the warp transposes through shared memory, every lane runs a second 32-point FFT, and the real-input
+// spectrum is untangled pairwise (k, 1024-k).
+//
+// Every function takes the lane index explicitly and is __host__ __device__, so that the index arithmetic is
+// verified on the CPU by running the 32 lanes one after another (tools/logmel_hostsim.cpp).
+#pragma once
+#include <stdint.h>
+#ifdef __CUDACC__
+#define HFT_HD __host__ __device__ __forceinline__
+#else
+#define HFT_HD inline
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+#include "fft32_gen.cuh"
+
+namespace hft {
+
+constexpr int kNfft = 2048;
+constexpr int kHop = 256;
+constexpr int kNmels = 256;
+constexpr int kNfreq = 1025;
+constexpr int kTStride = 33;          // float2 row stride of the 32x32 transpose tile (conflict-free)
+constexpr int kMaxMelW = 2048;        // packed band weights (2 036 for the reference's filterbank)
+
+// melinfo[m] = start | len << 11 | offset << 16     (start < 2048, len < 32, offset < 65536)
+HFT_HD uint32_t mel_pack(int start, int len, int off) { return (uint32_t)start | ((uint32_t)len << 11) | ((uint32_t)off << 16); }
+
+// Step 1+2+3: lane n1.  xs = this frame's 2048 samples (8-byte aligned), win = Hann[2048],
+// tw2[k2*32 + n1] = W_1024^{n1 k2}.  Writes T[k2*kTStride + n1].
+HFT_HD void lm_rows(int lane, const float* xs, const float* win, const float2* tw2, float2* T) {
+  float2 v[32];
+  const float2* x2 = reinterpret_cast<const float2*>(xs);
+  const float2* w2 = reinterpret_cast<const float2*>(win);
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) {
+    float2 a = x2[lane + 32 * n2], w = w2[lane + 32 * n2];
+    v[n2] = make_float2(a.x * w.x, a.y * w.y);
+  }
+  hft_fft32(v);
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) {
+    float2 y = v[HFT_BITREV5(k2)], w = tw2[k2 * 32 + lane];
+    T[k2 * kTStride + lane] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+  }
+}
+
+// Step 4a: lane k2 reads its row of the transposed tile and transforms it (result stays in registers).
+HFT_HD void lm_cols_load(int lane, const float2* T, float2 (&u)[32]) {
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) u[n1] = T[lane * kTStride + n1];
+  hft_fft32(u);
+}
+
+// Step 4b: Z[k2 + 32 k1] in natural order.
+HFT_HD void lm_cols_store(int lane, const float2 (&u)[32], float2* Z) {
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) Z[lane + 32 * k1] = u[HFT_BITREV5(k1)];
+}
+
+// Step 5: real-input untangle + power.  twr[k] = exp(-2 pi i k / 2048), k = 0..512.
+// P[k] = |X[k]|^2 for k = 0..1024.
+HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    int k = 1 + lane + 32 * j;                       // 1..512
+    float2 zk = Z[k], zn = Z[1024 - k], w = twr[k];
+    float ar = zk.x + zn.x, ai = zk.y - zn.y;        // A  = Z[k] + conj(Z[N-k])      (= 2 E[k])
+    float br = zk.x - zn.x, bi = zk.y + zn.y;        // B  = Z[k] - conj(Z[N-k])
+    float orr = bi, oi = -br;                        // O2 = B / i                    (= 2 O[k])
+    float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;   // T2 = W^k O2
+    float xr = ar + tr, xi = ai + ti, yr = ar - tr, yi = ai - ti;
+    P[k] = 0.25f * (xr * xr + xi * xi);
+    P[1024 - k] = 0.25f * (yr * yr + yi * yi);
+  }
+  if (lane == 0) {
+    float2 z0 = Z[0];
+    float s = z0.x + z0.y, d = z0.x - z0.y;
+    P[0] = s * s;
+    P[1024] = d * d;
+  }
+}
+
+// Step 6+7: banded mel sums and log.  Lane handles mel bins lane + 32 j.
+HFT_HD void lm_mel(int lane, const float* P, const float* melw, const uint32_t* melinfo, float log_offset, float* out_row) {
+#pragma unroll
+  for (int j = 0; j < kNmels / 32; ++j) {
+    int m = lane + 32 * j;
+    uint32_t info = melinfo[m];
+    int start = info & 2047, len = (info >> 11) & 31, off = info >> 16;
+    float acc = 0.f;
+    for (int i = 0; i < len; ++i) acc += P[start + i] * melw[off + i];
+#ifdef __CUDA_ARCH__
+    out_row[m] = logf(acc + log_offset);
+#else
+    out_row[m] = ::logf(acc + log_offset);
+#endif
+  }
+}
+
+}  // namespace hft

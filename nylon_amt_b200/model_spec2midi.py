@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference's hftt_code/model/model_spec2midi.py for the forward hot path.
+
+Same class names, constructor arguments, attribute names and state_dict schema as the reference
+(Model_SPEC2MIDI :9, Encoder_SPEC2MIDI :41, Decoder_SPEC2MIDI :112, EncoderLayer :222, DecoderLayer_Zero :247,
+DecoderLayer :274, MultiHeadAttentionLayer :308, PositionwiseFeedforwardLayer :362), so that
+`load_state_dict(checkpoint['model_dict'])` (hftt_code/training/m_training.py:275) and modules pickled by the
+reference (hftt_code/model/amt.py:24-25, after nylon_amt_b200.install_reference_aliases()) keep working.
+
+The sub-modules only hold parameters.  `Model_SPEC2MIDI.forward` does not run PyTorch ops: it hands the
+parameters and the input to libhft_sm100.so (hand-written sm_100a CUDA behind the C ABI in include/hft_sm100.h).
+There is no CPU path and no eager fallback: parameters or inputs that are not on a CUDA device raise.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class MultiHeadAttentionLayer(nn.Module):
+    """Parameter container of model_spec2midi.py:308-320 (fc_q / fc_k / fc_v / fc_o)."""
+
+    def __init__(self, hid_dim, n_heads, dropout, device):
+        super().__init__()
+        assert hid_dim % n_heads == 0
+        self.hid_dim = hid_dim
+        self.n_heads = n_heads
+        self.head_dim = hid_dim // n_heads
+        self.fc_q = nn.Linear(hid_dim, hid_dim)
+        self.fc_k = nn.Linear(hid_dim, hid_dim)
+        self.fc_v = nn.Linear(hid_dim, hid_dim)
+        self.fc_o = nn.Linear(hid_dim, hid_dim)
+        self.dropout = nn.Dropout(dropout)
+
+
+class PositionwiseFeedforwardLayer(nn.Module):
+    """Parameter container of model_spec2midi.py:362-367 (fc_1 / fc_2)."""
+
+    def __init__(self, hid_dim, pf_dim, dropout):
+        super().__init__()
+        self.fc_1 = nn.Linear(hid_dim, pf_dim)
+        self.fc_2 = nn.Linear(pf_dim, hid_dim)
+        self.dropout = nn.Dropout(dropout)
+
+
+class EncoderLayer(nn.Module):
+    """model_spec2midi.py:222-228: one LayerNorm shared by both residual sites."""
+
+    def __init__(self, hid_dim, n_heads, pf_dim, dropout, device):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(hid_dim)
+        self.self_attention = MultiHeadAttentionLayer(hid_dim, n_heads, dropout, device)
+        self.positionwise_feedforward = PositionwiseFeedforwardLayer(hid_dim, pf_dim, dropout)
+        self.dropout = nn.Dropout(dropout)
+
+
+class DecoderLayer_Zero(nn.Module):
+    """model_spec2midi.py:247-253: cross-attention + FFN, no self-attention."""
+
+    def __init__(self, hid_dim, n_heads, pf_dim, dropout, device):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(hid_dim)
+        self.encoder_attention = MultiHeadAttentionLayer(hid_dim, n_heads, dropout, device)
+        self.positionwise_feedforward = PositionwiseFeedforwardLayer(hid_dim, pf_dim, dropout)
+        self.dropout = nn.Dropout(dropout)
+
+
+class DecoderLayer(nn.Module):
+    """model_spec2midi.py:274-281: self-attention, cross-attention, FFN; one LayerNorm for the three sites."""
+
+    def __init__(self, hid_dim, n_heads, pf_dim, dropout, device):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(hid_dim)
+        self.self_attention = MultiHeadAttentionLayer(hid_dim, n_heads, dropout, device)
+        self.encoder_attention = MultiHeadAttentionLayer(hid_dim, n_heads, dropout, device)
+        self.positionwise_feedforward = PositionwiseFeedforwardLayer(hid_dim, pf_dim, dropout)
+        self.dropout = nn.Dropout(dropout)
+
+
+class Encoder_SPEC2MIDI(nn.Module):
+    """Same constructor as model_spec2midi.py:42; parameters conv / tok_embedding_freq / pos_embedding_freq / layers_freq."""
+
+    def __init__(self, n_margin, n_frame, n_bin, cnn_channel, cnn_kernel, hid_dim, n_layers, n_heads, pf_dim, dropout, device):
+        super().__init__()
+        self.device = device
+        self.n_frame = n_frame
+        self.n_bin = n_bin
+        self.cnn_channel = cnn_channel
+        self.cnn_kernel = cnn_kernel
+        self.hid_dim = hid_dim
+        self.conv = nn.Conv2d(1, self.cnn_channel, kernel_size=(1, self.cnn_kernel))
+        self.n_proc = n_margin * 2 + 1
+        self.cnn_dim = self.cnn_channel * (self.n_proc - (self.cnn_kernel - 1))
+        self.tok_embedding_freq = nn.Linear(self.cnn_dim, hid_dim)
+        self.pos_embedding_freq = nn.Embedding(n_bin, hid_dim)
+        self.layers_freq = nn.ModuleList([EncoderLayer(hid_dim, n_heads, pf_dim, dropout, device) for _ in range(n_layers)])
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, spec_in):
+        raise NotImplementedError("the B200 path fuses encoder and decoder; call Model_SPEC2MIDI.forward")
+
+
+class Decoder_SPEC2MIDI(nn.Module):
+    """Same constructor as model_spec2midi.py:113."""
+
+    def __init__(self, n_frame, n_bin, n_note, n_velocity, hid_dim, n_layers, n_heads, pf_dim, dropout, device):
+        super().__init__()
+        self.device = device
+        self.n_note = n_note
+        self.n_frame = n_frame
+        self.n_velocity = n_velocity
+        self.n_bin = n_bin
+        self.hid_dim = hid_dim
+        self.sigmoid = nn.Sigmoid()
+        self.dropout = nn.Dropout(dropout)
+        self.pos_embedding_freq = nn.Embedding(n_note, hid_dim)
+        self.layer_zero_freq = DecoderLayer_Zero(hid_dim, n_heads, pf_dim, dropout, device)
+        self.layers_freq = nn.ModuleList([DecoderLayer(hid_dim, n_heads, pf_dim, dropout, device) for _ in range(n_layers - 1)])
+        self.fc_onset_freq = nn.Linear(hid_dim, 1)
+        self.fc_offset_freq = nn.Linear(hid_dim, 1)
+        self.fc_mpe_freq = nn.Linear(hid_dim, 1)
+        self.fc_velocity_freq = nn.Linear(hid_dim, self.n_velocity)
+        self.pos_embedding_time = nn.Embedding(n_frame, hid_dim)
+        self.layers_time = nn.ModuleList([EncoderLayer(hid_dim, n_heads, pf_dim, dropout, device) for _ in range(n_layers)])
+        self.fc_onset_time = nn.Linear(hid_dim, 1)
+        self.fc_offset_time = nn.Linear(hid_dim, 1)
+        self.fc_mpe_time = nn.Linear(hid_dim, 1)
+        self.fc_velocity_time = nn.Linear(hid_dim, self.n_velocity)
+
+    def forward(self, enc_spec):
+        raise NotImplementedError("the B200 path fuses encoder and decoder; call Model_SPEC2MIDI.forward")
+
+
+class _Handle:
+    """Owns the hft_model handle of one module instance (freed with the module)."""
+
+    def __init__(self, dims):
+        self.ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().hft_model_create(ctypes.byref(self.ptr), ctypes.byref(dims)), "hft_model_create")
+        n = _lib.lib().hft_model_num_weights(self.ptr)
+        self.names = [_lib.lib().hft_model_weight_name(self.ptr, i).decode() for i in range(n)]
+        self.numel = [_lib.lib().hft_model_weight_numel(self.ptr, i) for i in range(n)]
+        self.stamp = None
+        self.max_batch = None
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().hft_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Model_SPEC2MIDI(nn.Module):
+    """Model_SPEC2MIDI(encoder, decoder).forward(input_spec[B,256,192]) -> the 9-tuple of model_spec2midi.py:35."""
+
+    precision = "fp32"      # 'fp32' (CUDA-core fp32), 'bf16' / 'fp16' (tcgen05 tensor cores)
+    max_batch = 8           # segments processed per internal pass (bounds the workspace)
+
+    def __init__(self, encoder, decoder):
+        super().__init__()
+        self.encoder_spec2midi = encoder
+        self.decoder_spec2midi = decoder
+
+    # ---- handle / weights ---------------------------------------------------------------------------------
+    def _dims(self):
+        e, d = self.encoder_spec2midi, self.decoder_spec2midi
+        sa = e.layers_freq[0].self_attention
+        dims = _lib.hft_dims()
+        dims.n_margin = (e.n_proc - 1) // 2
+        dims.n_frame, dims.n_bin = e.n_frame, e.n_bin
+        dims.cnn_channel, dims.cnn_kernel = e.cnn_channel, e.cnn_kernel
+        dims.hid_dim = e.hid_dim
+        dims.pf_dim = e.layers_freq[0].positionwise_feedforward.fc_1.out_features
+        dims.n_enc_layers = len(e.layers_freq)
+        dims.n_dec_layers = len(d.layers_time)
+        dims.n_heads = sa.n_heads
+        dims.n_note, dims.n_velocity = d.n_note, d.n_velocity
+        if d.layer_zero_freq.encoder_attention.n_heads != sa.n_heads:
+            raise RuntimeError("encoder and decoder head counts differ; unsupported by libhft_sm100")
+        return dims
+
+    def _handle(self):
+        h = self.__dict__.get("_hft")
+        if h is None:
+            h = _Handle(self._dims())
+            self.__dict__["_hft"] = h
+        return h
+
+    def sync_weights(self, force=False):
+        """(Re-)register the parameters with the library when they changed (load_state_dict, optimizer step, .to())."""
+        h = self._handle()
+        sd = dict(self.named_parameters())
+        tensors = []
+        for name, numel in zip(h.names, h.numel):
+            if name not in sd:
+                raise RuntimeError("parameter %s missing from the module (schema mismatch)" % name)
+            p = sd[name]
+            if p.numel() != numel:
+                raise RuntimeError("parameter %s has %d elements, expected %d" % (name, p.numel(), numel))
+            if not p.is_cuda:
+                raise RuntimeError("parameter %s is on %s: the B200 path has no CPU fallback, move the model to cuda" % (name, p.device))
+            tensors.append(p.detach())
+        stamp = tuple((t.data_ptr(), t._version) for t in tensors)
+        if force or stamp != h.stamp:
+            keep = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in tensors]
+            arr = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+            stream = torch.cuda.current_stream(keep[0].device).cuda_stream
+            with torch.cuda.device(keep[0].device):
+                _lib.check(_lib.lib().hft_model_set_weights(h.ptr, arr, len(keep), ctypes.c_void_p(stream)), "hft_model_set_weights")
+            h.stamp = stamp
+        return h
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def forward(self, input_spec):
+        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules()):
+            raise NotImplementedError("training-mode forward (dropout) is not on the B200 hot path yet; call model.eval()")
+        if not input_spec.is_cuda:
+            raise RuntimeError("input_spec is on %s: the B200 path has no CPU fallback" % input_spec.device)
+        e, d = self.encoder_spec2midi, self.decoder_spec2midi
+        x = input_spec if input_spec.dtype == torch.float32 else input_spec.float()
+        if x.dim() != 3 or x.shape[1] != e.n_bin or x.shape[2] != e.n_frame + e.n_proc - 1:
+            raise RuntimeError("input_spec must be [B, %d, %d], got %s" % (e.n_bin, e.n_frame + e.n_proc - 1, tuple(x.shape)))
+        h = self.sync_weights()
+        if h.max_batch != self.max_batch:
+            _lib.check(_lib.lib().hft_model_set_max_batch(h.ptr, int(self.max_batch)), "hft_model_set_max_batch")
+            h.max_batch = self.max_batch
+        B, F, N, V = x.shape[0], e.n_frame, d.n_note, d.n_velocity
+        heads = e.layers_freq[0].self_attention.n_heads
+        dev = x.device
+        opt = dict(device=dev, dtype=torch.float32)
+        outs = [torch.empty((B, F, N), **opt), torch.empty((B, F, N), **opt), torch.empty((B, F, N), **opt),
+                torch.empty((B, F, N, V), **opt), torch.empty((B, F, heads, N, e.n_bin), **opt),
+                torch.empty((B, F, N), **opt), torch.empty((B, F, N), **opt), torch.empty((B, F, N), **opt),
+                torch.empty((B, F, N, V), **opt)]
+        o = _lib.hft_outputs(*[ctypes.c_void_p(t.data_ptr()) for t in outs])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().hft_forward(h.ptr, _lib.PREC[self.precision], ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1),
+                                              x.stride(2), B, ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward")
+        return tuple(outs)
+
+    def forward_into(self, input_spec, outs, want_attention=True):
+        """Same computation writing into caller-owned output tensors (no allocation on the hot path)."""
+        h = self.sync_weights()
+        if h.max_batch != self.max_batch:
+            _lib.check(_lib.lib().hft_model_set_max_batch(h.ptr, int(self.max_batch)), "hft_model_set_max_batch")
+            h.max_batch = self.max_batch
+        x = input_spec
+        ptrs = [ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(None) for t in outs]
+        if not want_attention:
+            ptrs[4] = ctypes.c_void_p(None)
+        o = _lib.hft_outputs(*ptrs)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hft_forward(h.ptr, _lib.PREC[self.precision], ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1),
+                                              x.stride(2), x.shape[0], ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward")
+        return outs
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_hft", None)          # the device handle is rebuilt lazily after unpickling
+        return st
