@@ -142,10 +142,10 @@ static int derive_weights(Model* m, cudaStream_t s) {
   size_t n_self = m->enc.size() + m->tim.size() + m->dec.size();
   size_t n_cross = 1 + m->dec.size();
   size_t floats = (size_t)H * m->nproc + H + n_self * (3 * hh + 3 * H) + n_cross * (2 * hh + 2 * H) + (size_t)m->nnote * H +
-                  2 * ((size_t)(3 + V) * H + (3 + V));
+                  2 * ((size_t)(3 + V) * H + (3 + V)) + 64 * (8 + 2 * (n_self + n_cross));   // + per-slice alignment slack
   if (!m->derived_arena) HFT_CHECK_CUDA(cudaMalloc(&m->derived_arena, floats * sizeof(float)));
   float* p = m->derived_arena;
-  auto take = [&](size_t n) { float* r = p; p += n; return r; };
+  auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };   // 256-byte aligned slices
   m->front_w = take((size_t)H * m->nproc);
   m->front_b = take(H);
   int n_out = m->nproc - (m->d.cnn_kernel - 1);
