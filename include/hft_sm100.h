@@ -150,6 +150,21 @@ int64_t hft_last_launch_count(void);
 int hft_profile_enable(int on);
 int hft_profile_read(int kclass, double* ms, int64_t* launches);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Component entry points of the tensor-core path (used by the parity tests of the building blocks; a host may
+ * also call them directly).  16-bit tensors are bf16 (bf16 != 0) or fp16, row-major, device memory.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* out[M,N] = epilogue(a[M,K] * w[N,K]^T + bias).  epi: 0 store, 1 ReLU, 2 LayerNorm(x + resid)*gamma+beta (N <= 256).
+ * M % 128 == 0, K % 64 == 0, N % 64 == 0.  Replaces nn.Linear (+ReLU / +residual+LayerNorm), model_spec2midi.py:328-330,
+ * :357, :372-375, :236, :242. */
+int hft_tc_linear(int bf16, int epi, const void* a16_dev, const void* w16_dev, const float* bias_dev, int64_t M, int32_t N, int32_t K,
+                  void* out16_dev, const void* resid16_dev, const float* gamma_dev, const float* beta_dev, void* stream);
+/* Self-attention over n_seq sequences of L tokens (L in {256, 128, 88}) stored as qkv[n_seq*L, 3*heads*dh]
+ * (q | k | v): ctx[n_seq*L, heads*dh] = softmax(q k^T / sqrt(dh)) v, optional probs[n_seq, heads, L, L] fp32 (L = 256
+ * only).  Replaces MultiHeadAttentionLayer.forward :335-355. */
+int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16_dev, int64_t n_seq, int32_t L, void* ctx16_dev,
+                     float* probs_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,10 @@ SYMBOLS = {
     "hft_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int32, ctypes.POINTER(hft_outputs), ctypes.c_void_p]),
     "hft_last_launch_count": (ctypes.c_int64, []),
+    "hft_tc_linear": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                     ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_tc_attention": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "hft_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "hft_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 }

@@ -1,16 +1,535 @@
-// Tensor-core (tcgen05 / TMEM / TMA) forward of Model_SPEC2MIDI -- HFT_PREC_BF16 / HFT_PREC_F16.
+// Tensor-core forward of Model_SPEC2MIDI (reference hftt_code/model/model_spec2midi.py:15-35) -- HFT_PREC_BF16 /
+// HFT_PREC_F16: 16-bit operands on tcgen05 with fp32 accumulation in TMEM; softmax, LayerNorm, residuals, sigmoid in
+// fp32.  Activations live in HBM as 16-bit row-major [rows, H] tensors; every projection is one launch of the
+// persistent UMMA GEMM (tc_gemm.cuh) whose epilogue carries bias / ReLU / residual+LayerNorm / heads; attention is
+// tc_attn.cuh.  Host side: tensor maps are encoded once per (workspace, weights) and passed as __grid_constant__.
 #include "common.cuh"
 #include "model.h"
+#include "tc_attn.cuh"
+#include "tc_gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <map>
 
 namespace hft {
 
-int tc_prepare_weights(Model* m, cudaStream_t s) { (void)m; (void)s; return HFT_OK; }
-void tc_destroy(Model* m) { (void)m; }
+using namespace tc;
 
-int forward_tc(Model* m, int precision, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s) {
-  (void)m; (void)spec; (void)sb; (void)sbin; (void)st; (void)B; (void)o; (void)s;
-  set_error("hft_forward: precision %d (tensor-core path) is not built yet", precision);
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda) ---------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major 16-bit tensor [rows, cols] with row pitch ld (elements); box = box_cols x box_rows; swizzle = box_cols*2 bytes.
+static int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool bf16) {
+  auto enc = get_encode();
+  HFT_REQUIRE(enc != nullptr, HFT_ERR_STATE, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HFT_REQUIRE(r == CUDA_SUCCESS, HFT_ERR_STATE, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows);
+  return HFT_OK;
+}
+
+// ---- small CUDA-core kernels of the 16-bit path -----------------------------------------------------------------
+template <bool BF16>
+__global__ void cvt16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (uint16_t)(Op16<BF16>::pack(src[i], 0.f) & 0xffffu);
+}
+
+// heads weight [192, H]: rows 0..V-1 velocity, V..V+2 onset/offset/mpe, rest zero (so velocity stores are 16-byte aligned)
+template <bool BF16>
+__global__ void pack_heads_kernel(const float* __restrict__ w_on, const float* __restrict__ w_off, const float* __restrict__ w_mpe,
+                                  const float* __restrict__ w_vel, const float* __restrict__ b_on, const float* __restrict__ b_off,
+                                  const float* __restrict__ b_mpe, const float* __restrict__ b_vel, int V, int H, int rows,
+                                  uint16_t* __restrict__ w16, float* __restrict__ bias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  int r = i / H, h = i % H;
+  float v = 0.f, b = 0.f;
+  if (r < V) { v = w_vel[r * H + h]; b = b_vel[r]; }
+  else if (r == V) { v = w_on[h]; b = b_on[0]; }
+  else if (r == V + 1) { v = w_off[h]; b = b_off[0]; }
+  else if (r == V + 2) { v = w_mpe[h]; b = b_mpe[0]; }
+  w16[i] = (uint16_t)(Op16<BF16>::pack(v, 0.f) & 0xffffu);
+  if (h == 0) bias[r] = b;
+}
+
+// front: collapsed 65-tap filter per hidden unit, fp32 FMA, 16-bit store.  grid (n_bin, B).
+template <bool BF16, int NPROC>
+__global__ void __launch_bounds__(256) front16_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st,
+                                                      const float* __restrict__ Wc, const float* __restrict__ bc, const float* __restrict__ pos,
+                                                      float scale, int H, int F, int NB, uint16_t* __restrict__ X) {
+  __shared__ float s_row[256];
+  const int bin = blockIdx.x, b = blockIdx.y;
+  const int W = F + NPROC - 1;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) s_row[i] = spec[b * sb + bin * sbin + i * st];
+  __syncthreads();
+  const int groups = blockDim.x / H;
+  const int h = threadIdx.x % H, g = threadIdx.x / H;
+  if (g >= groups) return;
+  float w[NPROC];
+#pragma unroll
+  for (int j = 0; j < NPROC; ++j) w[j] = Wc[h * NPROC + j];
+  const float bias = bc[h], pe = pos[bin * H + h];
+  const int fpg = F / groups;
+  for (int f0 = g * fpg; f0 < (g + 1) * fpg; f0 += 8) {
+    float acc[8], sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = 0.f; sv[i] = s_row[f0 + i]; }
+#pragma unroll
+    for (int j = 0; j < NPROC; ++j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[j], sv[i], acc[i]);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) sv[i] = sv[i + 1];
+      sv[7] = (j + 1 < NPROC) ? s_row[f0 + j + 8] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      X[(((long long)b * F + f0 + i) * NB + bin) * H + h] = (uint16_t)(Op16<BF16>::pack((acc[i] + bias) * scale + pe, 0.f) & 0xffffu);
+  }
+}
+
+// U[((b*NN+n)*F+f)*H+h] = T[((b*F+f)*NN+n)*H+h] * sqrt(H) + pos_time[f*H+h]   (model_spec2midi.py:189-191); 8 elements / thread
+template <bool BF16>
+__global__ void time_relayout16_kernel(const uint16_t* __restrict__ T, const float* __restrict__ pos, float scale, int F, int NN, int H,
+                                       long long total8, uint16_t* __restrict__ U) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int h8 = H / 8;
+  int hq = (int)(i % h8);
+  long long r = i / h8;
+  int f = (int)(r % F);
+  long long bn = r / F;
+  int n = (int)(bn % NN);
+  long long b = bn / NN;
+  uint4 q = *reinterpret_cast<const uint4*>(T + (((b * F + f) * NN + n)) * H + hq * 8);
+  const float* pp = pos + f * H + hq * 8;
+  uint32_t w4[4] = {q.x, q.y, q.z, q.w}, o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    o[e] = Op16<BF16>::pack(Op16<BF16>::lo(w4[e]) * scale + pp[2 * e], Op16<BF16>::hi(w4[e]) * scale + pp[2 * e + 1]);
+  *reinterpret_cast<uint4*>(U + r * H + hq * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ---- per-dtype state ------------------------------------------------------------------------------------------
+struct W16 {            // one weight matrix [N, K] in 16-bit + its tensor map (box = 64 x n_tile)
+  uint16_t* ptr = nullptr;
+  int N = 0, K = 0, n_tile = 0;
+  CUtensorMap map;
+  const float* bias = nullptr;
+};
+
+struct TcLayer { W16 qkv, o, w1, w2; };                    // EncoderLayer
+struct TcDecLayer { W16 sa_qkv, sa_o, ca_q, ca_kv, ca_o, w1, w2; };
+
+struct TcState {
+  bool bf16 = true;
+  bool weights_ready = false;
+  uint16_t* warena = nullptr;
+  float* head_bias = nullptr;       // [2][192]
+  uint16_t* q0_16 = nullptr;        // [128, H] projected pitch queries (rows >= n_note zero)
+  std::vector<TcLayer> enc, tim;
+  TcDecLayer dec0;
+  std::vector<TcDecLayer> dec;
+  W16 headA, headB;
+  // workspace
+  int ws_batch = 0;
+  uint16_t* ws = nullptr;
+  uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
+  CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands, box 64 x 128
+  CUtensorMap mQKV_q, mQKV_kv, mDQ_q, mDQ_kv, mQ0;  // attention operands, box dh x {128, Lk}
+};
+
+struct TcBoth { TcState st[2]; };   // [0] = fp16, [1] = bf16
+
+static int n_tile_for(int N) {
+  const int cands[4] = {256, 192, 128, 64};
+  for (int c : cands)
+    if (N % c == 0) return c;
+  return 0;
+}
+
+template <bool BF16>
+static void cvt(const float* src, uint16_t* dst, long long n, cudaStream_t s) {
+  cvt16_kernel<BF16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+}
+
+static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
+  const int H = m->H, P = m->P, V = m->nvel;
+  const long long hh = (long long)H * H, hp = (long long)H * P;
+  const bool bf = t.bf16;
+  size_t n_self = m->enc.size() + m->tim.size() + m->dec.size();
+  size_t n_dec_layers = 1 + m->dec.size();
+  size_t elems = n_self * (3 * hh + hh) + (m->enc.size() + m->tim.size() + n_dec_layers) * 2 * hp + n_dec_layers * (hh + 2 * hh + hh) +
+                 2 * (size_t)192 * H + (size_t)128 * H + 4096;
+  if (!t.warena) {
+    HFT_CHECK_CUDA(cudaMalloc(&t.warena, elems * 2));
+    HFT_CHECK_CUDA(cudaMalloc(&t.head_bias, 2 * 192 * sizeof(float)));
+  }
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.warena, 0, elems * 2, s));
+  uint16_t* p = t.warena;
+  auto take = [&](size_t n) { uint16_t* r = p; p += (n + 127) & ~(size_t)127; return r; };
+  int rc = HFT_OK;
+  auto mk = [&](W16& w, const float* src, int N, int K, const float* bias) {
+    w.ptr = take((size_t)N * K);
+    w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
+    if (bf) cvt<true>(src, w.ptr, (long long)N * K, s); else cvt<false>(src, w.ptr, (long long)N * K, s);
+    int r = make_map(&w.map, w.ptr, N, K, K, kBlockK, w.n_tile, bf);
+    if (r != HFT_OK) rc = r;
+  };
+  auto mk_enc = [&](TcLayer& L, const EncLayerW& lw, const FusedAttn& f) {
+    mk(L.qkv, f.qkv_w, 3 * H, H, f.qkv_b);
+    mk(L.o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b]);
+    mk(L.w1, m->w[lw.ff.w1], P, H, m->w[lw.ff.b1]);
+    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2]);
+  };
+  t.enc.resize(m->enc.size()); t.tim.resize(m->tim.size()); t.dec.resize(m->dec.size());
+  for (size_t i = 0; i < m->enc.size(); ++i) mk_enc(t.enc[i], m->enc[i], m->enc_qkv[i]);
+  for (size_t i = 0; i < m->tim.size(); ++i) mk_enc(t.tim[i], m->tim[i], m->tim_qkv[i]);
+  auto mk_dec = [&](TcDecLayer& L, const DecLayerW& lw, const FusedAttn* sa, const FusedAttn& kv) {
+    if (sa) {
+      mk(L.sa_qkv, sa->qkv_w, 3 * H, H, sa->qkv_b);
+      mk(L.sa_o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b]);
+    }
+    mk(L.ca_q, m->w[lw.ca.q_w], H, H, m->w[lw.ca.q_b]);
+    mk(L.ca_kv, kv.qkv_w, 2 * H, H, kv.qkv_b);
+    mk(L.ca_o, m->w[lw.ca.o_w], H, H, m->w[lw.ca.o_b]);
+    mk(L.w1, m->w[lw.ff.w1], P, H, m->w[lw.ff.b1]);
+    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2]);
+  };
+  mk_dec(t.dec0, m->dec0, nullptr, m->dec_ca_kv[0]);
+  for (size_t i = 0; i < m->dec.size(); ++i) mk_dec(t.dec[i], m->dec[i], &m->dec_sa_qkv[i], m->dec_ca_kv[i + 1]);
+  // heads: packed + reordered
+  auto mk_heads = [&](W16& w, const int* idx, int which) -> int {
+    w.ptr = take((size_t)192 * H);
+    w.N = 192; w.K = H; w.n_tile = 192; w.bias = t.head_bias + which * 192;
+    HFT_CHECK_CUDA(cudaMemsetAsync(t.head_bias + which * 192, 0, 192 * sizeof(float), s));
+    if (bf) pack_heads_kernel<true><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, w.ptr, t.head_bias + which * 192);
+    else pack_heads_kernel<false><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, w.ptr, t.head_bias + which * 192);
+    int r = make_map(&w.map, w.ptr, 192, H, H, kBlockK, 192, bf);
+    if (r != HFT_OK) rc = r;
+    return (int)HFT_OK;
+  };
+  HFT_REQUIRE(V + 3 <= 192 && V % 32 == 0, HFT_ERR_UNSUPPORTED, "heads packing expects n_velocity %% 32 == 0 and <= 189");
+  mk_heads(t.headA, m->head_freq, 0);
+  mk_heads(t.headB, m->head_time, 1);
+  // projected pitch queries of layer zero, zero padded to 128 rows
+  t.q0_16 = take((size_t)128 * H);
+  if (bf) cvt<true>(m->q0, t.q0_16, (long long)m->nnote * H, s); else cvt<false>(m->q0, t.q0_16, (long long)m->nnote * H, s);
+  HFT_CHECK_CUDA(cudaGetLastError());
+  if (rc != HFT_OK) return rc;
+  t.weights_ready = true;
+  return HFT_OK;
+}
+
+static int ensure_ws(Model* m, TcState& t, int B) {
+  if (t.ws && t.ws_batch >= B) return HFT_OK;
+  cudaFree(t.ws);
+  t.ws = nullptr;
+  const long long Re = (long long)B * m->nframe * m->nbin, Rd = (long long)B * m->nframe * m->nnote;
+  const int H = m->H, P = m->P, dh = m->dh;
+  size_t elems = (size_t)Re * (5 * H + P) + (size_t)Rd * 5 * H + 4096;
+  HFT_CHECK_CUDA(cudaMalloc(&t.ws, elems * 2));
+  uint16_t* p = t.ws;
+  auto take = [&](size_t n) { uint16_t* r = p; p += (n + 511) & ~(size_t)511; return r; };
+  t.X = take((size_t)Re * H); t.QKV = take((size_t)Re * 3 * H); t.CTX = take((size_t)Re * H); t.HID = take((size_t)Re * P);
+  t.T = take((size_t)Rd * H); t.DQ = take((size_t)Rd * 3 * H); t.U = take((size_t)Rd * H);
+  const bool bf = t.bf16;
+  int rc = HFT_OK;
+  auto chk = [&](int r) { if (r != HFT_OK) rc = r; };
+  chk(make_map(&t.mX, t.X, Re, H, H, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mCTX, t.CTX, Re, H, H, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mHID, t.HID, Re, P, P, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mT, t.T, Rd, H, H, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mU, t.U, Rd, H, H, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mQKV_q, t.QKV, Re, 3 * H, 3 * H, dh, 128, bf));
+  chk(make_map(&t.mQKV_kv, t.QKV, Re, 3 * H, 3 * H, dh, 256, bf));
+  chk(make_map(&t.mDQ_q, t.DQ, Rd, 3 * H, 3 * H, dh, 128, bf));
+  chk(make_map(&t.mDQ_kv, t.DQ, Rd, 3 * H, 3 * H, dh, 96, bf));
+  chk(make_map(&t.mQ0, t.q0_16, 128, H, H, dh, 128, bf));
+  if (rc != HFT_OK) return rc;
+  t.ws_batch = B;
+  return HFT_OK;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------------
+template <bool BF16, int EPI>
+static int launch_gemm_hc(int half_cols, const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& gp, int grid, size_t smem, cudaStream_t s) {
+#define HFT_GEMM_CASE(HC)                                                                                                 \
+  case HC: {                                                                                                              \
+    auto kern = gemm_kernel<BF16, EPI, HC>;                                                                               \
+    static bool attr_set = false;                                                                                         \
+    if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(256))); attr_set = true; } \
+    kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, gp);                                                                    \
+    break;                                                                                                                \
+  }
+  switch (half_cols) {
+    HFT_GEMM_CASE(32)
+    HFT_GEMM_CASE(64)
+    HFT_GEMM_CASE(96)
+    HFT_GEMM_CASE(128)
+    default:
+      set_error("tc gemm: unsupported tile width %d", half_cols * 2);
+      return HFT_ERR_UNSUPPORTED;
+  }
+#undef HFT_GEMM_CASE
+  return HFT_OK;
+}
+
+static int launch_gemm(Model* m, bool bf16, int epi, const CUtensorMap& ma, const W16& w, long long M, GemmParams gp, cudaStream_t s) {
+  HFT_REQUIRE(M % kBlockM == 0 && w.K % kBlockK == 0 && w.n_tile > 0, HFT_ERR_UNSUPPORTED, "tc gemm: M=%lld K=%d N=%d unsupported", M, w.K, w.N);
+  gp.m_tiles = (int)(M / kBlockM);
+  gp.n_tile = w.n_tile;
+  gp.n_tiles = w.N / w.n_tile;
+  gp.k_chunks = w.K / kBlockK;
+  gp.bias = w.bias;
+  if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
+  const int total = gp.m_tiles * gp.n_tiles;
+  static int sms = num_sms();
+  const int grid = total < sms ? total : sms;
+  const size_t smem = gemm_smem_bytes(w.n_tile);
+  const int hc = w.n_tile / 2;
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  int rc;
+  if (bf16) {
+    rc = epi == EPI_STORE ? launch_gemm_hc<true, EPI_STORE>(hc, ma, w.map, gp, grid, smem, s)
+       : epi == EPI_RELU  ? launch_gemm_hc<true, EPI_RELU>(hc, ma, w.map, gp, grid, smem, s)
+       : epi == EPI_LN    ? launch_gemm_hc<true, EPI_LN>(hc, ma, w.map, gp, grid, smem, s)
+                          : launch_gemm_hc<true, EPI_HEADS>(hc, ma, w.map, gp, grid, smem, s);
+  } else {
+    rc = epi == EPI_STORE ? launch_gemm_hc<false, EPI_STORE>(hc, ma, w.map, gp, grid, smem, s)
+       : epi == EPI_RELU  ? launch_gemm_hc<false, EPI_RELU>(hc, ma, w.map, gp, grid, smem, s)
+       : epi == EPI_LN    ? launch_gemm_hc<false, EPI_LN>(hc, ma, w.map, gp, grid, smem, s)
+                          : launch_gemm_hc<false, EPI_HEADS>(hc, ma, w.map, gp, grid, smem, s);
+  }
+  (void)m;
+  return rc;
+}
+
+template <bool BF16, int DH, int LK, bool PROBS>
+static int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
+  auto kern = attn_kernel<BF16, DH, LK, PROBS>;
+  static bool attr_set = false;
+  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DH, LK>::total)); attr_set = true; }
+  kern<<<(unsigned)items, 128, AttnSmem<DH, LK>::total, s>>>(mq, mk, mv, ap);
+  return HFT_OK;
+}
+
+template <bool BF16, int DH>
+static int launch_attn_dh(int LK, bool probs, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
+  if (LK == 256) return probs ? launch_attn_t<BF16, DH, 256, true>(mq, mk, mv, ap, items, s) : launch_attn_t<BF16, DH, 256, false>(mq, mk, mv, ap, items, s);
+  if (LK == 128) return launch_attn_t<BF16, DH, 128, false>(mq, mk, mv, ap, items, s);
+  if (LK == 96) return launch_attn_t<BF16, DH, 96, false>(mq, mk, mv, ap, items, s);
+  set_error("tc attention: unsupported key tile %d", LK);
   return HFT_ERR_UNSUPPORTED;
 }
 
+static int launch_attn(Model* m, bool bf16, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams ap, long long n_seq, cudaStream_t s) {
+  ap.heads = m->heads;
+  ap.q_tiles = (ap.lq + 127) / 128;
+  ap.scale_log2e = 1.4426950408889634f / sqrtf((float)m->dh);
+  const long long items = n_seq * m->heads * ap.q_tiles;
+  HFT_REQUIRE(items < (1ll << 31), HFT_ERR_UNSUPPORTED, "tc attention: too many work items");
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  const bool probs = ap.probs != nullptr;
+  if (m->dh == 64) return bf16 ? launch_attn_dh<true, 64>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 64>(LK, probs, mq, mkv, mkv, ap, items, s);
+  return bf16 ? launch_attn_dh<true, 32>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 32>(LK, probs, mq, mkv, mkv, ap, items, s);
+}
+
+#define HFT_TRY(x) do { int _rc = (x); if (_rc != HFT_OK) return _rc; } while (0)
+
+// EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
+static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, uint16_t* x, const CUtensorMap& mx, uint16_t* qkv, const CUtensorMap& mq,
+                            const CUtensorMap& mkv, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
+  const int H = m->H, P = m->P;
+  const long long R = S * L;
+  const bool bf = t.bf16;
+  GemmParams g{};
+  g.out = qkv; g.ldc = 3 * H;
+  HFT_TRY(launch_gemm(m, bf, EPI_STORE, mx, lw.qkv, R, g, s));
+  AttnParams a{};
+  a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H; a.probs = nullptr;
+  HFT_TRY(launch_attn(m, bf, LK, mq, mkv, a, S, s));
+  g = GemmParams{};
+  g.out = x; g.ldc = H; g.resid16 = x; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
+  HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.o, R, g, s));
+  g = GemmParams{};
+  g.out = t.HID; g.ldc = P;
+  HFT_TRY(launch_gemm(m, bf, EPI_RELU, mx, lw.w1, R, g, s));
+  g = GemmParams{};
+  g.out = x; g.ldc = H; g.resid16 = x; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
+  HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mHID, lw.w2, R, g, s));
+  return HFT_OK;
+}
+
+int tc_prepare_weights(Model* m, cudaStream_t s) {
+  (void)s;
+  if (m->tc) {                                    // weights changed: 16-bit copies are rebuilt lazily per dtype
+    TcBoth* b = reinterpret_cast<TcBoth*>(m->tc);
+    b->st[0].weights_ready = false;
+    b->st[1].weights_ready = false;
+  }
+  return HFT_OK;
+}
+
+void tc_destroy(Model* m) {
+  if (!m->tc) return;
+  TcBoth* b = reinterpret_cast<TcBoth*>(m->tc);
+  for (auto& t : b->st) { cudaFree(t.warena); cudaFree(t.head_bias); cudaFree(t.ws); }
+  delete b;
+  m->tc = nullptr;
+}
+
+static TcState& state_for(Model* m, int precision) {
+  if (!m->tc) {
+    TcBoth* b = new TcBoth();
+    b->st[0].bf16 = false;
+    b->st[1].bf16 = true;
+    m->tc = b;
+  }
+  return reinterpret_cast<TcBoth*>(m->tc)->st[precision == HFT_PREC_BF16 ? 1 : 0];
+}
+
+int forward_tc(Model* m, int precision, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s) {
+  if (B == 0) return HFT_OK;
+  TcState& t = state_for(m, precision);
+  const bool bf = t.bf16;
+  if (!t.weights_ready) HFT_TRY(prepare_weights(m, t, s));
+  HFT_TRY(ensure_ws(m, t, B > m->max_batch ? B : m->max_batch));
+  const int H = m->H, P = m->P, F = m->nframe, NB = m->nbin, NN = m->nnote, V = m->nvel;
+  const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
+  const float sqrtH = sqrtf((float)H);
+  HFT_REQUIRE(m->nproc == 65, HFT_ERR_UNSUPPORTED, "front kernel is built for n_margin 32");
+  {
+    LaunchScope ls(HFT_KCLASS_FRONT, s);
+    if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.X);
+    else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.X);
+  }
+  for (size_t l = 0; l < m->enc.size(); ++l)
+    HFT_TRY(encoder_layer_tc(m, t, s, t.X, t.mX, t.QKV, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
+
+  const int n_cross = 1 + (int)m->dec.size();
+  auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
+    GemmParams g{};
+    g.out = t.HID; g.ldc = P;
+    HFT_TRY(launch_gemm(m, bf, EPI_RELU, t.mT, lw.w1, Rd, g, s));
+    g = GemmParams{};
+    g.out = t.T; g.ldc = H; g.resid16 = t.T; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
+    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mHID, lw.w2, Rd, g, s));
+    return HFT_OK;
+  };
+  auto cross = [&](const TcDecLayer& lw, const LnW& ln, bool zero, float* probs) -> int {
+    GemmParams g{};
+    g.out = t.QKV + H; g.ldc = 3 * H;                                    // K | V of the 256-bin memory at columns [H, 3H)
+    HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mX, lw.ca_kv, Re, g, s));
+    AttnParams a{};
+    a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H; a.probs = probs; a.q_col0 = 0;
+    if (zero) {
+      a.q_seq_rows = 0;
+      HFT_TRY(launch_attn(m, bf, 256, t.mQ0, t.mQKV_kv, a, Se, s));
+    } else {
+      g = GemmParams{};
+      g.out = t.DQ; g.ldc = 3 * H;
+      HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mT, lw.ca_q, Rd, g, s));
+      a.q_seq_rows = NN;
+      HFT_TRY(launch_attn(m, bf, 256, t.mDQ_q, t.mQKV_kv, a, Se, s));
+    }
+    g = GemmParams{};
+    g.out = t.T; g.ldc = H; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
+    if (zero) { g.resid32 = m->w[m->dec_pos_freq]; g.resid_rows = NN; } else { g.resid16 = t.T; }
+    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.ca_o, Rd, g, s));
+    return HFT_OK;
+  };
+  HFT_TRY(cross(t.dec0, m->dec0.ln, true, n_cross == 1 ? o->attention : nullptr));
+  HFT_TRY(ffn(t.dec0, m->dec0.ln));
+  for (size_t l = 0; l < m->dec.size(); ++l) {
+    const TcDecLayer& lw = t.dec[l];
+    const LnW& ln = m->dec[l].ln;
+    GemmParams g{};
+    g.out = t.DQ; g.ldc = 3 * H;
+    HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mT, lw.sa_qkv, Rd, g, s));
+    AttnParams a{};
+    a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H;
+    HFT_TRY(launch_attn(m, bf, 96, t.mDQ_q, t.mDQ_kv, a, Se, s));
+    g = GemmParams{};
+    g.out = t.T; g.ldc = H; g.resid16 = t.T; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
+    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.sa_o, Rd, g, s));
+    HFT_TRY(cross(lw, ln, false, ((int)l + 2 == n_cross) ? o->attention : nullptr));
+    HFT_TRY(ffn(lw, ln));
+  }
+  // heads A
+  {
+    GemmParams g{};
+    g.onset = o->onset_A; g.offset = o->offset_A; g.mpe = o->mpe_A; g.velocity = o->velocity_A; g.n_vel = V; g.time_major = 0; g.n_frame = F; g.n_note = NN;
+    HFT_TRY(launch_gemm(m, bf, EPI_HEADS, t.mT, t.headA, Rd, g, s));
+  }
+  {
+    LaunchScope ls(HFT_KCLASS_NORM, s);
+    const long long total8 = Rd * H / 8;
+    if (bf) time_relayout16_kernel<true><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, total8, t.U);
+    else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, total8, t.U);
+  }
+  for (size_t l = 0; l < m->tim.size(); ++l)
+    HFT_TRY(encoder_layer_tc(m, t, s, t.U, t.mU, t.DQ, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
+  {
+    GemmParams g{};
+    g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
+    HFT_TRY(launch_gemm(m, bf, EPI_HEADS, t.mU, t.headB, Rd, g, s));
+  }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
 }  // namespace hft
+
+// ---- component entry points (include/hft_sm100.h) ---------------------------------------------------------------
+using namespace hft;
+
+extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16, const float* bias, int64_t M, int32_t N, int32_t K, void* out16,
+                             const void* resid16, const float* gamma, const float* beta, void* stream) {
+  HFT_REQUIRE(a16 && w16 && bias && out16, HFT_ERR_ARG, "hft_tc_linear: NULL buffer");
+  HFT_REQUIRE(epi >= 0 && epi <= 2, HFT_ERR_ARG, "hft_tc_linear: epi %d", epi);
+  HFT_REQUIRE(M % 128 == 0 && K % 64 == 0 && N % 64 == 0 && (epi != 2 || (N <= 256 && resid16 && gamma && beta)), HFT_ERR_UNSUPPORTED,
+              "hft_tc_linear: M=%lld N=%d K=%d epi=%d unsupported", (long long)M, N, K, epi);
+  W16 w;
+  w.ptr = (uint16_t*)w16; w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
+  CUtensorMap ma;
+  HFT_TRY(make_map(&ma, a16, M, K, K, kBlockK, kBlockM, bf16 != 0));
+  HFT_TRY(make_map(&w.map, w16, N, K, K, kBlockK, w.n_tile, bf16 != 0));
+  GemmParams g{};
+  g.out = out16; g.ldc = N; g.resid16 = resid16; g.gamma = gamma; g.beta = beta;
+  reset_launch_count();
+  return launch_gemm(nullptr, bf16 != 0, epi, ma, w, M, g, (cudaStream_t)stream);
+}
+
+extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16, int64_t n_seq, int32_t L, void* ctx16, float* probs,
+                                void* stream) {
+  HFT_REQUIRE(qkv16 && ctx16 && n_seq > 0, HFT_ERR_ARG, "hft_tc_attention: bad argument");
+  HFT_REQUIRE((dh == 64 || dh == 32) && (L == 256 || L == 128 || L == 88) && (!probs || L == 256), HFT_ERR_UNSUPPORTED,
+              "hft_tc_attention: dh=%d L=%d unsupported", dh, L);
+  const int H = heads * dh, LK = L == 88 ? 96 : L;
+  Model fake;
+  fake.heads = heads; fake.dh = dh; fake.H = H;
+  CUtensorMap mq, mkv;
+  HFT_TRY(make_map(&mq, qkv16, n_seq * L, 3 * H, 3 * H, dh, 128, bf16 != 0));
+  HFT_TRY(make_map(&mkv, qkv16, n_seq * L, 3 * H, 3 * H, dh, LK, bf16 != 0));
+  AttnParams a{};
+  a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = ctx16; a.ld_ctx = H; a.probs = probs;
+  reset_launch_count();
+  return launch_attn(&fake, bf16 != 0, LK, mq, mkv, a, n_seq, (cudaStream_t)stream);
+}

@@ -1,0 +1,200 @@
+// tcgen05 attention for one (sequence, head, 128-query tile):  softmax(Q K^T / sqrt(dh)) V
+// (reference MultiHeadAttentionLayer.forward, model_spec2midi.py:342-348; probabilities returned at :360).
+//
+// Every sequence of the model is short (Lk <= 256), so a whole score row fits one TMEM accumulator: no online
+// softmax.  Q, K, V tiles arrive by TMA (swizzled); S = Q K^T is one UMMA chain into TMEM; the 128 threads each own
+// one score row (tcgen05.ld 32x32b), compute max / exp2 / sum in fp32, write the un-normalised probabilities as
+// 16-bit into shared memory in the UMMA K-major 128B-swizzled layout; O = P V is a second UMMA chain whose B operand
+// is V read MN-major straight from its row-major tile (no transpose pass); the epilogue scales by 1/sum.
+// Shared memory: P overlays Q, K (dead after S is complete) so two CTAs fit per SM; TMEM: O overlays S.
+#pragma once
+#include "tc_common.cuh"
+
+namespace hft {
+namespace tc {
+
+struct AttnParams {
+  int lq;                 // valid query rows per sequence (<= 128 * q_tiles)
+  int lk;                 // valid keys per sequence (<= LK)
+  int q_seq_rows;         // rows between consecutive sequences in the Q tensor (0 = the same queries for every sequence)
+  int q_tiles;            // ceil(lq / 128)
+  int heads;
+  int q_col0, k_col0, v_col0;   // first column of head 0 inside the Q / K / V tensors
+  float scale_log2e;      // log2(e) / sqrt(dh)
+  void* ctx;              // 16-bit [n_seq * lq, ld_ctx]
+  int ld_ctx;
+  float* probs;           // optional fp32 [n_seq, heads, lq, lk]
+};
+
+template <int DH, int LK>
+struct AttnSmem {
+  static constexpr int q_bytes = 128 * DH * 2;
+  static constexpr int k_bytes = LK * DH * 2;
+  static constexpr int v_bytes = LK * DH * 2;
+  static constexpr int p_blocks = (LK + 63) / 64;
+  static constexpr int p_bytes = p_blocks * 128 * 128;                       // [blocks][128 rows][64 x 16-bit]
+  static constexpr int front = (q_bytes + k_bytes > p_bytes) ? (q_bytes + k_bytes) : p_bytes;   // Q|K region, reused by P
+  static constexpr int front_al = (front + 1023) / 1024 * 1024;
+  static constexpr int total = 1024 + front_al + v_bytes + 64;
+};
+
+template <bool BF16, int DH, int LK, bool PROBS>
+__global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                                                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p) {
+  using L = AttnSmem<DH, LK>;
+  constexpr uint32_t kSwz = (DH == 64) ? kSwz128 : kSwz64;
+  constexpr uint32_t kRowBytes = DH * 2;                  // 128 or 64
+  constexpr uint32_t kAtom = 8 * kRowBytes;               // 8 rows of one swizzle atom: 1024 or 512 bytes
+  constexpr uint32_t kTmemCols = (LK <= 32) ? 32 : (LK <= 64) ? 64 : (LK <= 128) ? 128 : 256;
+  static_assert(LK % 16 == 0 && LK <= 256 && DH <= kTmemCols, "unsupported tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_q = smem;
+  uint8_t* s_k = smem + L::q_bytes;
+  uint8_t* s_p = smem;                                    // overlays Q|K once S is complete
+  uint8_t* s_v = smem + L::front_al;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + L::v_bytes);   // [0] loads, [1] S ready, [2] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int qt = item % p.q_tiles;
+  const int head = (item / p.q_tiles) % p.heads;
+  const int seq = item / (p.q_tiles * p.heads);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], L::q_bytes + L::k_bytes + L::v_bytes);
+    tma_load_2d(s_q, &map_q, p.q_col0 + head * DH, seq * p.q_seq_rows + qt * 128, &bars[0]);
+    tma_load_2d(s_k, &map_k, p.k_col0 + head * DH, seq * p.lk, &bars[0]);
+    tma_load_2d(s_v, &map_v, p.v_col0 + head * DH, seq * p.lk, &bars[0]);
+    mbar_wait(&bars[0], 0);
+    fence_after_sync();
+    // S[128, LK] = Q[128, DH] * K[LK, DH]^T : both operands K-major
+    const uint32_t idesc = make_idesc(128, LK, BF16, false, false);
+    const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_k);
+#pragma unroll
+    for (int k = 0; k < DH / 16; ++k)
+      umma_f16(tmem_base, make_sdesc(qa + k * 32, 16, kAtom, kSwz), make_sdesc(ka + k * 32, 16, kAtom, kSwz), idesc, k != 0);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  fence_after_sync();
+
+  // ---- softmax: thread = query row --------------------------------------------------------------------------
+  const int r = warp * 32 + lane;                          // row inside the tile == TMEM lane
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < LK / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < p.lk) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  float sum = 0.f;
+  const float mxs = mx * p.scale_log2e;
+#pragma unroll 1
+  for (int c = 0; c < LK / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float e0 = (c * 32 + 2 * j < p.lk) ? exp2f(__uint_as_float(v[2 * j]) * p.scale_log2e - mxs) : 0.f;
+      float e1 = (c * 32 + 2 * j + 1 < p.lk) ? exp2f(__uint_as_float(v[2 * j + 1]) * p.scale_log2e - mxs) : 0.f;
+      sum += e0 + e1;
+      pk[j] = Op16<BF16>::pack(e0, e1);
+    }
+    // P[r, c*32 .. +31] -> K-major 128B-swizzled blocks of 64 columns; wait until every thread has read S's first pass
+    // before the overlay region is written: the S MMA has completed (bars[1]), so Q and K are dead already.
+    uint8_t* blk = s_p + (c >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      int chunk = ((c & 1) * 4 + q4) ^ (r & 7);
+      *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+    }
+  }
+  const float inv_sum = 1.f / sum;
+  if (PROBS) {
+    const int qrow = qt * 128 + r;
+    const bool live = qrow < p.lq;
+    float* prow = p.probs + (((long long)seq * p.heads + head) * p.lq + (live ? qrow : 0)) * p.lk;
+#pragma unroll 1
+    for (int c = 0; c < LK / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_row + c * 32, v);                        // .aligned: every lane loads, only live rows store
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c * 32 + 4 * j + 3 < p.lk) {
+            *reinterpret_cast<float4*>(prow + c * 32 + 4 * j) =
+                make_float4(exp2f(__uint_as_float(v[4 * j]) * p.scale_log2e - mxs) * inv_sum, exp2f(__uint_as_float(v[4 * j + 1]) * p.scale_log2e - mxs) * inv_sum,
+                            exp2f(__uint_as_float(v[4 * j + 2]) * p.scale_log2e - mxs) * inv_sum, exp2f(__uint_as_float(v[4 * j + 3]) * p.scale_log2e - mxs) * inv_sum);
+          }
+        }
+      }
+    }
+  }
+  fence_proxy_async();                                     // generic-proxy smem writes -> visible to the UMMA (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  if (threadIdx.x == 0) {
+    // O[128, DH] = P[128, LK] * V[LK, DH] : A = P K-major (128B swizzle), B = V MN-major (d contiguous)
+    const uint32_t idesc = make_idesc(128, DH, BF16, false, true);
+    const uint32_t pa = smem_u32(s_p), va = smem_u32(s_v);
+#pragma unroll
+    for (int k = 0; k < LK / 16; ++k) {
+      const uint64_t dp = make_sdesc(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024, kSwz128);
+      const uint64_t dv = make_sdesc(va + k * 16 * kRowBytes, kAtom, kAtom, kSwz);
+      umma_f16(tmem_base, dp, dv, idesc, k != 0);
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  fence_after_sync();
+
+  // ---- epilogue: O / sum -> 16-bit context -----------------------------------------------------------------
+  {
+    const int qrow = qt * 128 + r;
+    uint32_t o[32];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.ctx) + ((long long)seq * p.lq + qrow) * p.ld_ctx + head * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      tmem_ld32(t_row + c * 32, o);
+      tmem_ld_wait();
+      if (qrow < p.lq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + c * 16 + j * 4) =
+              make_uint4(Op16<BF16>::pack(__uint_as_float(o[8 * j]) * inv_sum, __uint_as_float(o[8 * j + 1]) * inv_sum),
+                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 2]) * inv_sum, __uint_as_float(o[8 * j + 3]) * inv_sum),
+                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 4]) * inv_sum, __uint_as_float(o[8 * j + 5]) * inv_sum),
+                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 6]) * inv_sum, __uint_as_float(o[8 * j + 7]) * inv_sum));
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace hft
