@@ -95,6 +95,8 @@ typedef struct hft_dims {
 #define HFT_PREC_F32 0      /* fp32 CUDA-core kernels: the 2e-3 parity path */
 #define HFT_PREC_BF16 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 softmax/LayerNorm/sigmoid */
 #define HFT_PREC_F16 2      /* fp16 operands on tcgen05 tensor cores (3 more mantissa bits than bf16) */
+#define HFT_PREC_F16X3 3    /* split fp16 operands (hi + lo): a*w = ah*wh + al*wh + ah*wl on tcgen05, ~22 mantissa bits:
+                               the tensor-core path that meets the fp32 parity budget (2e-3) */
 
 int hft_model_create(hft_model** model, const hft_dims* dims);
 int hft_model_destroy(hft_model* model);

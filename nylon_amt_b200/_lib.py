@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhft_sm100.so")
 
-PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
+PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x3": 3}
 
 c_float_p = ctypes.c_void_p
 

@@ -44,17 +44,30 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
 }
 
 // ---- small CUDA-core kernels of the 16-bit path -----------------------------------------------------------------
+// In x3 (split) mode every 16-bit tensor carries two column blocks: hi = round16(v) at [0, C) and lo = round16(v - hi)
+// at [C, 2C); hi + lo reproduces v to ~22 bits with fp16 parts.
 template <bool BF16>
-__global__ void cvt16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+__device__ __forceinline__ void put16(uint16_t* dst, long long idx, long long lo_off, bool x3, float v) {
+  const uint32_t h = Op16<BF16>::pack(v, 0.f);
+  dst[idx] = (uint16_t)(h & 0xffffu);
+  if (x3) dst[idx + lo_off] = (uint16_t)(Op16<BF16>::pack(v - Op16<BF16>::lo(h), 0.f) & 0xffffu);
+}
+
+// dst[r, :] = 16-bit(src[r % period, :]) for r < valid_rows, 0 beyond   (weights: period = rows; pitch queries: 88)
+template <bool BF16>
+__global__ void cvt_rows_kernel(const float* __restrict__ src, int period, int valid_rows, int K, int rows, bool x3, uint16_t* __restrict__ dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (uint16_t)(Op16<BF16>::pack(src[i], 0.f) & 0xffffu);
+  if (i >= (long long)rows * K) return;
+  int r = (int)(i / K), k = (int)(i % K);
+  const int ld = x3 ? 2 * K : K;
+  put16<BF16>(dst, (long long)r * ld + k, K, x3, r < valid_rows ? src[(long long)(r % period) * K + k] : 0.f);
 }
 
 // heads weight [192, H]: rows 0..V-1 velocity, V..V+2 onset/offset/mpe, rest zero (so velocity stores are 16-byte aligned)
 template <bool BF16>
 __global__ void pack_heads_kernel(const float* __restrict__ w_on, const float* __restrict__ w_off, const float* __restrict__ w_mpe,
                                   const float* __restrict__ w_vel, const float* __restrict__ b_on, const float* __restrict__ b_off,
-                                  const float* __restrict__ b_mpe, const float* __restrict__ b_vel, int V, int H, int rows,
+                                  const float* __restrict__ b_mpe, const float* __restrict__ b_vel, int V, int H, int rows, bool x3,
                                   uint16_t* __restrict__ w16, float* __restrict__ bias) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
@@ -64,7 +77,7 @@ __global__ void pack_heads_kernel(const float* __restrict__ w_on, const float* _
   else if (r == V) { v = w_on[h]; b = b_on[0]; }
   else if (r == V + 1) { v = w_off[h]; b = b_off[0]; }
   else if (r == V + 2) { v = w_mpe[h]; b = b_mpe[0]; }
-  w16[i] = (uint16_t)(Op16<BF16>::pack(v, 0.f) & 0xffffu);
+  put16<BF16>(w16, (long long)r * (x3 ? 2 * H : H) + h, H, x3, v);
   if (h == 0) bias[r] = b;
 }
 
@@ -72,7 +85,7 @@ __global__ void pack_heads_kernel(const float* __restrict__ w_on, const float* _
 template <bool BF16, int NPROC>
 __global__ void __launch_bounds__(256) front16_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st,
                                                       const float* __restrict__ Wc, const float* __restrict__ bc, const float* __restrict__ pos,
-                                                      float scale, int H, int F, int NB, uint16_t* __restrict__ X) {
+                                                      float scale, int H, int F, int NB, bool x3, uint16_t* __restrict__ X) {
   __shared__ float s_row[256];
   const int bin = blockIdx.x, b = blockIdx.y;
   const int W = F + NPROC - 1;
@@ -86,6 +99,7 @@ __global__ void __launch_bounds__(256) front16_kernel(const float* __restrict__ 
   for (int j = 0; j < NPROC; ++j) w[j] = Wc[h * NPROC + j];
   const float bias = bc[h], pe = pos[bin * H + h];
   const int fpg = F / groups;
+  const int ld = x3 ? 2 * H : H;
   for (int f0 = g * fpg; f0 < (g + 1) * fpg; f0 += 8) {
     float acc[8], sv[8];
 #pragma unroll
@@ -99,35 +113,45 @@ __global__ void __launch_bounds__(256) front16_kernel(const float* __restrict__ 
       sv[7] = (j + 1 < NPROC) ? s_row[f0 + j + 8] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      X[(((long long)b * F + f0 + i) * NB + bin) * H + h] = (uint16_t)(Op16<BF16>::pack((acc[i] + bias) * scale + pe, 0.f) & 0xffffu);
+    for (int i = 0; i < 8; ++i) put16<BF16>(X, (((long long)b * F + f0 + i) * NB + bin) * ld + h, H, x3, (acc[i] + bias) * scale + pe);
   }
 }
 
-// U[((b*NN+n)*F+f)*H+h] = T[((b*F+f)*NN+n)*H+h] * sqrt(H) + pos_time[f*H+h]   (model_spec2midi.py:189-191); 8 elements / thread
+// U[((b*NN+n)*F+f), h] = T[((b*F+f)*NN+n), h] * sqrt(H) + pos_time[f, h]   (model_spec2midi.py:189-191); 8 elements / thread
 template <bool BF16>
-__global__ void time_relayout16_kernel(const uint16_t* __restrict__ T, const float* __restrict__ pos, float scale, int F, int NN, int H,
+__global__ void time_relayout16_kernel(const uint16_t* __restrict__ T, const float* __restrict__ pos, float scale, int F, int NN, int H, bool x3,
                                        long long total8, uint16_t* __restrict__ U) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int h8 = H / 8;
+  const int ld = x3 ? 2 * H : H;
   int hq = (int)(i % h8);
   long long r = i / h8;
   int f = (int)(r % F);
   long long bn = r / F;
   int n = (int)(bn % NN);
   long long b = bn / NN;
-  uint4 q = *reinterpret_cast<const uint4*>(T + (((b * F + f) * NN + n)) * H + hq * 8);
+  const uint16_t* src = T + (((b * F + f) * NN + n)) * ld + hq * 8;
+  uint4 q = *reinterpret_cast<const uint4*>(src);
+  uint4 ql = x3 ? *reinterpret_cast<const uint4*>(src + H) : make_uint4(0, 0, 0, 0);
   const float* pp = pos + f * H + hq * 8;
-  uint32_t w4[4] = {q.x, q.y, q.z, q.w}, o[4];
+  uint32_t w4[4] = {q.x, q.y, q.z, q.w}, l4[4] = {ql.x, ql.y, ql.z, ql.w}, o[4], ol[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
-    o[e] = Op16<BF16>::pack(Op16<BF16>::lo(w4[e]) * scale + pp[2 * e], Op16<BF16>::hi(w4[e]) * scale + pp[2 * e + 1]);
-  *reinterpret_cast<uint4*>(U + r * H + hq * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int e = 0; e < 4; ++e) {
+    float a = Op16<BF16>::lo(w4[e]), c = Op16<BF16>::hi(w4[e]);
+    if (x3) { a += Op16<BF16>::lo(l4[e]); c += Op16<BF16>::hi(l4[e]); }
+    a = a * scale + pp[2 * e];
+    c = c * scale + pp[2 * e + 1];
+    o[e] = Op16<BF16>::pack(a, c);
+    ol[e] = Op16<BF16>::pack(a - Op16<BF16>::lo(o[e]), c - Op16<BF16>::hi(o[e]));
+  }
+  uint16_t* dst = U + r * ld + hq * 8;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+  if (x3) *reinterpret_cast<uint4*>(dst + H) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
-// ---- per-dtype state ------------------------------------------------------------------------------------------
-struct W16 {            // one weight matrix [N, K] in 16-bit + its tensor map (box = 64 x n_tile)
+// ---- per-precision state -----------------------------------------------------------------------------------------
+struct W16 {            // one weight matrix [N, K] (x3: [N, 2K] = hi | lo) in 16-bit + its tensor map (box = 64 x n_tile)
   uint16_t* ptr = nullptr;
   int N = 0, K = 0, n_tile = 0;
   CUtensorMap map;
@@ -139,6 +163,7 @@ struct TcDecLayer { W16 sa_qkv, sa_o, ca_q, ca_kv, ca_o, w1, w2; };
 
 struct TcState {
   bool bf16 = true;
+  bool x3 = false;                  // split operands (hi | lo): fp32-class accuracy at 3 MMAs per product
   bool weights_ready = false;
   uint16_t* warena = nullptr;
   float* head_bias = nullptr;       // [2][192]
@@ -151,32 +176,37 @@ struct TcState {
   int ws_batch = 0;
   uint16_t* ws = nullptr;
   uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
-  CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands, box 64 x 128
+  CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands / TMA-store targets, box 64 x 128
+  CUtensorMap mQKV_o, mDQ_o, mPosRep;               // store targets of the projections; repeated pitch-query table (residual of layer zero)
+  uint16_t* pos_rep = nullptr;                      // [11*128, H]: pos_embedding_freq[row % 88] (lcm(88,128) = 1408 rows)
   CUtensorMap mQKV_q, mQKV_kv, mDQ_q, mDQ_kv, mQ0;  // attention operands, box dh x {128, Lk}
+  int cm() const { return x3 ? 2 : 1; }
 };
 
-struct TcBoth { TcState st[2]; };   // [0] = fp16, [1] = bf16
+struct TcBoth { TcState st[3]; };   // [0] = fp16, [1] = bf16, [2] = fp16 x3
 
 static int n_tile_for(int N) {
-  const int cands[4] = {256, 192, 128, 64};
+  const int cands[3] = {256, 128, 64};
   for (int c : cands)
     if (N % c == 0) return c;
   return 0;
 }
 
 template <bool BF16>
-static void cvt(const float* src, uint16_t* dst, long long n, cudaStream_t s) {
-  cvt16_kernel<BF16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+static void cvt_rows(const float* src, int period, int valid_rows, int K, int rows, bool x3, uint16_t* dst, cudaStream_t s) {
+  const long long n = (long long)rows * K;
+  cvt_rows_kernel<BF16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, period, valid_rows, K, rows, x3, dst);
 }
 
 static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
   const int H = m->H, P = m->P, V = m->nvel;
   const long long hh = (long long)H * H, hp = (long long)H * P;
-  const bool bf = t.bf16;
+  const bool bf = t.bf16, x3 = t.x3;
+  const int cm = t.cm();
   size_t n_self = m->enc.size() + m->tim.size() + m->dec.size();
   size_t n_dec_layers = 1 + m->dec.size();
-  size_t elems = n_self * (3 * hh + hh) + (m->enc.size() + m->tim.size() + n_dec_layers) * 2 * hp + n_dec_layers * (hh + 2 * hh + hh) +
-                 2 * (size_t)192 * H + (size_t)128 * H + 4096;
+  size_t elems = (n_self * (3 * hh + hh) + (m->enc.size() + m->tim.size() + n_dec_layers) * 2 * hp + n_dec_layers * (hh + 2 * hh + hh) +
+                  2 * (size_t)192 * H + (size_t)128 * H + (size_t)11 * 128 * H) * cm + 16384;
   if (!t.warena) {
     HFT_CHECK_CUDA(cudaMalloc(&t.warena, elems * 2));
     HFT_CHECK_CUDA(cudaMalloc(&t.head_bias, 2 * 192 * sizeof(float)));
@@ -186,10 +216,10 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
   auto take = [&](size_t n) { uint16_t* r = p; p += (n + 127) & ~(size_t)127; return r; };
   int rc = HFT_OK;
   auto mk = [&](W16& w, const float* src, int N, int K, const float* bias) {
-    w.ptr = take((size_t)N * K);
+    w.ptr = take((size_t)N * K * cm);
     w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
-    if (bf) cvt<true>(src, w.ptr, (long long)N * K, s); else cvt<false>(src, w.ptr, (long long)N * K, s);
-    int r = make_map(&w.map, w.ptr, N, K, K, kBlockK, w.n_tile, bf);
+    if (bf) cvt_rows<true>(src, N, N, K, N, x3, w.ptr, s); else cvt_rows<false>(src, N, N, K, N, x3, w.ptr, s);
+    int r = make_map(&w.map, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile, bf);
     if (r != HFT_OK) rc = r;
   };
   auto mk_enc = [&](TcLayer& L, const EncLayerW& lw, const FusedAttn& f) {
@@ -215,165 +245,193 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
   mk_dec(t.dec0, m->dec0, nullptr, m->dec_ca_kv[0]);
   for (size_t i = 0; i < m->dec.size(); ++i) mk_dec(t.dec[i], m->dec[i], &m->dec_sa_qkv[i], m->dec_ca_kv[i + 1]);
   // heads: packed + reordered
+  HFT_REQUIRE(V + 3 <= 192 && V % 32 == 0, HFT_ERR_UNSUPPORTED, "heads packing expects n_velocity %% 32 == 0 and <= 189");
   auto mk_heads = [&](W16& w, const int* idx, int which) -> int {
-    w.ptr = take((size_t)192 * H);
+    w.ptr = take((size_t)192 * H * cm);
     w.N = 192; w.K = H; w.n_tile = 192; w.bias = t.head_bias + which * 192;
     HFT_CHECK_CUDA(cudaMemsetAsync(t.head_bias + which * 192, 0, 192 * sizeof(float), s));
-    if (bf) pack_heads_kernel<true><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, w.ptr, t.head_bias + which * 192);
-    else pack_heads_kernel<false><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, w.ptr, t.head_bias + which * 192);
-    int r = make_map(&w.map, w.ptr, 192, H, H, kBlockK, 192, bf);
+    if (bf) pack_heads_kernel<true><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, x3, w.ptr, t.head_bias + which * 192);
+    else pack_heads_kernel<false><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, x3, w.ptr, t.head_bias + which * 192);
+    int r = make_map(&w.map, w.ptr, 192, (long long)H * cm, (long long)H * cm, kBlockK, 192, bf);
     if (r != HFT_OK) rc = r;
     return (int)HFT_OK;
   };
-  HFT_REQUIRE(V + 3 <= 192 && V % 32 == 0, HFT_ERR_UNSUPPORTED, "heads packing expects n_velocity %% 32 == 0 and <= 189");
   mk_heads(t.headA, m->head_freq, 0);
   mk_heads(t.headB, m->head_time, 1);
+  // pitch-query table repeated over lcm(88,128) = 1408 rows: residual operand of layer zero's LayerNorm GEMM
+  t.pos_rep = take((size_t)11 * 128 * H * cm);
+  if (bf) cvt_rows<true>(m->w[m->dec_pos_freq], m->nnote, 11 * 128, H, 11 * 128, x3, t.pos_rep, s);
+  else cvt_rows<false>(m->w[m->dec_pos_freq], m->nnote, 11 * 128, H, 11 * 128, x3, t.pos_rep, s);
   // projected pitch queries of layer zero, zero padded to 128 rows
-  t.q0_16 = take((size_t)128 * H);
-  if (bf) cvt<true>(m->q0, t.q0_16, (long long)m->nnote * H, s); else cvt<false>(m->q0, t.q0_16, (long long)m->nnote * H, s);
+  t.q0_16 = take((size_t)128 * H * cm);
+  if (bf) cvt_rows<true>(m->q0, m->nnote, m->nnote, H, 128, x3, t.q0_16, s); else cvt_rows<false>(m->q0, m->nnote, m->nnote, H, 128, x3, t.q0_16, s);
   HFT_CHECK_CUDA(cudaGetLastError());
   if (rc != HFT_OK) return rc;
   t.weights_ready = true;
+  t.ws_batch = 0;                    // tensor maps of q0 / pos_rep are rebuilt with the workspace maps
   return HFT_OK;
 }
 
 static int ensure_ws(Model* m, TcState& t, int B) {
   if (t.ws && t.ws_batch >= B) return HFT_OK;
+  const long long Re = (long long)B * m->nframe * m->nbin, Rd = (long long)B * m->nframe * m->nnote;
+  const int H = m->H, P = m->P, dh = m->dh, cm = t.cm();
+  size_t elems = ((size_t)Re * (5 * H + P) + (size_t)Rd * 5 * H) * cm + 8192;
+  static_assert(sizeof(uint16_t) == 2, "");
   cudaFree(t.ws);
   t.ws = nullptr;
-  const long long Re = (long long)B * m->nframe * m->nbin, Rd = (long long)B * m->nframe * m->nnote;
-  const int H = m->H, P = m->P, dh = m->dh;
-  size_t elems = (size_t)Re * (5 * H + P) + (size_t)Rd * 5 * H + 4096;
   HFT_CHECK_CUDA(cudaMalloc(&t.ws, elems * 2));
   uint16_t* p = t.ws;
   auto take = [&](size_t n) { uint16_t* r = p; p += (n + 511) & ~(size_t)511; return r; };
-  t.X = take((size_t)Re * H); t.QKV = take((size_t)Re * 3 * H); t.CTX = take((size_t)Re * H); t.HID = take((size_t)Re * P);
-  t.T = take((size_t)Rd * H); t.DQ = take((size_t)Rd * 3 * H); t.U = take((size_t)Rd * H);
+  t.X = take((size_t)Re * H * cm); t.QKV = take((size_t)Re * 3 * H * cm); t.CTX = take((size_t)Re * H * cm); t.HID = take((size_t)Re * P * cm);
+  t.T = take((size_t)Rd * H * cm); t.DQ = take((size_t)Rd * 3 * H * cm); t.U = take((size_t)Rd * H * cm);
   const bool bf = t.bf16;
   int rc = HFT_OK;
   auto chk = [&](int r) { if (r != HFT_OK) rc = r; };
-  chk(make_map(&t.mX, t.X, Re, H, H, kBlockK, kBlockM, bf));
-  chk(make_map(&t.mCTX, t.CTX, Re, H, H, kBlockK, kBlockM, bf));
-  chk(make_map(&t.mHID, t.HID, Re, P, P, kBlockK, kBlockM, bf));
-  chk(make_map(&t.mT, t.T, Rd, H, H, kBlockK, kBlockM, bf));
-  chk(make_map(&t.mU, t.U, Rd, H, H, kBlockK, kBlockM, bf));
-  chk(make_map(&t.mQKV_q, t.QKV, Re, 3 * H, 3 * H, dh, 128, bf));
-  chk(make_map(&t.mQKV_kv, t.QKV, Re, 3 * H, 3 * H, dh, 256, bf));
-  chk(make_map(&t.mDQ_q, t.DQ, Rd, 3 * H, 3 * H, dh, 128, bf));
-  chk(make_map(&t.mDQ_kv, t.DQ, Rd, 3 * H, 3 * H, dh, 96, bf));
-  chk(make_map(&t.mQ0, t.q0_16, 128, H, H, dh, 128, bf));
+  const long long h1 = (long long)H * cm, h3 = (long long)3 * H * cm, p1 = (long long)P * cm;
+  chk(make_map(&t.mX, t.X, Re, h1, h1, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mCTX, t.CTX, Re, h1, h1, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mHID, t.HID, Re, p1, p1, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mT, t.T, Rd, h1, h1, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mU, t.U, Rd, h1, h1, kBlockK, kBlockM, bf));
+  chk(make_map(&t.mQKV_q, t.QKV, Re, h3, h3, dh, 128, bf));
+  chk(make_map(&t.mQKV_kv, t.QKV, Re, h3, h3, dh, 256, bf));
+  chk(make_map(&t.mDQ_q, t.DQ, Rd, h3, h3, dh, 128, bf));
+  chk(make_map(&t.mDQ_kv, t.DQ, Rd, h3, h3, dh, 96, bf));
+  chk(make_map(&t.mQ0, t.q0_16, 128, h1, h1, dh, 128, bf));
+  chk(make_map(&t.mQKV_o, t.QKV, Re, h3, h3, 64, 128, bf));
+  chk(make_map(&t.mDQ_o, t.DQ, Rd, h3, h3, 64, 128, bf));
+  chk(make_map(&t.mPosRep, t.pos_rep, 11 * 128, h1, h1, 64, 128, bf));
   if (rc != HFT_OK) return rc;
   t.ws_batch = B;
   return HFT_OK;
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-template <bool BF16, int EPI>
-static int launch_gemm_hc(int half_cols, const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& gp, int grid, size_t smem, cudaStream_t s) {
-#define HFT_GEMM_CASE(HC)                                                                                                 \
-  case HC: {                                                                                                              \
-    auto kern = gemm_kernel<BF16, EPI, HC>;                                                                               \
-    static bool attr_set = false;                                                                                         \
-    if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(256))); attr_set = true; } \
-    kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, gp);                                                                    \
-    break;                                                                                                                \
-  }
-  switch (half_cols) {
-    HFT_GEMM_CASE(32)
-    HFT_GEMM_CASE(64)
-    HFT_GEMM_CASE(96)
-    HFT_GEMM_CASE(128)
-    default:
-      set_error("tc gemm: unsupported tile width %d", half_cols * 2);
-      return HFT_ERR_UNSUPPORTED;
-  }
-#undef HFT_GEMM_CASE
+template <bool BF16, int EPI, int HALVES, int COLS>
+static int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp, int grid,
+                         size_t smem, cudaStream_t s) {
+  auto kern = gemm_kernel<BF16, EPI, HALVES, COLS>;
+  static bool attr_set = false;
+  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+  kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, mr, mo, gp);
   return HFT_OK;
 }
 
-static int launch_gemm(Model* m, bool bf16, int epi, const CUtensorMap& ma, const W16& w, long long M, GemmParams gp, cudaStream_t s) {
+template <bool BF16, int EPI>
+static int launch_gemm_e(int n_tile, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp,
+                         int grid, size_t smem, cudaStream_t s) {
+  if (EPI == EPI_HEADS) return launch_gemm_t<BF16, EPI_HEADS, 2, 96>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 256) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 2, 128>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 128) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 2, 64>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 64) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 1, 64>(ma, mw, mr, mo, gp, grid, smem, s);
+  set_error("tc gemm: unsupported tile width %d", n_tile);
+  return HFT_ERR_UNSUPPORTED;
+}
+
+// out: tensor map of the output tensor (box 64 x 128) for the TMA-store epilogues; resid: tensor map of the residual
+// (box 64 x 128) for EPI_LN (added by the identity MMA).
+static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, long long M, GemmParams gp, const CUtensorMap* mo,
+                       const CUtensorMap* mr, cudaStream_t s) {
   HFT_REQUIRE(M % kBlockM == 0 && w.K % kBlockK == 0 && w.n_tile > 0, HFT_ERR_UNSUPPORTED, "tc gemm: M=%lld K=%d N=%d unsupported", M, w.K, w.N);
   gp.m_tiles = (int)(M / kBlockM);
-  gp.n_tile = w.n_tile;
   gp.n_tiles = w.N / w.n_tile;
   gp.k_chunks = w.K / kBlockK;
   gp.bias = w.bias;
+  gp.has_resid = (epi == EPI_LN && mr != nullptr) ? 1 : 0;
   if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
-  const int total = gp.m_tiles * gp.n_tiles;
+  // W stays resident when its slice fits beside a 3-deep A ring, the identity block and the store staging
+  const size_t w_bytes = (size_t)w.n_tile * w.K * 2 * (gp.x3 ? 2 : 1);
+  gp.w_resident = w_bytes <= 128 * 1024 ? 1 : 0;
+  gp.n_stages = gp.w_resident ? (w_bytes <= 64 * 1024 ? 6 : 3) : 3;
   static int sms = num_sms();
-  const int grid = total < sms ? total : sms;
-  const size_t smem = gemm_smem_bytes(w.n_tile);
-  const int hc = w.n_tile / 2;
+  int grid = (sms / gp.n_tiles) * gp.n_tiles;
+  if (grid > gp.m_tiles * gp.n_tiles) grid = gp.m_tiles * gp.n_tiles;
+  const size_t smem = gemm_smem_bytes(w.n_tile, gp.k_chunks, gp.w_resident, gp.n_stages, gp.x3);
+  HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "tc gemm: %zu bytes of shared memory needed", smem);
+  const CUtensorMap& o = mo ? *mo : ma;
+  const CUtensorMap& r = mr ? *mr : ma;
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  int rc;
   if (bf16) {
-    rc = epi == EPI_STORE ? launch_gemm_hc<true, EPI_STORE>(hc, ma, w.map, gp, grid, smem, s)
-       : epi == EPI_RELU  ? launch_gemm_hc<true, EPI_RELU>(hc, ma, w.map, gp, grid, smem, s)
-       : epi == EPI_LN    ? launch_gemm_hc<true, EPI_LN>(hc, ma, w.map, gp, grid, smem, s)
-                          : launch_gemm_hc<true, EPI_HEADS>(hc, ma, w.map, gp, grid, smem, s);
-  } else {
-    rc = epi == EPI_STORE ? launch_gemm_hc<false, EPI_STORE>(hc, ma, w.map, gp, grid, smem, s)
-       : epi == EPI_RELU  ? launch_gemm_hc<false, EPI_RELU>(hc, ma, w.map, gp, grid, smem, s)
-       : epi == EPI_LN    ? launch_gemm_hc<false, EPI_LN>(hc, ma, w.map, gp, grid, smem, s)
-                          : launch_gemm_hc<false, EPI_HEADS>(hc, ma, w.map, gp, grid, smem, s);
+    return epi == EPI_STORE ? launch_gemm_e<true, EPI_STORE>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+         : epi == EPI_RELU  ? launch_gemm_e<true, EPI_RELU>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+         : epi == EPI_LN    ? launch_gemm_e<true, EPI_LN>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+                            : launch_gemm_e<true, EPI_HEADS>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s);
   }
-  (void)m;
-  return rc;
+  return epi == EPI_STORE ? launch_gemm_e<false, EPI_STORE>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+       : epi == EPI_RELU  ? launch_gemm_e<false, EPI_RELU>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+       : epi == EPI_LN    ? launch_gemm_e<false, EPI_LN>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
+                          : launch_gemm_e<false, EPI_HEADS>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s);
 }
 
-template <bool BF16, int DH, int LK, bool PROBS>
+template <bool BF16, int DH, int LK, bool PROBS, bool X3>
 static int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
-  auto kern = attn_kernel<BF16, DH, LK, PROBS>;
+  auto kern = attn_kernel<BF16, DH, LK, PROBS, X3>;
   static bool attr_set = false;
-  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DH, LK>::total)); attr_set = true; }
-  kern<<<(unsigned)items, 128, AttnSmem<DH, LK>::total, s>>>(mq, mk, mv, ap);
+  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DH, LK, X3>::total)); attr_set = true; }
+  kern<<<(unsigned)items, 128, AttnSmem<DH, LK, X3>::total, s>>>(mq, mk, mv, ap);
   return HFT_OK;
 }
 
-template <bool BF16, int DH>
+template <bool BF16, int DH, bool X3>
 static int launch_attn_dh(int LK, bool probs, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
-  if (LK == 256) return probs ? launch_attn_t<BF16, DH, 256, true>(mq, mk, mv, ap, items, s) : launch_attn_t<BF16, DH, 256, false>(mq, mk, mv, ap, items, s);
-  if (LK == 128) return launch_attn_t<BF16, DH, 128, false>(mq, mk, mv, ap, items, s);
-  if (LK == 96) return launch_attn_t<BF16, DH, 96, false>(mq, mk, mv, ap, items, s);
+  if (LK == 256) return probs ? launch_attn_t<BF16, DH, 256, true, X3>(mq, mk, mv, ap, items, s) : launch_attn_t<BF16, DH, 256, false, X3>(mq, mk, mv, ap, items, s);
+  if (LK == 128) return launch_attn_t<BF16, DH, 128, false, X3>(mq, mk, mv, ap, items, s);
+  if (LK == 96) return launch_attn_t<BF16, DH, 96, false, X3>(mq, mk, mv, ap, items, s);
   set_error("tc attention: unsupported key tile %d", LK);
   return HFT_ERR_UNSUPPORTED;
 }
 
-static int launch_attn(Model* m, bool bf16, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams ap, long long n_seq, cudaStream_t s) {
-  ap.heads = m->heads;
+static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams ap, long long n_seq, cudaStream_t s) {
+  ap.heads = heads;
   ap.q_tiles = (ap.lq + 127) / 128;
-  ap.scale_log2e = 1.4426950408889634f / sqrtf((float)m->dh);
-  const long long items = n_seq * m->heads * ap.q_tiles;
+  ap.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
+  const long long items = n_seq * heads * ap.q_tiles;
   HFT_REQUIRE(items < (1ll << 31), HFT_ERR_UNSUPPORTED, "tc attention: too many work items");
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   const bool probs = ap.probs != nullptr;
-  if (m->dh == 64) return bf16 ? launch_attn_dh<true, 64>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 64>(LK, probs, mq, mkv, mkv, ap, items, s);
-  return bf16 ? launch_attn_dh<true, 32>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 32>(LK, probs, mq, mkv, mkv, ap, items, s);
+  if (x3) {                                             // split mode is fp16 only
+    HFT_REQUIRE(!bf16, HFT_ERR_UNSUPPORTED, "x3 attention is built for fp16 parts");
+    if (dh == 64) return launch_attn_dh<false, 64, true>(LK, probs, mq, mkv, mkv, ap, items, s);
+    return launch_attn_dh<false, 32, true>(LK, probs, mq, mkv, mkv, ap, items, s);
+  }
+  if (dh == 64) return bf16 ? launch_attn_dh<true, 64, false>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 64, false>(LK, probs, mq, mkv, mkv, ap, items, s);
+  return bf16 ? launch_attn_dh<true, 32, false>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 32, false>(LK, probs, mq, mkv, mkv, ap, items, s);
 }
 
 #define HFT_TRY(x) do { int _rc = (x); if (_rc != HFT_OK) return _rc; } while (0)
 
+// one projection launch: out[:, out_col0 ..] = epilogue(A * W^T); out_width = columns of the output tensor's hi block
+static int linear(TcState& t, cudaStream_t s, int epi, const CUtensorMap& a, const W16& w, long long M, const CUtensorMap& out, int out_col0,
+                  int out_width, const CUtensorMap* resid = nullptr, const LnW* ln = nullptr, Model* m = nullptr, int resid_period = 0) {
+  GemmParams g{};
+  g.out_col0 = out_col0;
+  g.resid_period = resid_period;
+  g.x3 = t.x3 ? 1 : 0;
+  g.a_lo_off = w.K; g.w_lo_off = w.K; g.out_lo_off = out_width;
+  if (ln) { g.gamma = m->w[ln->g]; g.beta = m->w[ln->b]; }
+  return launch_gemm(t.bf16, epi, a, w, M, g, &out, resid, s);
+}
+
+static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams a, long long n_seq, int q_width) {
+  a.q_lo_off = q_width;            // hi-block width of the Q tensor (3H for fused QKV buffers, H for the pitch-query table)
+  a.kv_lo_off = 3 * m->H;
+  a.ctx = t.CTX; a.ld_ctx = m->H * t.cm(); a.ctx_lo_off = m->H;
+  return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, a, n_seq, s);
+}
+
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
-static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, uint16_t* x, const CUtensorMap& mx, uint16_t* qkv, const CUtensorMap& mq,
+static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& mqkv_o, const CUtensorMap& mq,
                             const CUtensorMap& mkv, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
   const int H = m->H, P = m->P;
   const long long R = S * L;
-  const bool bf = t.bf16;
-  GemmParams g{};
-  g.out = qkv; g.ldc = 3 * H;
-  HFT_TRY(launch_gemm(m, bf, EPI_STORE, mx, lw.qkv, R, g, s));
+  HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, mqkv_o, 0, 3 * H));
   AttnParams a{};
-  a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H; a.probs = nullptr;
-  HFT_TRY(launch_attn(m, bf, LK, mq, mkv, a, S, s));
-  g = GemmParams{};
-  g.out = x; g.ldc = H; g.resid16 = x; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
-  HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.o, R, g, s));
-  g = GemmParams{};
-  g.out = t.HID; g.ldc = P;
-  HFT_TRY(launch_gemm(m, bf, EPI_RELU, mx, lw.w1, R, g, s));
-  g = GemmParams{};
-  g.out = x; g.ldc = H; g.resid16 = x; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
-  HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mHID, lw.w2, R, g, s));
+  a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
+  HFT_TRY(attention(m, t, s, LK, mq, mkv, a, S, 3 * H));
+  HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, mx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
+  HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.mHID, 0, P));
+  HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, mx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
   return HFT_OK;
 }
 
@@ -381,8 +439,7 @@ int tc_prepare_weights(Model* m, cudaStream_t s) {
   (void)s;
   if (m->tc) {                                    // weights changed: 16-bit copies are rebuilt lazily per dtype
     TcBoth* b = reinterpret_cast<TcBoth*>(m->tc);
-    b->st[0].weights_ready = false;
-    b->st[1].weights_ready = false;
+    for (auto& t : b->st) t.weights_ready = false;
   }
   return HFT_OK;
 }
@@ -400,59 +457,53 @@ static TcState& state_for(Model* m, int precision) {
     TcBoth* b = new TcBoth();
     b->st[0].bf16 = false;
     b->st[1].bf16 = true;
+    b->st[2].bf16 = false;
+    b->st[2].x3 = true;
     m->tc = b;
   }
-  return reinterpret_cast<TcBoth*>(m->tc)->st[precision == HFT_PREC_BF16 ? 1 : 0];
+  return reinterpret_cast<TcBoth*>(m->tc)->st[precision == HFT_PREC_BF16 ? 1 : precision == HFT_PREC_F16X3 ? 2 : 0];
 }
 
 int forward_tc(Model* m, int precision, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s) {
   if (B == 0) return HFT_OK;
+  HFT_REQUIRE(m->H == 64 || m->H == 128 || m->H == 256, HFT_ERR_UNSUPPORTED, "tensor-core path supports hid_dim 64 / 128 / 256 (got %d)", m->H);
   TcState& t = state_for(m, precision);
   const bool bf = t.bf16;
   if (!t.weights_ready) HFT_TRY(prepare_weights(m, t, s));
   HFT_TRY(ensure_ws(m, t, B > m->max_batch ? B : m->max_batch));
-  const int H = m->H, P = m->P, F = m->nframe, NB = m->nbin, NN = m->nnote, V = m->nvel;
+  const int H = m->H, F = m->nframe, NB = m->nbin, NN = m->nnote, V = m->nvel;
   const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
   const float sqrtH = sqrtf((float)H);
   HFT_REQUIRE(m->nproc == 65, HFT_ERR_UNSUPPORTED, "front kernel is built for n_margin 32");
   {
     LaunchScope ls(HFT_KCLASS_FRONT, s);
-    if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.X);
-    else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.X);
+    if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
+    else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
   }
   for (size_t l = 0; l < m->enc.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.X, t.mX, t.QKV, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.mQKV_o, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
-    GemmParams g{};
-    g.out = t.HID; g.ldc = P;
-    HFT_TRY(launch_gemm(m, bf, EPI_RELU, t.mT, lw.w1, Rd, g, s));
-    g = GemmParams{};
-    g.out = t.T; g.ldc = H; g.resid16 = t.T; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
-    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mHID, lw.w2, Rd, g, s));
+    HFT_TRY(linear(t, s, EPI_RELU, t.mT, lw.w1, Rd, t.mHID, 0, m->P));
+    HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, Rd, t.mT, 0, H, &t.mT, &ln, m));
     return HFT_OK;
   };
   auto cross = [&](const TcDecLayer& lw, const LnW& ln, bool zero, float* probs) -> int {
-    GemmParams g{};
-    g.out = t.QKV + H; g.ldc = 3 * H;                                    // K | V of the 256-bin memory at columns [H, 3H)
-    HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mX, lw.ca_kv, Re, g, s));
+    HFT_TRY(linear(t, s, EPI_STORE, t.mX, lw.ca_kv, Re, t.mQKV_o, H, 3 * H));   // K | V of the 256-bin memory at columns [H, 3H)
     AttnParams a{};
-    a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H; a.probs = probs; a.q_col0 = 0;
+    a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = probs; a.q_col0 = 0;
     if (zero) {
       a.q_seq_rows = 0;
-      HFT_TRY(launch_attn(m, bf, 256, t.mQ0, t.mQKV_kv, a, Se, s));
+      HFT_TRY(attention(m, t, s, 256, t.mQ0, t.mQKV_kv, a, Se, H));
+      // t = LN(pos_embedding_freq + fc_o(ctx)): the residual is the constant pitch-query table, period lcm(88,128)/128 = 11 tiles
+      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.mT, 0, H, &t.mPosRep, &ln, m, 11));
     } else {
-      g = GemmParams{};
-      g.out = t.DQ; g.ldc = 3 * H;
-      HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mT, lw.ca_q, Rd, g, s));
+      HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.ca_q, Rd, t.mDQ_o, 0, 3 * H));
       a.q_seq_rows = NN;
-      HFT_TRY(launch_attn(m, bf, 256, t.mDQ_q, t.mQKV_kv, a, Se, s));
+      HFT_TRY(attention(m, t, s, 256, t.mDQ_q, t.mQKV_kv, a, Se, 3 * H));
+      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.mT, 0, H, &t.mT, &ln, m));
     }
-    g = GemmParams{};
-    g.out = t.T; g.ldc = H; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
-    if (zero) { g.resid32 = m->w[m->dec_pos_freq]; g.resid_rows = NN; } else { g.resid16 = t.T; }
-    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.ca_o, Rd, g, s));
     return HFT_OK;
   };
   HFT_TRY(cross(t.dec0, m->dec0.ln, true, n_cross == 1 ? o->attention : nullptr));
@@ -460,15 +511,11 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   for (size_t l = 0; l < m->dec.size(); ++l) {
     const TcDecLayer& lw = t.dec[l];
     const LnW& ln = m->dec[l].ln;
-    GemmParams g{};
-    g.out = t.DQ; g.ldc = 3 * H;
-    HFT_TRY(launch_gemm(m, bf, EPI_STORE, t.mT, lw.sa_qkv, Rd, g, s));
+    HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.sa_qkv, Rd, t.mDQ_o, 0, 3 * H));
     AttnParams a{};
-    a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = t.CTX; a.ld_ctx = H;
-    HFT_TRY(launch_attn(m, bf, 96, t.mDQ_q, t.mDQ_kv, a, Se, s));
-    g = GemmParams{};
-    g.out = t.T; g.ldc = H; g.resid16 = t.T; g.gamma = m->w[ln.g]; g.beta = m->w[ln.b];
-    HFT_TRY(launch_gemm(m, bf, EPI_LN, t.mCTX, lw.sa_o, Rd, g, s));
+    a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H;
+    HFT_TRY(attention(m, t, s, 96, t.mDQ_q, t.mDQ_kv, a, Se, 3 * H));
+    HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.sa_o, Rd, t.mT, 0, H, &t.mT, &ln, m));
     HFT_TRY(cross(lw, ln, false, ((int)l + 2 == n_cross) ? o->attention : nullptr));
     HFT_TRY(ffn(lw, ln));
   }
@@ -476,20 +523,22 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   {
     GemmParams g{};
     g.onset = o->onset_A; g.offset = o->offset_A; g.mpe = o->mpe_A; g.velocity = o->velocity_A; g.n_vel = V; g.time_major = 0; g.n_frame = F; g.n_note = NN;
-    HFT_TRY(launch_gemm(m, bf, EPI_HEADS, t.mT, t.headA, Rd, g, s));
+    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
+    HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mT, t.headA, Rd, g, nullptr, nullptr, s));
   }
   {
     LaunchScope ls(HFT_KCLASS_NORM, s);
     const long long total8 = Rd * H / 8;
-    if (bf) time_relayout16_kernel<true><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, total8, t.U);
-    else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, total8, t.U);
+    if (bf) time_relayout16_kernel<true><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, t.x3, total8, t.U);
+    else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, t.x3, total8, t.U);
   }
   for (size_t l = 0; l < m->tim.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.U, t.mU, t.DQ, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.mDQ_o, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
   {
     GemmParams g{};
     g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
-    HFT_TRY(launch_gemm(m, bf, EPI_HEADS, t.mU, t.headB, Rd, g, s));
+    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
+    HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mU, t.headB, Rd, g, nullptr, nullptr, s));
   }
   HFT_CHECK_CUDA(cudaGetLastError());
   return HFT_OK;
@@ -504,17 +553,19 @@ extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16
                              const void* resid16, const float* gamma, const float* beta, void* stream) {
   HFT_REQUIRE(a16 && w16 && bias && out16, HFT_ERR_ARG, "hft_tc_linear: NULL buffer");
   HFT_REQUIRE(epi >= 0 && epi <= 2, HFT_ERR_ARG, "hft_tc_linear: epi %d", epi);
-  HFT_REQUIRE(M % 128 == 0 && K % 64 == 0 && N % 64 == 0 && (epi != 2 || (N <= 256 && resid16 && gamma && beta)), HFT_ERR_UNSUPPORTED,
-              "hft_tc_linear: M=%lld N=%d K=%d epi=%d unsupported", (long long)M, N, K, epi);
+  HFT_REQUIRE(M % 128 == 0 && K % 64 == 0 && N % 64 == 0 && (epi != 2 || ((N == 64 || N == 128 || N == 256) && resid16 && gamma && beta)),
+              HFT_ERR_UNSUPPORTED, "hft_tc_linear: M=%lld N=%d K=%d epi=%d unsupported", (long long)M, N, K, epi);
   W16 w;
   w.ptr = (uint16_t*)w16; w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
-  CUtensorMap ma;
+  CUtensorMap ma, mo, mr;
   HFT_TRY(make_map(&ma, a16, M, K, K, kBlockK, kBlockM, bf16 != 0));
   HFT_TRY(make_map(&w.map, w16, N, K, K, kBlockK, w.n_tile, bf16 != 0));
+  HFT_TRY(make_map(&mo, out16, M, N, N, 64, 128, bf16 != 0));
+  if (epi == 2) HFT_TRY(make_map(&mr, resid16, M, N, N, 64, 128, bf16 != 0));
   GemmParams g{};
-  g.out = out16; g.ldc = N; g.resid16 = resid16; g.gamma = gamma; g.beta = beta;
+  g.gamma = gamma; g.beta = beta;
   reset_launch_count();
-  return launch_gemm(nullptr, bf16 != 0, epi, ma, w, M, g, (cudaStream_t)stream);
+  return launch_gemm(bf16 != 0, epi, ma, w, M, g, &mo, epi == 2 ? &mr : nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16, int64_t n_seq, int32_t L, void* ctx16, float* probs,
@@ -523,13 +574,11 @@ extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void*
   HFT_REQUIRE((dh == 64 || dh == 32) && (L == 256 || L == 128 || L == 88) && (!probs || L == 256), HFT_ERR_UNSUPPORTED,
               "hft_tc_attention: dh=%d L=%d unsupported", dh, L);
   const int H = heads * dh, LK = L == 88 ? 96 : L;
-  Model fake;
-  fake.heads = heads; fake.dh = dh; fake.H = H;
   CUtensorMap mq, mkv;
   HFT_TRY(make_map(&mq, qkv16, n_seq * L, 3 * H, 3 * H, dh, 128, bf16 != 0));
   HFT_TRY(make_map(&mkv, qkv16, n_seq * L, 3 * H, 3 * H, dh, LK, bf16 != 0));
   AttnParams a{};
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = ctx16; a.ld_ctx = H; a.probs = probs;
   reset_launch_count();
-  return launch_attn(&fake, bf16 != 0, LK, mq, mkv, a, n_seq, (cudaStream_t)stream);
+  return launch_attn(heads, dh, bf16 != 0, false, LK, mq, mkv, a, n_seq, (cudaStream_t)stream);
 }

@@ -24,24 +24,29 @@ struct AttnParams {
   void* ctx;              // 16-bit [n_seq * lq, ld_ctx]
   int ld_ctx;
   float* probs;           // optional fp32 [n_seq, heads, lq, lk]
+  int q_lo_off, kv_lo_off;   // x3: column distance between the hi and lo halves of the Q tensor / the K,V tensor
+  int ctx_lo_off;         // x3: same for ctx
 };
 
-template <int DH, int LK>
+template <int DH, int LK, bool X3 = false>
 struct AttnSmem {
+  static constexpr int parts = X3 ? 2 : 1;                                   // hi (+ lo) copies of every operand
   static constexpr int q_bytes = 128 * DH * 2;
   static constexpr int k_bytes = LK * DH * 2;
   static constexpr int v_bytes = LK * DH * 2;
   static constexpr int p_blocks = (LK + 63) / 64;
   static constexpr int p_bytes = p_blocks * 128 * 128;                       // [blocks][128 rows][64 x 16-bit]
-  static constexpr int front = (q_bytes + k_bytes > p_bytes) ? (q_bytes + k_bytes) : p_bytes;   // Q|K region, reused by P
+  static constexpr int qk_al = (q_bytes + k_bytes + 1023) / 1024 * 1024;     // one Q|K pair, 1024-aligned
+  static constexpr int front = (parts * qk_al > parts * p_bytes) ? parts * qk_al : parts * p_bytes;   // Q|K region, reused by P
   static constexpr int front_al = (front + 1023) / 1024 * 1024;
-  static constexpr int total = 1024 + front_al + v_bytes + 64;
+  static constexpr int total = 1024 + front_al + parts * v_bytes + 64;
 };
 
-template <bool BF16, int DH, int LK, bool PROBS>
+template <bool BF16, int DH, int LK, bool PROBS, bool X3>
 __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p) {
-  using L = AttnSmem<DH, LK>;
+  using L = AttnSmem<DH, LK, X3>;
+  constexpr int kParts = X3 ? 2 : 1;
   constexpr uint32_t kSwz = (DH == 64) ? kSwz128 : kSwz64;
   constexpr uint32_t kRowBytes = DH * 2;                  // 128 or 64
   constexpr uint32_t kAtom = 8 * kRowBytes;               // 8 rows of one swizzle atom: 1024 or 512 bytes
@@ -50,11 +55,11 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_q = smem;
+  uint8_t* s_q = smem;                                    // part i: Q at i*qk_al, K right after it
   uint8_t* s_k = smem + L::q_bytes;
-  uint8_t* s_p = smem;                                    // overlays Q|K once S is complete
-  uint8_t* s_v = smem + L::front_al;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + L::v_bytes);   // [0] loads, [1] S ready, [2] O ready
+  uint8_t* s_p = smem;                                    // overlays Q|K once S is complete; part i at i*p_bytes
+  uint8_t* s_v = smem + L::front_al;                      // part i at i*v_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + kParts * L::v_bytes);   // [0] loads, [1] S ready, [2] O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,18 +80,28 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], L::q_bytes + L::k_bytes + L::v_bytes);
-    tma_load_2d(s_q, &map_q, p.q_col0 + head * DH, seq * p.q_seq_rows + qt * 128, &bars[0]);
-    tma_load_2d(s_k, &map_k, p.k_col0 + head * DH, seq * p.lk, &bars[0]);
-    tma_load_2d(s_v, &map_v, p.v_col0 + head * DH, seq * p.lk, &bars[0]);
+    mbar_expect_tx(&bars[0], kParts * (L::q_bytes + L::k_bytes + L::v_bytes));
+#pragma unroll
+    for (int part = 0; part < kParts; ++part) {
+      tma_load_2d(s_q + part * L::qk_al, &map_q, part * p.q_lo_off + p.q_col0 + head * DH, seq * p.q_seq_rows + qt * 128, &bars[0]);
+      tma_load_2d(s_k + part * L::qk_al, &map_k, part * p.kv_lo_off + p.k_col0 + head * DH, seq * p.lk, &bars[0]);
+      tma_load_2d(s_v + part * L::v_bytes, &map_v, part * p.kv_lo_off + p.v_col0 + head * DH, seq * p.lk, &bars[0]);
+    }
     mbar_wait(&bars[0], 0);
     fence_after_sync();
-    // S[128, LK] = Q[128, DH] * K[LK, DH]^T : both operands K-major
+    // S[128, LK] = Q[128, DH] * K[LK, DH]^T : both operands K-major.  x3: Qh Kh + Ql Kh + Qh Kl.
     const uint32_t idesc = make_idesc(128, LK, BF16, false, false);
     const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_k);
+    uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < DH / 16; ++k)
-      umma_f16(tmem_base, make_sdesc(qa + k * 32, 16, kAtom, kSwz), make_sdesc(ka + k * 32, 16, kAtom, kSwz), idesc, k != 0);
+    for (int part = 0; part < (X3 ? 3 : 1); ++part) {
+      const uint32_t qp = qa + (part == 1 ? L::qk_al : 0), kp = ka + (part == 2 ? L::qk_al : 0);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) {
+        umma_f16(tmem_base, make_sdesc(qp + k * 32, 16, kAtom, kSwz), make_sdesc(kp + k * 32, 16, kAtom, kSwz), idesc, acc);
+        acc = 1;
+      }
+    }
     umma_commit(&bars[1]);
   }
   mbar_wait(&bars[1], 0);
@@ -112,13 +127,14 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
     uint32_t v[32];
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
-    uint32_t pk[16];
+    uint32_t pk[16], pl[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float e0 = (c * 32 + 2 * j < p.lk) ? exp2f(__uint_as_float(v[2 * j]) * p.scale_log2e - mxs) : 0.f;
       float e1 = (c * 32 + 2 * j + 1 < p.lk) ? exp2f(__uint_as_float(v[2 * j + 1]) * p.scale_log2e - mxs) : 0.f;
       sum += e0 + e1;
       pk[j] = Op16<BF16>::pack(e0, e1);
+      if (X3) pl[j] = Op16<BF16>::pack(e0 - Op16<BF16>::lo(pk[j]), e1 - Op16<BF16>::hi(pk[j]));
     }
     // P[r, c*32 .. +31] -> K-major 128B-swizzled blocks of 64 columns; wait until every thread has read S's first pass
     // before the overlay region is written: the S MMA has completed (bars[1]), so Q and K are dead already.
@@ -127,6 +143,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
     for (int q4 = 0; q4 < 4; ++q4) {
       int chunk = ((c & 1) * 4 + q4) ^ (r & 7);
       *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      if (X3) *reinterpret_cast<uint4*>(blk + L::p_bytes + chunk * 16) = make_uint4(pl[4 * q4], pl[4 * q4 + 1], pl[4 * q4 + 2], pl[4 * q4 + 3]);
     }
   }
   const float inv_sum = 1.f / sum;
@@ -160,11 +177,17 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
     // O[128, DH] = P[128, LK] * V[LK, DH] : A = P K-major (128B swizzle), B = V MN-major (d contiguous)
     const uint32_t idesc = make_idesc(128, DH, BF16, false, true);
     const uint32_t pa = smem_u32(s_p), va = smem_u32(s_v);
+    uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < LK / 16; ++k) {
-      const uint64_t dp = make_sdesc(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024, kSwz128);
-      const uint64_t dv = make_sdesc(va + k * 16 * kRowBytes, kAtom, kAtom, kSwz);
-      umma_f16(tmem_base, dp, dv, idesc, k != 0);
+    for (int part = 0; part < (X3 ? 3 : 1); ++part) {                 // x3: Ph Vh + Pl Vh + Ph Vl
+      const uint32_t pp = pa + (part == 1 ? L::p_bytes : 0), vp = va + (part == 2 ? L::v_bytes : 0);
+#pragma unroll
+      for (int k = 0; k < LK / 16; ++k) {
+        const uint64_t dp = make_sdesc(pp + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024, kSwz128);
+        const uint64_t dv = make_sdesc(vp + k * 16 * kRowBytes, kAtom, kAtom, kSwz);
+        umma_f16(tmem_base, dp, dv, idesc, acc);
+        acc = 1;
+      }
     }
     umma_commit(&bars[2]);
   }
@@ -182,12 +205,17 @@ __global__ void __launch_bounds__(128) attn_kernel(const __grid_constant__ CUten
       tmem_ld_wait();
       if (qrow < p.lq) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(dst + c * 16 + j * 4) =
-              make_uint4(Op16<BF16>::pack(__uint_as_float(o[8 * j]) * inv_sum, __uint_as_float(o[8 * j + 1]) * inv_sum),
-                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 2]) * inv_sum, __uint_as_float(o[8 * j + 3]) * inv_sum),
-                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 4]) * inv_sum, __uint_as_float(o[8 * j + 5]) * inv_sum),
-                         Op16<BF16>::pack(__uint_as_float(o[8 * j + 6]) * inv_sum, __uint_as_float(o[8 * j + 7]) * inv_sum));
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(o[8 * j + 2 * e]) * inv_sum, b = __uint_as_float(o[8 * j + 2 * e + 1]) * inv_sum;
+            h[e] = Op16<BF16>::pack(a, b);
+            if (X3) l[e] = Op16<BF16>::pack(a - Op16<BF16>::lo(h[e]), b - Op16<BF16>::hi(h[e]));
+          }
+          *reinterpret_cast<uint4*>(dst + c * 16 + j * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (X3) *reinterpret_cast<uint4*>(dst + p.ctx_lo_off / 2 + c * 16 + j * 4) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
       }
     }
   }

@@ -1,15 +1,22 @@
 // Persistent, warp-specialised tcgen05 GEMM for the hFT projections:  C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
 //
-//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, kStages-deep mbarrier ring)
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, mbarrier ring of A (and W) chunks)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
 //                               two 256-column accumulator buffers so tile i+1's MMAs overlap tile i's epilogue)
 //   warps 2..9  epilogue       (tcgen05.ld TMEM -> registers; warp w owns TMEM lanes 32*(w%4).., column half (w-2)/4;
-//                               bias / ReLU / residual + LayerNorm / sigmoid heads; 16-byte global stores)
+//                               bias / ReLU / LayerNorm / sigmoid heads; results staged in swizzled shared memory
+//                               and written with TMA stores so that HBM sees full 128-byte lines)
 //
-// A and W are 16-bit (bf16 or fp16), K-major; every GEMM of the model has K in {64..512} and N <= 768, so the
-// kernel is short-K: per 128-row tile it moves 128*K*2 bytes of A against 2*128*N*K flops, i.e. it is HBM-bound
-// unless fused, which is why the epilogues carry everything that follows the projection in the reference
-// (model_spec2midi.py:236,242 residual + LayerNorm; :372 ReLU; :172-175 sigmoid heads).
+// A and W are 16-bit (bf16 or fp16), K-major.  Every GEMM of the model has K in {64..512} and N <= 768: per 128-row
+// tile it moves 128*K*2 bytes of A against 2*128*N*K flops, so it is bound by HBM/L2 bytes, not by the tensor pipe.
+// Hence:
+//   * W-resident mode: a CTA keeps its [n_tile, K] slice of W in shared memory for its whole life and only streams A
+//     (re-streaming W per tile from L2 was the first bottleneck measured, profiles/r01_v1_*).
+//   * the residual add of `x = LN(x + f(x))` (model_spec2midi.py:236,242) is folded into the accumulator by the
+//     tensor core: the residual tile arrives through the same TMA ring and is multiplied by a 64x64 identity block
+//     (exact: 1.0 * x accumulates in fp32), so the epilogue has no strided residual reads.
+//   * x3 mode (split operands): A = A_hi + A_lo, W = W_hi + W_lo stored side by side ([rows, 2K]); the accumulator
+//     receives A_hi W_hi + A_lo W_hi + A_hi W_lo, which carries ~22 mantissa bits with fp16 parts (fp32-class result).
 #pragma once
 #include "tc_common.cuh"
 
@@ -18,28 +25,28 @@ namespace tc {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 x 16-bit = 128 bytes = one swizzle atom row
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kChunkA = kBlockM * kBlockK * 2;          // 16 KB
+constexpr int kStageBlk = kBlockM * 64 * 2;             // one 128 x 64 output staging block, 16 KB
 
 enum Epi : int { EPI_STORE = 0, EPI_RELU = 1, EPI_LN = 2, EPI_HEADS = 3 };
 
 struct GemmParams {
   int m_tiles;            // M / 128
   int n_tiles;            // N / n_tile
-  int n_tile;             // UMMA N (multiple of 64, <= 256)
   int k_chunks;           // K / 64
+  int w_resident;         // 1: the CTA's W slice stays in shared memory; 0: W chunks stream through the ring with A
+  int n_stages;           // ring depth
+  int has_resid;          // EPI_LN: residual tile added through the identity MMA
+  int resid_period;       // > 0: residual row tile index = m_tile % resid_period (constant pitch-query table)
+  int x3;                 // split-operand mode (A/W/out/resid are [rows, 2*cols]: hi | lo)
+  int out_col0;           // first output column inside the output tensor
+  int a_lo_off, w_lo_off, out_lo_off;   // x3: column distance between the hi and lo halves of A / W / out
   const float* bias;      // [N]
-  // EPI_STORE / EPI_RELU / EPI_LN: 16-bit output [M, ldc]
-  void* out;
-  int ldc;
-  // EPI_LN
-  const void* resid16;    // 16-bit residual [M, H] (or nullptr when resid32 is used)
-  const float* resid32;   // fp32 residual table [resid_rows, H] indexed by row % resid_rows (constant pitch queries)
-  int resid_rows;
-  const float* gamma;
+  const float* gamma;     // EPI_LN
   const float* beta;
-  // EPI_HEADS: columns 0..V-1 velocity logits, V..V+2 onset / offset / mpe logits
+  // EPI_HEADS: columns 0..V-1 velocity logits, V..V+2 onset / offset / mpe logits; fp32 outputs
   float* onset;
   float* offset;
   float* mpe;
@@ -49,55 +56,96 @@ struct GemmParams {
   int n_frame, n_note;
 };
 
-__host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile) {
-  return 1024 /*align slack*/ + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)n_tile * kBlockK * 2) + 4096 /*LN exchange*/ + 256 /*barriers*/;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile, int k_chunks, int w_resident, int n_stages, int x3) {
+  size_t w = w_resident ? (size_t)n_tile * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : 0;
+  size_t stage = kChunkA + (w_resident ? 0 : (size_t)n_tile * kBlockK * 2);
+  return 1024 /*align*/ + w + (size_t)n_stages * stage + 8192 /*I64*/ + 2 * kStageBlk /*store staging*/ + 4096 /*LN exchange*/ + 512 /*barriers*/;
 }
 
-template <bool BF16, int EPI, int HALF_COLS>   // HALF_COLS = n_tile / 2 = columns each epilogue thread owns (multiple of 32)
+// HALVES x COLS = n_tile: every epilogue thread owns COLS consecutive accumulator columns of its row.
+template <bool BF16, int EPI, int HALVES, int COLS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r,
+            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmParams p) {
+  constexpr int n_tile = HALVES * COLS;
+  constexpr uint32_t w_chunk = (uint32_t)n_tile * kBlockK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int n_tile = HALF_COLS * 2;
-  const uint32_t a_bytes = kBlockM * kBlockK * 2, w_bytes = (uint32_t)n_tile * kBlockK * 2;
-  uint8_t* s_a = smem;
-  uint8_t* s_w = smem + kStages * a_bytes;
-  float* s_ln = reinterpret_cast<float*>(s_w + kStages * w_bytes);                      // [2 stats][2 halves][128 rows]
+  const int kc_w = p.k_chunks * (p.x3 ? 2 : 1);                         // W chunks held when resident
+  uint8_t* s_w = smem;                                                   // resident W: [kc_w][n_tile x 64]
+  uint8_t* s_ring = s_w + (p.w_resident ? (size_t)kc_w * w_chunk : 0);
+  const uint32_t stage_bytes = kChunkA + (p.w_resident ? 0 : w_chunk);
+  uint8_t* s_i64 = s_ring + (size_t)p.n_stages * stage_bytes;           // 64 x 64 identity, K-major SW128
+  uint8_t* s_out = s_i64 + 8192;                                         // [2 halves][128 x 64] staging
+  float* s_ln = reinterpret_cast<float*>(s_out + 2 * kStageBlk);        // [2 stats][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_ln) + 4096);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;  // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* full = bars;                 // [8]
+  uint64_t* empty = bars + 8;            // [8]
+  uint64_t* tfull = bars + 16;           // [2]
+  uint64_t* tempty = bars + 18;          // [2]
+  uint64_t* wbar = bars + 20;            // resident W landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // persistent schedule: this CTA owns n-tile `nt` and walks m-tiles mt0, mt0 + m_step, ...
+  const int nt = blockIdx.x % p.n_tiles;
+  const int mt0 = blockIdx.x / p.n_tiles;
+  const int m_step = gridDim.x / p.n_tiles;
+
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_w);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
+    if (p.has_resid) tma_prefetch_desc(&map_r);
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    mbar_init(wbar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (p.has_resid) {                     // identity block for the residual MMA: I[n][k] = (n == k), swizzled like a TMA tile
+    const uint16_t one = BF16 ? 0x3F80 : 0x3C00;
+    for (int i = threadIdx.x; i < 64 * 64; i += kGemmThreads) {
+      int n = i >> 6, k = i & 63;
+      uint32_t off = n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+      *reinterpret_cast<uint16_t*>(s_i64 + off) = (n == k) ? one : (uint16_t)0;
+    }
+    fence_proxy_async();
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int n_parts = p.x3 ? 3 : 1;                                      // (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo)
+  const int resid_chunks = p.has_resid ? (n_tile / 64) * (p.x3 ? 2 : 1) : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.w_resident) {
+        mbar_expect_tx(wbar, (uint32_t)kc_w * w_chunk);
+        for (int c = 0; c < kc_w; ++c)
+          tma_load_2d(s_w + (size_t)c * w_chunk, &map_w, (c < p.k_chunks ? c : c - p.k_chunks) * kBlockK + (c < p.k_chunks ? 0 : p.w_lo_off), nt * n_tile, wbar);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+      for (int mt = mt0; mt < p.m_tiles; mt += m_step) {
+        for (int part = 0; part < n_parts; ++part) {
+          const int a_col0 = (part == 1) ? p.a_lo_off : 0, w_col0 = (part == 2) ? p.w_lo_off : 0;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = s_ring + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full[stage], stage_bytes);
+            tma_load_2d(st, &map_a, a_col0 + kc * kBlockK, mt * kBlockM, &full[stage]);
+            if (!p.w_resident) tma_load_2d(st + kChunkA, &map_w, w_col0 + kc * kBlockK, nt * n_tile, &full[stage]);
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        const int r_row = (p.resid_period > 0 ? (mt % p.resid_period) : mt) * kBlockM;
+        for (int rc = 0; rc < resid_chunks; ++rc) {                      // residual tile (hi chunks, then lo chunks)
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], a_bytes + w_bytes);
-          tma_load_2d(s_a + stage * a_bytes, &map_a, kc * kBlockK, mt * kBlockM, &full[stage]);
-          tma_load_2d(s_w + stage * w_bytes, &map_w, kc * kBlockK, nt * n_tile, &full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          uint8_t* st = s_ring + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full[stage], kChunkA);
+          tma_load_2d(st, &map_r, (rc % (n_tile / 64)) * 64 + (rc >= n_tile / 64 ? p.out_lo_off : 0), r_row, &full[stage]);
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -105,27 +153,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBlockM, n_tile, BF16, false, false);
+      const uint32_t idesc64 = make_idesc(kBlockM, 64, BF16, false, false);
+      const uint32_t i64_addr = smem_u32(s_i64);
+      if (p.w_resident) { mbar_wait(wbar, 0); fence_after_sync(); }
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
         const int ab = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[ab], aphase ^ 1);             // epilogue has drained this accumulator buffer
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + ab * 256;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        uint32_t first = 1;
+        for (int part = 0; part < n_parts; ++part) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&full[stage], phase);
+            fence_after_sync();
+            const uint32_t a_addr = smem_u32(s_ring + (size_t)stage * stage_bytes);
+            const uint32_t w_addr = p.w_resident ? smem_u32(s_w + (size_t)(kc + (part == 2 ? p.k_chunks : 0)) * w_chunk) : a_addr + kChunkA;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma_f16(d_tmem, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(w_addr + k * 32, 16, 1024, kSwz128), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(&empty[stage]);                 // frees the ring slot when these MMAs retire
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        for (int rc = 0; rc < resid_chunks; ++rc) {     // acc[:, 64j .. 64j+63] += R[:, chunk] * I64
           mbar_wait(&full[stage], phase);
           fence_after_sync();
-          const uint32_t a_addr = smem_u32(s_a + stage * a_bytes), w_addr = smem_u32(s_w + stage * w_bytes);
+          const uint32_t a_addr = smem_u32(s_ring + (size_t)stage * stage_bytes);
+          const uint32_t col = (uint32_t)(rc % (n_tile / 64)) * 64;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024, kSwz128);
-            const uint64_t dw = make_sdesc(w_addr + k * 32, 16, 1024, kSwz128);
-            umma_f16(d_tmem, da, dw, idesc, (kc | k) != 0);
-          }
-          umma_commit(&empty[stage]);                   // frees the smem stage when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem + col, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(i64_addr + k * 32, 16, 1024, kSwz128), idesc64, 1u);
+          umma_commit(&empty[stage]);
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[ab]);                        // accumulator complete
       }
@@ -136,98 +201,147 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
+    const bool active = half < HALVES;
+    const int half_tid = (ew & 3) * 32 + lane;          // 0..127 inside the half
+    uint8_t* my_stage = s_out + half * kStageBlk;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+    for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
       const int ab = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull[ab], aphase);
       fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + half * HALF_COLS;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + half * COLS;
       const long long row = (long long)mt * kBlockM + row_in_tile;
-      const int col_base = nt * n_tile + half * HALF_COLS;      // global output column of this thread's first value
+      const int col_base = nt * n_tile + half * COLS;           // column of this thread's first value inside [0, N)
 
       if (EPI == EPI_STORE || EPI == EPI_RELU) {
-        uint32_t* orow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldc + col_base);
+        if (active) {
 #pragma unroll 1
-        for (int c = 0; c < HALF_COLS / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
+          for (int blk = 0; blk < COLS / 64; ++blk) {
+            uint32_t pk[32], pl[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v0 = __uint_as_float(r[2 * j]) + __ldg(p.bias + col_base + c * 32 + 2 * j);
-            float v1 = __uint_as_float(r[2 * j + 1]) + __ldg(p.bias + col_base + c * 32 + 2 * j + 1);
-            if (EPI == EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            pk[j] = Op16<BF16>::pack(v0, v1);
-          }
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld32(t_row + blk * 64 + c * 32, r);
+              tmem_ld_wait();
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col_base + blk * 64 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(orow + c * 16 + j * 4) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-      } else if (EPI == EPI_LN) {
-        // v = acc + bias + residual, kept in registers (HALF_COLS values); LayerNorm over the full row of 2*HALF_COLS
-        float v[HALF_COLS];
-        const int H = 2 * HALF_COLS;
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < HALF_COLS / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_ld_wait();
-          if (p.resid16) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.resid16) + row * H + col_base + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = rp[j];
-              uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[c * 32 + j * 8 + 2 * e] = __uint_as_float(r[j * 8 + 2 * e]) + Op16<BF16>::lo(w4[e]);
-                v[c * 32 + j * 8 + 2 * e + 1] = __uint_as_float(r[j * 8 + 2 * e + 1]) + Op16<BF16>::hi(w4[e]);
+              for (int j = 0; j < 8; ++j) {
+                float4 b4 = __ldg(bp + j);
+                float v0 = __uint_as_float(r[4 * j]) + b4.x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+                float v2 = __uint_as_float(r[4 * j + 2]) + b4.z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                if (EPI == EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                const uint32_t h0 = Op16<BF16>::pack(v0, v1), h1 = Op16<BF16>::pack(v2, v3);
+                pk[c * 16 + 2 * j] = h0; pk[c * 16 + 2 * j + 1] = h1;
+                if (p.x3) {
+                  pl[c * 16 + 2 * j] = Op16<BF16>::pack(v0 - Op16<BF16>::lo(h0), v1 - Op16<BF16>::hi(h0));
+                  pl[c * 16 + 2 * j + 1] = Op16<BF16>::pack(v2 - Op16<BF16>::lo(h1), v3 - Op16<BF16>::hi(h1));
+                }
               }
             }
-          } else {
-            const float* rp = p.resid32 + (row % p.resid_rows) * H + col_base + c * 32;
+            const int n_pass = p.x3 ? 2 : 1;
+            for (int pass = 0; pass < n_pass; ++pass) {
+              // staging buffer must have been read by the previous TMA store before it is overwritten
+              if (half_tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              named_bar_sync(2 + half, 128);
+              uint8_t* dst = my_stage + row_in_tile * 128;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]) + __ldg(rp + j);
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(dst + ((q ^ (row_in_tile & 7)) << 4)) =
+                    pass ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              fence_proxy_async();
+              named_bar_sync(2 + half, 128);
+              if (half_tid == 0) {
+                const int oc = p.out_col0 + col_base + blk * 64 + (pass ? p.out_lo_off : 0);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_o)),
+                             "r"(smem_u32(my_stage)), "r"(oc), "r"(mt * kBlockM)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
           }
+        }
+      } else if (EPI == EPI_LN) {
+        // v = acc (+ residual already accumulated by the identity MMA) + bias; LayerNorm over the full row of n_tile values
+        float v[COLS];
+        float sum = 0.f;
+        if (active) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[c * 32 + j] += __ldg(p.bias + col_base + c * 32 + j);
-            sum += v[c * 32 + j];
+          for (int c = 0; c < COLS / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c * 32, r);
+            tmem_ld_wait();
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b4 = __ldg(bp + j);
+              v[c * 32 + 4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[c * 32 + 4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+              v[c * 32 + 4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[c * 32 + 4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+              sum += (v[c * 32 + 4 * j] + v[c * 32 + 4 * j + 1]) + (v[c * 32 + 4 * j + 2] + v[c * 32 + 4 * j + 3]);
+            }
           }
         }
         // the accumulator is in registers now: hand the TMEM buffer back before the row statistics
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        s_ln[half * 128 + row_in_tile] = sum;
+        if (active) s_ln[half * 128 + row_in_tile] = sum;
         named_bar_sync(1, kEpiWarps * 32);
-        const float mean = (s_ln[row_in_tile] + s_ln[128 + row_in_tile]) / (float)H;
+        float mean = s_ln[row_in_tile];
+        if (HALVES == 2) mean += s_ln[128 + row_in_tile];
+        mean *= (1.f / (float)n_tile);
         float sq = 0.f;
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) { float d = v[j] - mean; sq = fmaf(d, d, sq); }
-        s_ln[256 + half * 128 + row_in_tile] = sq;
+          for (int j = 0; j < COLS; ++j) { float d = v[j] - mean; sq = fmaf(d, d, sq); }
+          s_ln[256 + half * 128 + row_in_tile] = sq;
+        }
         named_bar_sync(1, kEpiWarps * 32);
-        const float rstd = rsqrtf((s_ln[256 + row_in_tile] + s_ln[384 + row_in_tile]) / (float)H + 1e-5f);
-        uint32_t* orow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldc + col_base);
+        float var = s_ln[256 + row_in_tile];
+        if (HALVES == 2) var += s_ln[384 + row_in_tile];
+        const float rstd = rsqrtf(var * (1.f / (float)n_tile) + 1e-5f);
+        if (active) {
+#pragma unroll 1
+          for (int blk = 0; blk < COLS / 64; ++blk) {
+            uint32_t pk[32], pl[32];
+            const float4* gp = reinterpret_cast<const float4*>(p.gamma + col_base + blk * 64);
+            const float4* bp = reinterpret_cast<const float4*>(p.beta + col_base + blk * 64);
 #pragma unroll
-        for (int j = 0; j < HALF_COLS / 8; ++j) {
-          uint32_t pk[4];
+            for (int j = 0; j < 16; ++j) {
+              float4 g4 = __ldg(gp + j), b4 = __ldg(bp + j);
+              const float y0 = (v[blk * 64 + 4 * j] - mean) * rstd * g4.x + b4.x, y1 = (v[blk * 64 + 4 * j + 1] - mean) * rstd * g4.y + b4.y;
+              const float y2 = (v[blk * 64 + 4 * j + 2] - mean) * rstd * g4.z + b4.z, y3 = (v[blk * 64 + 4 * j + 3] - mean) * rstd * g4.w + b4.w;
+              const uint32_t h0 = Op16<BF16>::pack(y0, y1), h1 = Op16<BF16>::pack(y2, y3);
+              pk[2 * j] = h0; pk[2 * j + 1] = h1;
+              if (p.x3) {
+                pl[2 * j] = Op16<BF16>::pack(y0 - Op16<BF16>::lo(h0), y1 - Op16<BF16>::hi(h0));
+                pl[2 * j + 1] = Op16<BF16>::pack(y2 - Op16<BF16>::lo(h1), y3 - Op16<BF16>::hi(h1));
+              }
+            }
+            const int n_pass = p.x3 ? 2 : 1;
+            for (int pass = 0; pass < n_pass; ++pass) {
+              if (half_tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              named_bar_sync(2 + half, 128);
+              uint8_t* dst = my_stage + row_in_tile * 128;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int c0 = j * 8 + 2 * e;
-            float y0 = (v[c0] - mean) * rstd * __ldg(p.gamma + col_base + c0) + __ldg(p.beta + col_base + c0);
-            float y1 = (v[c0 + 1] - mean) * rstd * __ldg(p.gamma + col_base + c0 + 1) + __ldg(p.beta + col_base + c0 + 1);
-            pk[e] = Op16<BF16>::pack(y0, y1);
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(dst + ((q ^ (row_in_tile & 7)) << 4)) =
+                    pass ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              fence_proxy_async();
+              named_bar_sync(2 + half, 128);
+              if (half_tid == 0) {
+                const int oc = p.out_col0 + col_base + blk * 64 + (pass ? p.out_lo_off : 0);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_o)),
+                             "r"(smem_u32(my_stage)), "r"(oc), "r"(mt * kBlockM)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
           }
-          *reinterpret_cast<uint4*>(orow + j * 4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         named_bar_sync(1, kEpiWarps * 32);              // s_ln is reused by the next tile
         continue;                                       // tempty already signalled
-      } else {                                          // EPI_HEADS
+      } else {                                          // EPI_HEADS (direct fp32 stores)
         long long orow_idx = row;
         if (p.time_major) {
           int f = (int)(row % p.n_frame);
@@ -235,25 +349,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           int n = (int)(bn % p.n_note);
           orow_idx = ((bn / p.n_note) * p.n_frame + f) * p.n_note + n;
         }
+        if (active) {
 #pragma unroll 1
-        for (int c = 0; c < HALF_COLS / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_ld_wait();
-          const int c0 = col_base + c * 32;
-          if (c0 + 32 <= p.n_vel) {
-            if (p.velocity) {
-              float4* dst = reinterpret_cast<float4*>(p.velocity + orow_idx * p.n_vel + c0);
+          for (int c = 0; c < COLS / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c * 32, r);
+            tmem_ld_wait();
+            const int c0 = col_base + c * 32;
+            if (c0 + 32 <= p.n_vel) {
+              if (p.velocity) {
+                float4* dst = reinterpret_cast<float4*>(p.velocity + orow_idx * p.n_vel + c0);
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(__uint_as_float(r[4 * j]) + __ldg(p.bias + c0 + 4 * j), __uint_as_float(r[4 * j + 1]) + __ldg(p.bias + c0 + 4 * j + 1),
-                                     __uint_as_float(r[4 * j + 2]) + __ldg(p.bias + c0 + 4 * j + 2), __uint_as_float(r[4 * j + 3]) + __ldg(p.bias + c0 + 4 * j + 3));
+                for (int j = 0; j < 8; ++j) {
+                  float4 b4 = __ldg(bp + j);
+                  dst[j] = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
+                                       __uint_as_float(r[4 * j + 3]) + b4.w);
+                }
+              }
+            } else if (c0 == p.n_vel) {
+              float* dsts[3] = {p.onset, p.offset, p.mpe};
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                if (dsts[j]) dsts[j][orow_idx] = 1.f / (1.f + expf(-(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j))));
             }
-          } else if (c0 == p.n_vel) {
-            float* dsts[3] = {p.onset, p.offset, p.mpe};
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              if (dsts[j]) dsts[j][orow_idx] = 1.f / (1.f + expf(-(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j))));
           }
         }
       }
@@ -261,6 +380,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[ab]);
     }
+    if (active && half_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
   }
   fence_before_sync();
   __syncthreads();

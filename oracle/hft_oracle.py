@@ -52,9 +52,14 @@ class Oracle:
         self.dtype = dtype
 
     # ---- building blocks -------------------------------------------------------------------
+    @staticmethod
+    def _t(tag, role):
+        """operand tag handed to the gemm_in hook: '<site>:<role>' with role in a/w (linear), q/k/p/v (attention)"""
+        return None if tag is None else tag + ':' + role
+
     def linear(self, x, prefix, tag=None):
         w, b = self.sd[prefix + ".weight"], self.sd[prefix + ".bias"]
-        return self.q(x, tag) @ self.q(w, tag).t() + b
+        return self.q(x, self._t(tag, 'a')) @ self.q(w, self._t(tag, 'w')).t() + b
 
     def ln(self, x, prefix):
         return self.st(F.layer_norm(x, (self.hid,), self.sd[prefix + ".weight"], self.sd[prefix + ".bias"], 1e-5))
@@ -66,9 +71,9 @@ class Oracle:
         Q = self.linear(q_in, prefix + ".fc_q", tag).view(S, Lq, self.h, d).permute(0, 2, 1, 3)
         K = self.linear(kv_in, prefix + ".fc_k", tag).view(S, -1, self.h, d).permute(0, 2, 1, 3)
         V = self.linear(kv_in, prefix + ".fc_v", tag).view(S, -1, self.h, d).permute(0, 2, 1, 3)
-        energy = (self.q(Q, tag) @ self.q(K, tag).transpose(-1, -2)) / math.sqrt(d)
+        energy = (self.q(Q, self._t(tag, 'q')) @ self.q(K, self._t(tag, 'k')).transpose(-1, -2)) / math.sqrt(d)
         attn = torch.softmax(energy, dim=-1)
-        x = self.q(attn, tag) @ self.q(V, tag)
+        x = self.q(attn, self._t(tag, 'p')) @ self.q(V, self._t(tag, 'v'))
         x = x.permute(0, 2, 1, 3).reshape(S, Lq, H)
         return self.linear(x, prefix + ".fc_o", tag), attn
 
