@@ -39,8 +39,10 @@ def reduced(golden_dir):
     return model.cuda().eval(), g
 
 
-def test_reduced_matches_reference_golden_fp32(reduced):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_reduced_matches_reference_golden_fp32(reduced, precision):
     model, g = reduced
+    model.precision = precision
     out = model(torch.from_numpy(g["spec"]).cuda())
     assert [tuple(o.shape) for o in out] == [(2, 128, 88)] * 3 + [(2, 128, 88, 128), (2, 128, 2, 88, 256)] + [(2, 128, 88)] * 3 + [(2, 128, 88, 128)]
     _golden_check(out, g, TOL_FP32)
@@ -63,20 +65,24 @@ def test_non_contiguous_batch1_view(reduced, golden_dir):
         assert torch.equal(x, y)
 
 
-def test_paper_size_matches_reference_golden_fp32(golden_dir):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_paper_size_matches_reference_golden_fp32(golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "hft_paper.npz"))
     cs = json.loads(str(g["checksums"]))
     model = hft.build_model(hft.default_config(), 256, 512, 3, 4, seed=1234, device="cpu")
     for k, v in model.state_dict().items():
         assert abs(float(v.double().sum()) - cs[k][0]) <= 1e-9 * max(1.0, cs[k][1]), k
     model = model.cuda()
+    model.precision = precision
     out = model(torch.from_numpy(g["spec"]).cuda())
     _golden_check(out, g, TOL_FP32)
 
 
-def test_batch_and_chunking_vs_oracle(reduced, golden_dir):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_batch_and_chunking_vs_oracle(reduced, golden_dir, precision):
     """B = 5 with max_batch 2 (internal chunk loop, ragged last chunk) against the CPU oracle on the same inputs."""
     model, g = reduced
+    model.precision = precision
     rng = np.random.default_rng(3)
     spec = torch.from_numpy((rng.standard_normal((5, 256, 192)) * 3 - 8).astype(np.float32))
     orc = ho.Oracle({k: v.cpu() for k, v in model.state_dict().items()}, 2)(spec)
