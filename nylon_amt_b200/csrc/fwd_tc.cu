@@ -365,25 +365,31 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
 }
 
 template <bool BF16, int DH, int LK, bool PROBS, bool X3>
-static int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
+static int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const AttnParams& ap, long long items,
+                         cudaStream_t s) {
   auto kern = attn_kernel<BF16, DH, LK, PROBS, X3>;
   static bool attr_set = false;
   if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DH, LK, X3>::total)); attr_set = true; }
-  kern<<<(unsigned)items, 128, AttnSmem<DH, LK, X3>::total, s>>>(mq, mk, mv, ap);
+  kern<<<(unsigned)items, kAttnThreads, AttnSmem<DH, LK, X3>::total, s>>>(mq, mk, mv, mo, ap);
   return HFT_OK;
 }
 
 template <bool BF16, int DH, bool X3>
-static int launch_attn_dh(int LK, bool probs, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, long long items, cudaStream_t s) {
-  if (LK == 256) return probs ? launch_attn_t<BF16, DH, 256, true, X3>(mq, mk, mv, ap, items, s) : launch_attn_t<BF16, DH, 256, false, X3>(mq, mk, mv, ap, items, s);
-  if (LK == 128) return launch_attn_t<BF16, DH, 128, false, X3>(mq, mk, mv, ap, items, s);
-  if (LK == 96) return launch_attn_t<BF16, DH, 96, false, X3>(mq, mk, mv, ap, items, s);
+static int launch_attn_dh(int LK, bool probs, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const AttnParams& ap,
+                          long long items, cudaStream_t s) {
+  if (LK == 256) return probs ? launch_attn_t<BF16, DH, 256, true, X3>(mq, mk, mv, mo, ap, items, s) : launch_attn_t<BF16, DH, 256, false, X3>(mq, mk, mv, mo, ap, items, s);
+  if (LK == 128) return launch_attn_t<BF16, DH, 128, false, X3>(mq, mk, mv, mo, ap, items, s);
+  if (LK == 96) return launch_attn_t<BF16, DH, 96, false, X3>(mq, mk, mv, mo, ap, items, s);
   set_error("tc attention: unsupported key tile %d", LK);
   return HFT_ERR_UNSUPPORTED;
 }
 
-static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams ap, long long n_seq, cudaStream_t s) {
+// mo: tensor map of the ctx tensor (box 64 x 128) for the TMA-store epilogue, or nullptr for direct stores
+static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap* mo, AttnParams ap,
+                       long long n_seq, cudaStream_t s) {
   ap.heads = heads;
+  ap.tma_store = (mo != nullptr && dh == 64 && ap.lq % 128 == 0) ? 1 : 0;
+  const CUtensorMap& mo_ = mo ? *mo : mq;
   ap.q_tiles = (ap.lq + 127) / 128;
   ap.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
   const long long items = n_seq * heads * ap.q_tiles;
@@ -392,11 +398,11 @@ static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUte
   const bool probs = ap.probs != nullptr;
   if (x3) {                                             // split mode is fp16 only
     HFT_REQUIRE(!bf16, HFT_ERR_UNSUPPORTED, "x3 attention is built for fp16 parts");
-    if (dh == 64) return launch_attn_dh<false, 64, true>(LK, probs, mq, mkv, mkv, ap, items, s);
-    return launch_attn_dh<false, 32, true>(LK, probs, mq, mkv, mkv, ap, items, s);
+    if (dh == 64) return launch_attn_dh<false, 64, true>(LK, probs, mq, mkv, mkv, mo_, ap, items, s);
+    return launch_attn_dh<false, 32, true>(LK, probs, mq, mkv, mkv, mo_, ap, items, s);
   }
-  if (dh == 64) return bf16 ? launch_attn_dh<true, 64, false>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 64, false>(LK, probs, mq, mkv, mkv, ap, items, s);
-  return bf16 ? launch_attn_dh<true, 32, false>(LK, probs, mq, mkv, mkv, ap, items, s) : launch_attn_dh<false, 32, false>(LK, probs, mq, mkv, mkv, ap, items, s);
+  if (dh == 64) return bf16 ? launch_attn_dh<true, 64, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s) : launch_attn_dh<false, 64, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s);
+  return bf16 ? launch_attn_dh<true, 32, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s) : launch_attn_dh<false, 32, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s);
 }
 
 #define HFT_TRY(x) do { int _rc = (x); if (_rc != HFT_OK) return _rc; } while (0)
@@ -417,7 +423,7 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
   a.q_lo_off = q_width;            // hi-block width of the Q tensor (3H for fused QKV buffers, H for the pitch-query table)
   a.kv_lo_off = 3 * m->H;
   a.ctx = t.CTX; a.ld_ctx = m->H * t.cm(); a.ctx_lo_off = m->H;
-  return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, a, n_seq, s);
+  return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }
 
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
@@ -579,6 +585,9 @@ extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void*
   HFT_TRY(make_map(&mkv, qkv16, n_seq * L, 3 * H, 3 * H, dh, LK, bf16 != 0));
   AttnParams a{};
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.ctx = ctx16; a.ld_ctx = H; a.probs = probs;
+  CUtensorMap mo;
+  const bool use_tma = dh == 64 && L % 128 == 0;
+  if (use_tma) HFT_TRY(make_map(&mo, ctx16, n_seq * L, H, H, 64, 128, bf16 != 0));
   reset_launch_count();
-  return launch_attn(heads, dh, bf16 != 0, false, LK, mq, mkv, a, n_seq, (cudaStream_t)stream);
+  return launch_attn(heads, dh, bf16 != 0, false, LK, mq, mkv, use_tma ? &mo : nullptr, a, n_seq, (cudaStream_t)stream);
 }
