@@ -185,7 +185,10 @@ struct TcState {
 
 struct TcBoth { TcState st[3]; };   // [0] = fp16, [1] = bf16, [2] = fp16 x3
 
-static int n_tile_for(int N) {
+// UMMA N of a projection: LayerNorm epilogues need the whole row in one tile; otherwise the widest tile dividing N
+// (measured: in x3 mode a 256-wide streamed W with a deep A ring beats a 128-wide resident W with a 3-deep A ring).
+static int n_tile_for(int N, bool x3 = false, bool full_row = false) {
+  if (full_row) return (N == 256 || N == 128 || N == 64) ? N : 0;
   const int cands[3] = {256, 128, 64};
   for (int c : cands)
     if (N % c == 0) return c;
@@ -215,18 +218,18 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
   uint16_t* p = t.warena;
   auto take = [&](size_t n) { uint16_t* r = p; p += (n + 127) & ~(size_t)127; return r; };
   int rc = HFT_OK;
-  auto mk = [&](W16& w, const float* src, int N, int K, const float* bias) {
+  auto mk = [&](W16& w, const float* src, int N, int K, const float* bias, bool full_row = false) {
     w.ptr = take((size_t)N * K * cm);
-    w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
+    w.N = N; w.K = K; w.n_tile = n_tile_for(N, x3, full_row); w.bias = bias;
     if (bf) cvt_rows<true>(src, N, N, K, N, x3, w.ptr, s); else cvt_rows<false>(src, N, N, K, N, x3, w.ptr, s);
     int r = make_map(&w.map, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile, bf);
     if (r != HFT_OK) rc = r;
   };
   auto mk_enc = [&](TcLayer& L, const EncLayerW& lw, const FusedAttn& f) {
     mk(L.qkv, f.qkv_w, 3 * H, H, f.qkv_b);
-    mk(L.o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b]);
+    mk(L.o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b], true);
     mk(L.w1, m->w[lw.ff.w1], P, H, m->w[lw.ff.b1]);
-    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2]);
+    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2], true);
   };
   t.enc.resize(m->enc.size()); t.tim.resize(m->tim.size()); t.dec.resize(m->dec.size());
   for (size_t i = 0; i < m->enc.size(); ++i) mk_enc(t.enc[i], m->enc[i], m->enc_qkv[i]);
@@ -234,13 +237,13 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
   auto mk_dec = [&](TcDecLayer& L, const DecLayerW& lw, const FusedAttn* sa, const FusedAttn& kv) {
     if (sa) {
       mk(L.sa_qkv, sa->qkv_w, 3 * H, H, sa->qkv_b);
-      mk(L.sa_o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b]);
+      mk(L.sa_o, m->w[lw.sa.o_w], H, H, m->w[lw.sa.o_b], true);
     }
     mk(L.ca_q, m->w[lw.ca.q_w], H, H, m->w[lw.ca.q_b]);
     mk(L.ca_kv, kv.qkv_w, 2 * H, H, kv.qkv_b);
-    mk(L.ca_o, m->w[lw.ca.o_w], H, H, m->w[lw.ca.o_b]);
+    mk(L.ca_o, m->w[lw.ca.o_w], H, H, m->w[lw.ca.o_b], true);
     mk(L.w1, m->w[lw.ff.w1], P, H, m->w[lw.ff.b1]);
-    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2]);
+    mk(L.w2, m->w[lw.ff.w2], H, P, m->w[lw.ff.b2], true);
   };
   mk_dec(t.dec0, m->dec0, nullptr, m->dec_ca_kv[0]);
   for (size_t i = 0; i < m->dec.size(); ++i) mk_dec(t.dec[i], m->dec[i], &m->dec_sa_qkv[i], m->dec_ca_kv[i + 1]);
@@ -340,14 +343,22 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   gp.bias = w.bias;
   gp.has_resid = (epi == EPI_LN && mr != nullptr) ? 1 : 0;
   if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
-  // W stays resident when its slice fits beside a 3-deep A ring, the identity block and the store staging
+  // W stays resident when its slice fits beside a >= 3-deep A ring, the identity block and the store staging;
+  // otherwise W chunks stream through a 2-deep ring of their own.
   const size_t w_bytes = (size_t)w.n_tile * w.K * 2 * (gp.x3 ? 2 : 1);
-  gp.w_resident = w_bytes <= 128 * 1024 ? 1 : 0;
-  gp.n_stages = gp.w_resident ? (w_bytes <= 64 * 1024 ? 6 : 3) : 3;
+  const size_t w_chunk = (size_t)w.n_tile * kBlockK * 2;
+  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + 2 * kStageBlk + 4096 + 512;
+  const size_t budget = 227 * 1024;
+  gp.w_resident = (w_bytes + fixed + 3 * kChunkA <= budget) ? 1 : 0;
+  gp.w_stages = gp.w_resident ? 0 : 2;
+  const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
+  long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
+  gp.a_stages = a_st > 8 ? 8 : (int)a_st;
+  HFT_REQUIRE(gp.a_stages >= (gp.x3 ? 3 : 2), HFT_ERR_UNSUPPORTED, "tc gemm: no room for the operand rings (N tile %d, K %d)", w.n_tile, w.K);
   static int sms = num_sms();
   int grid = (sms / gp.n_tiles) * gp.n_tiles;
   if (grid > gp.m_tiles * gp.n_tiles) grid = gp.m_tiles * gp.n_tiles;
-  const size_t smem = gemm_smem_bytes(w.n_tile, gp.k_chunks, gp.w_resident, gp.n_stages, gp.x3);
+  const size_t smem = gemm_smem_bytes(w.n_tile, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid);
   HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "tc gemm: %zu bytes of shared memory needed", smem);
   const CUtensorMap& o = mo ? *mo : ma;
   const CUtensorMap& r = mr ? *mr : ma;
@@ -562,7 +573,7 @@ extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16
   HFT_REQUIRE(M % 128 == 0 && K % 64 == 0 && N % 64 == 0 && (epi != 2 || ((N == 64 || N == 128 || N == 256) && resid16 && gamma && beta)),
               HFT_ERR_UNSUPPORTED, "hft_tc_linear: M=%lld N=%d K=%d epi=%d unsupported", (long long)M, N, K, epi);
   W16 w;
-  w.ptr = (uint16_t*)w16; w.N = N; w.K = K; w.n_tile = n_tile_for(N); w.bias = bias;
+  w.ptr = (uint16_t*)w16; w.N = N; w.K = K; w.n_tile = n_tile_for(N, false, epi == 2); w.bias = bias;
   CUtensorMap ma, mo, mr;
   HFT_TRY(make_map(&ma, a16, M, K, K, kBlockK, kBlockM, bf16 != 0));
   HFT_TRY(make_map(&w.map, w16, N, K, K, kBlockK, w.n_tile, bf16 != 0));

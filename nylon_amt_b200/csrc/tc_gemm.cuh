@@ -37,7 +37,8 @@ struct GemmParams {
   int n_tiles;            // N / n_tile
   int k_chunks;           // K / 64
   int w_resident;         // 1: the CTA's W slice stays in shared memory; 0: W chunks stream through the ring with A
-  int n_stages;           // ring depth
+  int a_stages;           // depth of the A ring (16 KB slots: A chunks and residual chunks)
+  int w_stages;           // depth of the W ring (n_tile x 64 slots; 0 when W is resident)
   int has_resid;          // EPI_LN: residual tile added through the identity MMA
   int resid_period;       // > 0: residual row tile index = m_tile % resid_period (constant pitch-query table)
   int x3;                 // split-operand mode (A/W/out/resid are [rows, 2*cols]: hi | lo)
@@ -56,10 +57,9 @@ struct GemmParams {
   int n_frame, n_note;
 };
 
-__host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile, int k_chunks, int w_resident, int n_stages, int x3) {
-  size_t w = w_resident ? (size_t)n_tile * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : 0;
-  size_t stage = kChunkA + (w_resident ? 0 : (size_t)n_tile * kBlockK * 2);
-  return 1024 /*align*/ + w + (size_t)n_stages * stage + 8192 /*I64*/ + 2 * kStageBlk /*store staging*/ + 4096 /*LN exchange*/ + 512 /*barriers*/;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid) {
+  size_t w = w_resident ? (size_t)n_tile * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : (size_t)w_stages * n_tile * kBlockK * 2;
+  return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + 2 * kStageBlk /*store staging*/ + 4096 /*LN exchange*/ + 512 /*barriers*/;
 }
 
 // HALVES x COLS = n_tile: every epilogue thread owns COLS consecutive accumulator columns of its row.
@@ -72,19 +72,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int kc_w = p.k_chunks * (p.x3 ? 2 : 1);                         // W chunks held when resident
-  uint8_t* s_w = smem;                                                   // resident W: [kc_w][n_tile x 64]
-  uint8_t* s_ring = s_w + (p.w_resident ? (size_t)kc_w * w_chunk : 0);
-  const uint32_t stage_bytes = kChunkA + (p.w_resident ? 0 : w_chunk);
-  uint8_t* s_i64 = s_ring + (size_t)p.n_stages * stage_bytes;           // 64 x 64 identity, K-major SW128
-  uint8_t* s_out = s_i64 + 8192;                                         // [2 halves][128 x 64] staging
+  uint8_t* s_w = smem;                                                   // resident W: [kc_w][n_tile x 64]; else the W ring
+  uint8_t* s_a = s_w + (p.w_resident ? (size_t)kc_w * w_chunk : (size_t)p.w_stages * w_chunk);   // A ring: a_stages x 16 KB
+  uint8_t* s_i64 = s_a + (size_t)p.a_stages * kChunkA;                   // 64 x 64 identity, K-major SW128 (only with a residual)
+  uint8_t* s_out = s_i64 + (p.has_resid ? 8192 : 0);                     // [2 halves][128 x 64] staging
   float* s_ln = reinterpret_cast<float*>(s_out + 2 * kStageBlk);        // [2 stats][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_ln) + 4096);
-  uint64_t* full = bars;                 // [8]
-  uint64_t* empty = bars + 8;            // [8]
-  uint64_t* tfull = bars + 16;           // [2]
-  uint64_t* tempty = bars + 18;          // [2]
-  uint64_t* wbar = bars + 20;            // resident W landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* full_a = bars;               // [8]
+  uint64_t* empty_a = bars + 8;          // [8]
+  uint64_t* full_w = bars + 16;          // [4]
+  uint64_t* empty_w = bars + 20;         // [4]
+  uint64_t* tfull = bars + 24;           // [2]
+  uint64_t* tempty = bars + 26;          // [2]
+  uint64_t* wbar = bars + 28;            // resident W landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // persistent schedule: this CTA owns n-tile `nt` and walks m-tiles mt0, mt0 + m_step, ...
@@ -95,7 +96,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
     if (p.has_resid) tma_prefetch_desc(&map_r);
-    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < p.w_stages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -114,9 +116,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_parts = p.x3 ? 3 : 1;                                      // (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo)
   const int resid_chunks = p.has_resid ? (n_tile / 64) * (p.x3 ? 2 : 1) : 0;
 
+  // Per k-chunk the operand schedule is (x3):  Wh, Ah, Al, Wl  ->  MMA(Ah,Wh)  MMA(Al,Wh) [free Al, Wh]  MMA(Ah,Wl) [free Ah, Wl]
+  // (single product):                          W,  A           ->  MMA(A,W)   [free A, W]
+  // so every A chunk is fetched once per tile and every streamed W chunk once per tile.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -125,28 +129,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int c = 0; c < kc_w; ++c)
           tma_load_2d(s_w + (size_t)c * w_chunk, &map_w, (c < p.k_chunks ? c : c - p.k_chunks) * kBlockK + (c < p.k_chunks ? 0 : p.w_lo_off), nt * n_tile, wbar);
       }
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      auto load_a = [&](const CUtensorMap* map, int col, int row) {
+        mbar_wait(&empty_a[sa], pa ^ 1);
+        mbar_expect_tx(&full_a[sa], kChunkA);
+        tma_load_2d(s_a + (size_t)sa * kChunkA, map, col, row, &full_a[sa]);
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+      };
+      auto load_w = [&](int col) {
+        mbar_wait(&empty_w[sw], pw ^ 1);
+        mbar_expect_tx(&full_w[sw], w_chunk);
+        tma_load_2d(s_w + (size_t)sw * w_chunk, &map_w, col, nt * n_tile, &full_w[sw]);
+        if (++sw == p.w_stages) { sw = 0; pw ^= 1; }
+      };
       for (int mt = mt0; mt < p.m_tiles; mt += m_step) {
-        for (int part = 0; part < n_parts; ++part) {
-          const int a_col0 = (part == 1) ? p.a_lo_off : 0, w_col0 = (part == 2) ? p.w_lo_off : 0;
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* st = s_ring + (size_t)stage * stage_bytes;
-            mbar_expect_tx(&full[stage], stage_bytes);
-            tma_load_2d(st, &map_a, a_col0 + kc * kBlockK, mt * kBlockM, &full[stage]);
-            if (!p.w_resident) tma_load_2d(st + kChunkA, &map_w, w_col0 + kc * kBlockK, nt * n_tile, &full[stage]);
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          if (!p.w_resident) load_w(kc * kBlockK);
+          load_a(&map_a, kc * kBlockK, mt * kBlockM);
+          if (p.x3) {
+            load_a(&map_a, p.a_lo_off + kc * kBlockK, mt * kBlockM);
+            if (!p.w_resident) load_w(p.w_lo_off + kc * kBlockK);
           }
         }
         const int r_row = (p.resid_period > 0 ? (mt % p.resid_period) : mt) * kBlockM;
-        for (int rc = 0; rc < resid_chunks; ++rc) {                      // residual tile (hi chunks, then lo chunks)
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* st = s_ring + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full[stage], kChunkA);
-          tma_load_2d(st, &map_r, (rc % (n_tile / 64)) * 64 + (rc >= n_tile / 64 ? p.out_lo_off : 0), r_row, &full[stage]);
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-        }
+        for (int rc = 0; rc < resid_chunks; ++rc)                        // residual tile (hi chunks, then lo chunks)
+          load_a(&map_r, (rc % (n_tile / 64)) * 64 + (rc >= n_tile / 64 ? p.out_lo_off : 0), r_row);
       }
     }
   } else if (warp == 1) {
@@ -156,41 +164,71 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const uint32_t idesc64 = make_idesc(kBlockM, 64, BF16, false, false);
       const uint32_t i64_addr = smem_u32(s_i64);
       if (p.w_resident) { mbar_wait(wbar, 0); fence_after_sync(); }
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
       int it = 0;
+      uint32_t first = 1;
+      auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          umma_f16(d, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(b_addr + k * 32, 16, 1024, kSwz128), id, first ? 0u : 1u);
+          first = 0;
+        }
+      };
+      auto wait_a = [&]() -> uint32_t {                  // next A-ring slot, filled
+        mbar_wait(&full_a[sa], pa);
+        fence_after_sync();
+        return smem_u32(s_a + (size_t)sa * kChunkA);
+      };
+      auto free_a = [&]() {                              // release the oldest held A slot once the MMAs issued so far retire
+        umma_commit(&empty_a[sa]);
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+      };
+      auto wait_w = [&]() -> uint32_t {
+        mbar_wait(&full_w[sw], pw);
+        fence_after_sync();
+        return smem_u32(s_w + (size_t)sw * w_chunk);
+      };
+      auto free_w = [&]() {
+        umma_commit(&empty_w[sw]);
+        if (++sw == p.w_stages) { sw = 0; pw ^= 1; }
+      };
       for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
         const int ab = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[ab], aphase ^ 1);             // epilogue has drained this accumulator buffer
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + ab * 256;
-        uint32_t first = 1;
-        for (int part = 0; part < n_parts; ++part) {
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&full[stage], phase);
-            fence_after_sync();
-            const uint32_t a_addr = smem_u32(s_ring + (size_t)stage * stage_bytes);
-            const uint32_t w_addr = p.w_resident ? smem_u32(s_w + (size_t)(kc + (part == 2 ? p.k_chunks : 0)) * w_chunk) : a_addr + kChunkA;
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              umma_f16(d_tmem, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(w_addr + k * 32, 16, 1024, kSwz128), idesc, first ? 0u : 1u);
-              first = 0;
-            }
-            umma_commit(&empty[stage]);                 // frees the ring slot when these MMAs retire
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        first = 1;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const uint32_t wh = p.w_resident ? smem_u32(s_w + (size_t)kc * w_chunk) : wait_w();
+          const uint32_t ah = wait_a();
+          mma4(d_tmem, ah, wh, idesc);
+          if (!p.x3) {
+            free_a();
+            if (!p.w_resident) free_w();
+          } else {
+            // the A ring is consumed in order: Ah occupies slot sa, Al slot sa+1
+            const int sa_hi = sa;
+            const uint32_t pa_hi = pa;
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            const uint32_t al = wait_a();
+            mma4(d_tmem, al, wh, idesc);
+            umma_commit(&empty_a[sa]);                  // Al done
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            if (!p.w_resident) free_w();                // Wh done
+            const uint32_t wl = p.w_resident ? smem_u32(s_w + (size_t)(p.k_chunks + kc) * w_chunk) : wait_w();
+            mma4(d_tmem, ah, wl, idesc);
+            umma_commit(&empty_a[sa_hi]);               // Ah done
+            (void)pa_hi;
+            if (!p.w_resident) free_w();                // Wl done
           }
         }
         for (int rc = 0; rc < resid_chunks; ++rc) {     // acc[:, 64j .. 64j+63] += R[:, chunk] * I64
-          mbar_wait(&full[stage], phase);
-          fence_after_sync();
-          const uint32_t a_addr = smem_u32(s_ring + (size_t)stage * stage_bytes);
+          const uint32_t a_addr = wait_a();
           const uint32_t col = (uint32_t)(rc % (n_tile / 64)) * 64;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d_tmem + col, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(i64_addr + k * 32, 16, 1024, kSwz128), idesc64, 1u);
-          umma_commit(&empty[stage]);
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          mma4(d_tmem + col, a_addr, i64_addr, idesc64);
+          free_a();
         }
         umma_commit(&tfull[ab]);                        // accumulator complete
       }
