@@ -177,7 +177,8 @@ struct TcState {
   uint16_t* ws = nullptr;
   uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
   CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands / TMA-store targets, box 64 x 128
-  CUtensorMap mQKV_o, mDQ_o, mPosRep;               // store targets of the projections; repeated pitch-query table (residual of layer zero)
+  CUtensorMap sX, sHID, sT, sU, sQKV, sDQ;          // TMA-store targets of the projections, box 64 x 32 (one epilogue warp)
+  CUtensorMap mPosRep;                              // repeated pitch-query table (residual of layer zero)
   uint16_t* pos_rep = nullptr;                      // [11*128, H]: pos_embedding_freq[row % 88] (lcm(88,128) = 1408 rows)
   CUtensorMap mQKV_q, mQKV_kv, mDQ_q, mDQ_kv, mQ0;  // attention operands, box dh x {128, Lk}
   int cm() const { return x3 ? 2 : 1; }
@@ -302,8 +303,12 @@ static int ensure_ws(Model* m, TcState& t, int B) {
   chk(make_map(&t.mDQ_q, t.DQ, Rd, h3, h3, dh, 128, bf));
   chk(make_map(&t.mDQ_kv, t.DQ, Rd, h3, h3, dh, 96, bf));
   chk(make_map(&t.mQ0, t.q0_16, 128, h1, h1, dh, 128, bf));
-  chk(make_map(&t.mQKV_o, t.QKV, Re, h3, h3, 64, 128, bf));
-  chk(make_map(&t.mDQ_o, t.DQ, Rd, h3, h3, 64, 128, bf));
+  chk(make_map(&t.sX, t.X, Re, h1, h1, 64, 32, bf));
+  chk(make_map(&t.sHID, t.HID, Re, p1, p1, 64, 32, bf));
+  chk(make_map(&t.sT, t.T, Rd, h1, h1, 64, 32, bf));
+  chk(make_map(&t.sU, t.U, Rd, h1, h1, 64, 32, bf));
+  chk(make_map(&t.sQKV, t.QKV, Re, h3, h3, 64, 32, bf));
+  chk(make_map(&t.sDQ, t.DQ, Rd, h3, h3, 64, 32, bf));
   chk(make_map(&t.mPosRep, t.pos_rep, 11 * 128, h1, h1, 64, 128, bf));
   if (rc != HFT_OK) return rc;
   t.ws_batch = B;
@@ -311,10 +316,10 @@ static int ensure_ws(Model* m, TcState& t, int B) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-template <bool BF16, int EPI, int HALVES, int COLS>
+template <bool BF16, int EPI, int NT>
 static int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp, int grid,
                          size_t smem, cudaStream_t s) {
-  auto kern = gemm_kernel<BF16, EPI, HALVES, COLS>;
+  auto kern = gemm_kernel<BF16, EPI, NT>;
   static bool attr_set = false;
   if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
   kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, mr, mo, gp);
@@ -324,16 +329,16 @@ static int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUt
 template <bool BF16, int EPI>
 static int launch_gemm_e(int n_tile, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp,
                          int grid, size_t smem, cudaStream_t s) {
-  if (EPI == EPI_HEADS) return launch_gemm_t<BF16, EPI_HEADS, 2, 96>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 256) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 2, 128>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 128) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 2, 64>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 64) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 1, 64>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (EPI == EPI_HEADS) return launch_gemm_t<BF16, EPI_HEADS, 192>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 256) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 256>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 128) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 128>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 64) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 64>(ma, mw, mr, mo, gp, grid, smem, s);
   set_error("tc gemm: unsupported tile width %d", n_tile);
   return HFT_ERR_UNSUPPORTED;
 }
 
-// out: tensor map of the output tensor (box 64 x 128) for the TMA-store epilogues; resid: tensor map of the residual
-// (box 64 x 128) for EPI_LN (added by the identity MMA).
+// out: STORE tensor map of the output tensor (box 64 x 32: one epilogue warp's rows); resid: LOAD tensor map of the
+// residual (box 64 x 128) for EPI_LN (added by the identity MMA).
 static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, long long M, GemmParams gp, const CUtensorMap* mo,
                        const CUtensorMap* mr, cudaStream_t s) {
   HFT_REQUIRE(M % kBlockM == 0 && w.K % kBlockK == 0 && w.n_tile > 0, HFT_ERR_UNSUPPORTED, "tc gemm: M=%lld K=%d N=%d unsupported", M, w.K, w.N);
@@ -347,7 +352,7 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   // otherwise W chunks stream through a 2-deep ring of their own.
   const size_t w_bytes = (size_t)w.n_tile * w.K * 2 * (gp.x3 ? 2 : 1);
   const size_t w_chunk = (size_t)w.n_tile * kBlockK * 2;
-  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + 2 * kStageBlk + 4096 + 512;
+  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * (gp.x3 ? 2 : 1) * kWarpStage + kConstBytes + 512;
   const size_t budget = 227 * 1024;
   gp.w_resident = (w_bytes + fixed + 3 * kChunkA <= budget) ? 1 : 0;
   gp.w_stages = gp.w_resident ? 0 : 2;
@@ -438,17 +443,17 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
 }
 
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
-static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& mqkv_o, const CUtensorMap& mq,
+static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, const CUtensorMap& sqkv, const CUtensorMap& mq,
                             const CUtensorMap& mkv, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
   const int H = m->H, P = m->P;
   const long long R = S * L;
-  HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, mqkv_o, 0, 3 * H));
+  HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, sqkv, 0, 3 * H));
   AttnParams a{};
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
   HFT_TRY(attention(m, t, s, LK, mq, mkv, a, S, 3 * H));
-  HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, mx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
-  HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.mHID, 0, P));
-  HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, mx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
+  HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
+  HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P));
+  HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
   return HFT_OK;
 }
 
@@ -498,28 +503,28 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
   }
   for (size_t l = 0; l < m->enc.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.mQKV_o, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.sX, t.sQKV, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
-    HFT_TRY(linear(t, s, EPI_RELU, t.mT, lw.w1, Rd, t.mHID, 0, m->P));
-    HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, Rd, t.mT, 0, H, &t.mT, &ln, m));
+    HFT_TRY(linear(t, s, EPI_RELU, t.mT, lw.w1, Rd, t.sHID, 0, m->P));
+    HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, Rd, t.sT, 0, H, &t.mT, &ln, m));
     return HFT_OK;
   };
   auto cross = [&](const TcDecLayer& lw, const LnW& ln, bool zero, float* probs) -> int {
-    HFT_TRY(linear(t, s, EPI_STORE, t.mX, lw.ca_kv, Re, t.mQKV_o, H, 3 * H));   // K | V of the 256-bin memory at columns [H, 3H)
+    HFT_TRY(linear(t, s, EPI_STORE, t.mX, lw.ca_kv, Re, t.sQKV, H, 3 * H));   // K | V of the 256-bin memory at columns [H, 3H)
     AttnParams a{};
     a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = probs; a.q_col0 = 0;
     if (zero) {
       a.q_seq_rows = 0;
       HFT_TRY(attention(m, t, s, 256, t.mQ0, t.mQKV_kv, a, Se, H));
       // t = LN(pos_embedding_freq + fc_o(ctx)): the residual is the constant pitch-query table, period lcm(88,128)/128 = 11 tiles
-      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.mT, 0, H, &t.mPosRep, &ln, m, 11));
+      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.sT, 0, H, &t.mPosRep, &ln, m, 11));
     } else {
-      HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.ca_q, Rd, t.mDQ_o, 0, 3 * H));
+      HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.ca_q, Rd, t.sDQ, 0, 3 * H));
       a.q_seq_rows = NN;
       HFT_TRY(attention(m, t, s, 256, t.mDQ_q, t.mQKV_kv, a, Se, 3 * H));
-      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.mT, 0, H, &t.mT, &ln, m));
+      HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.sT, 0, H, &t.mT, &ln, m));
     }
     return HFT_OK;
   };
@@ -528,11 +533,11 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   for (size_t l = 0; l < m->dec.size(); ++l) {
     const TcDecLayer& lw = t.dec[l];
     const LnW& ln = m->dec[l].ln;
-    HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.sa_qkv, Rd, t.mDQ_o, 0, 3 * H));
+    HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.sa_qkv, Rd, t.sDQ, 0, 3 * H));
     AttnParams a{};
     a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H;
     HFT_TRY(attention(m, t, s, 96, t.mDQ_q, t.mDQ_kv, a, Se, 3 * H));
-    HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.sa_o, Rd, t.mT, 0, H, &t.mT, &ln, m));
+    HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.sa_o, Rd, t.sT, 0, H, &t.mT, &ln, m));
     HFT_TRY(cross(lw, ln, false, ((int)l + 2 == n_cross) ? o->attention : nullptr));
     HFT_TRY(ffn(lw, ln));
   }
@@ -550,7 +555,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, t.x3, total8, t.U);
   }
   for (size_t l = 0; l < m->tim.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.mDQ_o, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
   {
     GemmParams g{};
     g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
@@ -577,7 +582,7 @@ extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16
   CUtensorMap ma, mo, mr;
   HFT_TRY(make_map(&ma, a16, M, K, K, kBlockK, kBlockM, bf16 != 0));
   HFT_TRY(make_map(&w.map, w16, N, K, K, kBlockK, w.n_tile, bf16 != 0));
-  HFT_TRY(make_map(&mo, out16, M, N, N, 64, 128, bf16 != 0));
+  HFT_TRY(make_map(&mo, out16, M, N, N, 64, 32, bf16 != 0));
   if (epi == 2) HFT_TRY(make_map(&mr, resid16, M, N, N, 64, 128, bf16 != 0));
   GemmParams g{};
   g.gamma = gamma; g.beta = beta;

@@ -115,5 +115,31 @@ struct Op16<false> {
   __device__ static __forceinline__ float hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
 };
 
+// hi = round16(v), lo = round16(v - hi) for a pair of values (x3 split operands).  fp16: the residual is one mixed-precision
+// FMA per element (fma.rn.f32.f16 -> FHFMA with .H0/.H1 selectors), so a pair costs 2 packs + 2 FMAs.
+template <bool BF16>
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = Op16<BF16>::pack(a, b);
+  if (BF16) {
+    lo = Op16<BF16>::pack(a - Op16<BF16>::lo(hi), b - Op16<BF16>::hi(hi));
+  } else {
+    const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16), m1 = 0xBC00;   // -1.0h
+    float l0, l1;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l0) : "h"(h0), "h"(m1), "f"(a));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l1) : "h"(h1), "h"(m1), "f"(b));
+    lo = Op16<BF16>::pack(l0, l1);
+  }
+}
+
+// TMA tile store shared -> global (bulk group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 }  // namespace tc
 }  // namespace hft

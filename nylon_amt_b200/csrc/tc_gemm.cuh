@@ -3,9 +3,13 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, mbarrier ring of A (and W) chunks)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
 //                               two 256-column accumulator buffers so tile i+1's MMAs overlap tile i's epilogue)
-//   warps 2..9  epilogue       (tcgen05.ld TMEM -> registers; warp w owns TMEM lanes 32*(w%4).., column half (w-2)/4;
-//                               bias / ReLU / LayerNorm / sigmoid heads; results staged in swizzled shared memory
-//                               and written with TMA stores so that HBM sees full 128-byte lines)
+//   warps 2..9  epilogue       two warpgroups; warpgroup g drains accumulator buffer g (tiles of parity g), one thread per
+//                               tile row (TMEM lane) and the whole row of n_tile columns, so LayerNorm needs no cross-thread
+//                               exchange.  tcgen05.ld TMEM -> registers (LayerNorm: one statistics pass and one output
+//                               pass over TMEM, nothing held in registers across them); bias / gamma / beta come from
+//                               shared memory; bias / ReLU / LayerNorm / sigmoid heads; every warp stages its own
+//                               32-row x 64-column blocks in swizzled shared memory and writes them with its own TMA
+//                               stores (no CTA-wide barrier anywhere in the epilogue)
 //
 // A and W are 16-bit (bf16 or fp16), K-major.  Every GEMM of the model has K in {64..512} and N <= 768: per 128-row
 // tile it moves 128*K*2 bytes of A against 2*128*N*K flops, so it is bound by HBM/L2 bytes, not by the tensor pipe.
@@ -28,7 +32,8 @@ constexpr int kBlockK = 64;            // 64 x 16-bit = 128 bytes = one swizzle 
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kChunkA = kBlockM * kBlockK * 2;          // 16 KB
-constexpr int kStageBlk = kBlockM * 64 * 2;             // one 128 x 64 output staging block, 16 KB
+constexpr int kWarpStage = 32 * 64 * 2;                 // one warp's 32 x 64 output staging block (one TMA-store box), 4 KB
+constexpr int kConstBytes = 3 * 256 * 4;                // bias | gamma | beta of this CTA's column slice
 
 enum Epi : int { EPI_STORE = 0, EPI_RELU = 1, EPI_LN = 2, EPI_HEADS = 3 };
 
@@ -59,15 +64,16 @@ struct GemmParams {
 
 __host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid) {
   size_t w = w_resident ? (size_t)n_tile * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : (size_t)w_stages * n_tile * kBlockK * 2;
-  return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + 2 * kStageBlk /*store staging*/ + 4096 /*LN exchange*/ + 512 /*barriers*/;
+  return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + (size_t)kEpiWarps * (x3 ? 2 : 1) * kWarpStage /*store staging*/ +
+         kConstBytes + 512 /*barriers*/;
 }
 
-// HALVES x COLS = n_tile: every epilogue thread owns COLS consecutive accumulator columns of its row.
-template <bool BF16, int EPI, int HALVES, int COLS>
+// NT = n_tile: UMMA N and the number of accumulator columns every epilogue thread walks.  map_o: box 64 x 32 (one warp's rows).
+template <bool BF16, int EPI, int NT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r,
             const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmParams p) {
-  constexpr int n_tile = HALVES * COLS;
+  constexpr int n_tile = NT;
   constexpr uint32_t w_chunk = (uint32_t)n_tile * kBlockK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -75,9 +81,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint8_t* s_w = smem;                                                   // resident W: [kc_w][n_tile x 64]; else the W ring
   uint8_t* s_a = s_w + (p.w_resident ? (size_t)kc_w * w_chunk : (size_t)p.w_stages * w_chunk);   // A ring: a_stages x 16 KB
   uint8_t* s_i64 = s_a + (size_t)p.a_stages * kChunkA;                   // 64 x 64 identity, K-major SW128 (only with a residual)
-  uint8_t* s_out = s_i64 + (p.has_resid ? 8192 : 0);                     // [2 halves][128 x 64] staging
-  float* s_ln = reinterpret_cast<float*>(s_out + 2 * kStageBlk);        // [2 stats][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_ln) + 4096);
+  const int parts = p.x3 ? 2 : 1;
+  uint8_t* s_out = s_i64 + (p.has_resid ? 8192 : 0);                     // [8 warps][parts][32 x 64] staging
+  float* s_const = reinterpret_cast<float*>(s_out + (size_t)kEpiWarps * parts * kWarpStage);   // bias[NT] | gamma[NT] | beta[NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_const) + kConstBytes);
   uint64_t* full_a = bars;               // [8]
   uint64_t* empty_a = bars + 8;          // [8]
   uint64_t* full_w = bars + 16;          // [4]
@@ -98,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (p.has_resid) tma_prefetch_desc(&map_r);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps / 2); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -111,6 +118,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       *reinterpret_cast<uint16_t*>(s_i64 + off) = (n == k) ? one : (uint16_t)0;
     }
     fence_proxy_async();
+  }
+  for (int i = threadIdx.x; i < NT; i += kGemmThreads) {   // per-column constants of this CTA's slice
+    s_const[i] = p.bias[nt * NT + i];
+    if (EPI == EPI_LN) { s_const[NT + i] = p.gamma[i]; s_const[2 * NT + i] = p.beta[i]; }
   }
   fence_before_sync();
   __syncthreads();
@@ -236,149 +247,140 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else {
     // ===================== epilogue =====================
     const int ew = warp - 2;
+    const int wg = ew >> 2;                             // accumulator buffer (= tile parity) drained by this warpgroup
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    const bool active = half < HALVES;
-    const int half_tid = (ew & 3) * 32 + lane;          // 0..127 inside the half
-    uint8_t* my_stage = s_out + half * kStageBlk;
+    uint8_t* my_stage = s_out + (size_t)ew * parts * kWarpStage;
+    const float* s_bias = s_const;
+    const float* s_gamma = s_const + NT;
+    const float* s_beta = s_const + 2 * NT;
+    const bool x3 = p.x3 != 0;
+    // one 32-row x 64-column block of this warp: registers -> swizzled staging -> TMA store (hi, and lo in x3 mode)
+    auto store_block = [&](const uint32_t (&pk)[32], const uint32_t (&pl)[32], int col, int row0) {
+      if (lane == 0) tma_store_wait_read();             // the previous stores of this warp have read the staging block
+      __syncwarp();
+      uint8_t* dst = my_stage + lane * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        *reinterpret_cast<uint4*>(dst + ((q ^ (lane & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        if (x3) *reinterpret_cast<uint4*>(dst + kWarpStage + ((q ^ (lane & 7)) << 4)) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_o, my_stage, col, row0);
+        if (x3) tma_store_2d(&map_o, my_stage + kWarpStage, col + p.out_lo_off, row0);
+        tma_store_commit();
+      }
+    };
     int it = 0;
     for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
-      const int ab = it & 1;
+      if ((it & 1) != wg) continue;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull[ab], aphase);
+      mbar_wait(&tfull[wg], aphase);
       fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * 256 + half * COLS;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * 256;
       const long long row = (long long)mt * kBlockM + row_in_tile;
-      const int col_base = nt * n_tile + half * COLS;           // column of this thread's first value inside [0, N)
+      const int row0 = mt * kBlockM + quarter * 32;             // first row of this warp's store boxes
+      const int col_base = p.out_col0 + nt * NT;                // first output column of this CTA's slice
 
       if (EPI == EPI_STORE || EPI == EPI_RELU) {
-        if (active) {
 #pragma unroll 1
-          for (int blk = 0; blk < COLS / 64; ++blk) {
-            uint32_t pk[32], pl[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld32(t_row + blk * 64 + c * 32, r);
-              tmem_ld_wait();
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col_base + blk * 64 + c * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 b4 = __ldg(bp + j);
-                float v0 = __uint_as_float(r[4 * j]) + b4.x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y;
-                float v2 = __uint_as_float(r[4 * j + 2]) + b4.z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w;
-                if (EPI == EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                const uint32_t h0 = Op16<BF16>::pack(v0, v1), h1 = Op16<BF16>::pack(v2, v3);
-                pk[c * 16 + 2 * j] = h0; pk[c * 16 + 2 * j + 1] = h1;
-                if (p.x3) {
-                  pl[c * 16 + 2 * j] = Op16<BF16>::pack(v0 - Op16<BF16>::lo(h0), v1 - Op16<BF16>::hi(h0));
-                  pl[c * 16 + 2 * j + 1] = Op16<BF16>::pack(v2 - Op16<BF16>::lo(h1), v3 - Op16<BF16>::hi(h1));
-                }
-              }
-            }
-            const int n_pass = p.x3 ? 2 : 1;
-            for (int pass = 0; pass < n_pass; ++pass) {
-              // staging buffer must have been read by the previous TMA store before it is overwritten
-              if (half_tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              named_bar_sync(2 + half, 128);
-              uint8_t* dst = my_stage + row_in_tile * 128;
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(dst + ((q ^ (row_in_tile & 7)) << 4)) =
-                    pass ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              fence_proxy_async();
-              named_bar_sync(2 + half, 128);
-              if (half_tid == 0) {
-                const int oc = p.out_col0 + col_base + blk * 64 + (pass ? p.out_lo_off : 0);
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_o)),
-                             "r"(smem_u32(my_stage)), "r"(oc), "r"(mt * kBlockM)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
-            }
+        for (int blk = 0; blk < NT / 64; ++blk) {
+          uint32_t pk[32], pl[32];
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + blk * 64, r0);
+          tmem_ld32(t_row + blk * 64 + 32, r1);
+          tmem_ld_wait();
+          if (blk == NT / 64 - 1) {                             // accumulator fully read: hand the TMEM buffer back
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[wg]);
           }
-        }
-      } else if (EPI == EPI_LN) {
-        // v = acc (+ residual already accumulated by the identity MMA) + bias; LayerNorm over the full row of n_tile values
-        float v[COLS];
-        float sum = 0.f;
-        if (active) {
 #pragma unroll
-          for (int c = 0; c < COLS / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c * 32, r);
-            tmem_ld_wait();
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+          for (int c = 0; c < 2; ++c) {
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + blk * 64 + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 b4 = __ldg(bp + j);
-              v[c * 32 + 4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[c * 32 + 4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-              v[c * 32 + 4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[c * 32 + 4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
-              sum += (v[c * 32 + 4 * j] + v[c * 32 + 4 * j + 1]) + (v[c * 32 + 4 * j + 2] + v[c * 32 + 4 * j + 3]);
+              const float4 b4 = bp[j];
+              const uint32_t* r = c ? r1 : r0;
+              float v0 = __uint_as_float(r[4 * j]) + b4.x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+              float v2 = __uint_as_float(r[4 * j + 2]) + b4.z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+              if (EPI == EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+              if (x3) {
+                split_pack<BF16>(v0, v1, pk[c * 16 + 2 * j], pl[c * 16 + 2 * j]);
+                split_pack<BF16>(v2, v3, pk[c * 16 + 2 * j + 1], pl[c * 16 + 2 * j + 1]);
+              } else {
+                pk[c * 16 + 2 * j] = Op16<BF16>::pack(v0, v1);
+                pk[c * 16 + 2 * j + 1] = Op16<BF16>::pack(v2, v3);
+              }
             }
           }
+          store_block(pk, pl, col_base + blk * 64, row0);
         }
-        // the accumulator is in registers now: hand the TMEM buffer back before the row statistics
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[ab]);
-        if (active) s_ln[half * 128 + row_in_tile] = sum;
-        named_bar_sync(1, kEpiWarps * 32);
-        float mean = s_ln[row_in_tile];
-        if (HALVES == 2) mean += s_ln[128 + row_in_tile];
-        mean *= (1.f / (float)n_tile);
-        float sq = 0.f;
-        if (active) {
-#pragma unroll
-          for (int j = 0; j < COLS; ++j) { float d = v[j] - mean; sq = fmaf(d, d, sq); }
-          s_ln[256 + half * 128 + row_in_tile] = sq;
-        }
-        named_bar_sync(1, kEpiWarps * 32);
-        float var = s_ln[256 + row_in_tile];
-        if (HALVES == 2) var += s_ln[384 + row_in_tile];
-        const float rstd = rsqrtf(var * (1.f / (float)n_tile) + 1e-5f);
-        if (active) {
+        continue;                                               // tempty already signalled
+      } else if (EPI == EPI_LN) {
+        // v = acc (+ residual already accumulated by the identity MMA) + bias; LayerNorm over the row of NT values.
+        // Pass 1 over TMEM: shifted one-pass statistics (shift = the row's first value, so E[d^2] - E[d]^2 does not cancel).
+        float shift = 0.f, sum = 0.f, sq = 0.f;
 #pragma unroll 1
-          for (int blk = 0; blk < COLS / 64; ++blk) {
-            uint32_t pk[32], pl[32];
-            const float4* gp = reinterpret_cast<const float4*>(p.gamma + col_base + blk * 64);
-            const float4* bp = reinterpret_cast<const float4*>(p.beta + col_base + blk * 64);
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 32);
+          if (c == 0) shift = __uint_as_float(r[0]) + s_bias[0];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float4 g4 = __ldg(gp + j), b4 = __ldg(bp + j);
-              const float y0 = (v[blk * 64 + 4 * j] - mean) * rstd * g4.x + b4.x, y1 = (v[blk * 64 + 4 * j + 1] - mean) * rstd * g4.y + b4.y;
-              const float y2 = (v[blk * 64 + 4 * j + 2] - mean) * rstd * g4.z + b4.z, y3 = (v[blk * 64 + 4 * j + 3] - mean) * rstd * g4.w + b4.w;
-              const uint32_t h0 = Op16<BF16>::pack(y0, y1), h1 = Op16<BF16>::pack(y2, y3);
-              pk[2 * j] = h0; pk[2 * j + 1] = h1;
-              if (p.x3) {
-                pl[2 * j] = Op16<BF16>::pack(y0 - Op16<BF16>::lo(h0), y1 - Op16<BF16>::hi(h0));
-                pl[2 * j + 1] = Op16<BF16>::pack(y2 - Op16<BF16>::lo(h1), y3 - Op16<BF16>::hi(h1));
-              }
-            }
-            const int n_pass = p.x3 ? 2 : 1;
-            for (int pass = 0; pass < n_pass; ++pass) {
-              if (half_tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              named_bar_sync(2 + half, 128);
-              uint8_t* dst = my_stage + row_in_tile * 128;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bp[j];
+            const float d0 = (__uint_as_float(r[4 * j]) + b4.x) - shift, d1 = (__uint_as_float(r[4 * j + 1]) + b4.y) - shift;
+            const float d2 = (__uint_as_float(r[4 * j + 2]) + b4.z) - shift, d3 = (__uint_as_float(r[4 * j + 3]) + b4.w) - shift;
+            sum += (d0 + d1) + (d2 + d3);
+            sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+          }
+        }
+        const float md = sum * (1.f / (float)NT);
+        const float var = fmaxf(sq * (1.f / (float)NT) - md * md, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        const float nmr = -(shift + md) * rstd;
+        // Pass 2 over TMEM: normalise, scale, split, store
+#pragma unroll 1
+        for (int blk = 0; blk < NT / 64; ++blk) {
+          uint32_t pk[32], pl[32];
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + blk * 64, r0);
+          tmem_ld32(t_row + blk * 64 + 32, r1);
+          tmem_ld_wait();
+          if (blk == NT / 64 - 1) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[wg]);
+          }
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(dst + ((q ^ (row_in_tile & 7)) << 4)) =
-                    pass ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              fence_proxy_async();
-              named_bar_sync(2 + half, 128);
-              if (half_tid == 0) {
-                const int oc = p.out_col0 + col_base + blk * 64 + (pass ? p.out_lo_off : 0);
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_o)),
-                             "r"(smem_u32(my_stage)), "r"(oc), "r"(mt * kBlockM)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          for (int c = 0; c < 2; ++c) {
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + blk * 64 + c * 32);
+            const float4* gp = reinterpret_cast<const float4*>(s_gamma + blk * 64 + c * 32);
+            const float4* ep = reinterpret_cast<const float4*>(s_beta + blk * 64 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = bp[j], g4 = gp[j], e4 = ep[j];
+              const uint32_t* r = c ? r1 : r0;
+              const float y0 = fmaf(fmaf(__uint_as_float(r[4 * j]) + b4.x, rstd, nmr), g4.x, e4.x);
+              const float y1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]) + b4.y, rstd, nmr), g4.y, e4.y);
+              const float y2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]) + b4.z, rstd, nmr), g4.z, e4.z);
+              const float y3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]) + b4.w, rstd, nmr), g4.w, e4.w);
+              if (x3) {
+                split_pack<BF16>(y0, y1, pk[c * 16 + 2 * j], pl[c * 16 + 2 * j]);
+                split_pack<BF16>(y2, y3, pk[c * 16 + 2 * j + 1], pl[c * 16 + 2 * j + 1]);
+              } else {
+                pk[c * 16 + 2 * j] = Op16<BF16>::pack(y0, y1);
+                pk[c * 16 + 2 * j + 1] = Op16<BF16>::pack(y2, y3);
               }
             }
           }
+          store_block(pk, pl, col_base + blk * 64, row0);
         }
-        named_bar_sync(1, kEpiWarps * 32);              // s_ln is reused by the next tile
-        continue;                                       // tempty already signalled
+        continue;                                               // tempty already signalled
       } else {                                          // EPI_HEADS (direct fp32 stores)
         long long orow_idx = row;
         if (p.time_major) {
@@ -387,38 +389,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           int n = (int)(bn % p.n_note);
           orow_idx = ((bn / p.n_note) * p.n_frame + f) * p.n_note + n;
         }
-        if (active) {
 #pragma unroll 1
-          for (int c = 0; c < COLS / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c * 32, r);
-            tmem_ld_wait();
-            const int c0 = col_base + c * 32;
-            if (c0 + 32 <= p.n_vel) {
-              if (p.velocity) {
-                float4* dst = reinterpret_cast<float4*>(p.velocity + orow_idx * p.n_vel + c0);
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int c0 = c * 32;
+          if (c0 + 32 <= p.n_vel) {
+            if (p.velocity) {
+              float4* dst = reinterpret_cast<float4*>(p.velocity + orow_idx * p.n_vel + c0);
+              const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float4 b4 = __ldg(bp + j);
-                  dst[j] = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
-                                       __uint_as_float(r[4 * j + 3]) + b4.w);
-                }
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = bp[j];
+                dst[j] = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
+                                     __uint_as_float(r[4 * j + 3]) + b4.w);
               }
-            } else if (c0 == p.n_vel) {
-              float* dsts[3] = {p.onset, p.offset, p.mpe};
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                if (dsts[j]) dsts[j][orow_idx] = 1.f / (1.f + expf(-(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j))));
             }
+          } else if (c0 == p.n_vel) {
+            float* dsts[3] = {p.onset, p.offset, p.mpe};
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (dsts[j]) dsts[j][orow_idx] = 1.f / (1.f + expf(-(__uint_as_float(r[j]) + s_bias[c0 + j])));
           }
         }
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[ab]);
+      if (lane == 0) mbar_arrive(&tempty[wg]);
     }
-    if (active && half_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
+    if (lane == 0) tma_store_wait_all();                // all stores landed before exit
   }
   fence_before_sync();
   __syncthreads();
