@@ -10,6 +10,7 @@
 
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 
 namespace hft {
@@ -154,7 +155,8 @@ __global__ void time_relayout16_kernel(const uint16_t* __restrict__ T, const flo
 struct W16 {            // one weight matrix [N, K] (x3: [N, 2K] = hi | lo) in 16-bit + its tensor map (box = 64 x n_tile)
   uint16_t* ptr = nullptr;
   int N = 0, K = 0, n_tile = 0;
-  CUtensorMap map;
+  CUtensorMap map;                  // box 64 x n_tile
+  CUtensorMap map2;                 // box 64 x n_tile/2: one CTA's half of the W rows in PAIR (cta_group::2) mode
   const float* bias = nullptr;
 };
 
@@ -225,6 +227,8 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
     if (bf) cvt_rows<true>(src, N, N, K, N, x3, w.ptr, s); else cvt_rows<false>(src, N, N, K, N, x3, w.ptr, s);
     int r = make_map(&w.map, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile, bf);
     if (r != HFT_OK) rc = r;
+    r = make_map(&w.map2, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile / 2, bf);
+    if (r != HFT_OK) rc = r;
   };
   auto mk_enc = [&](TcLayer& L, const EncLayerW& lw, const FusedAttn& f) {
     mk(L.qkv, f.qkv_w, 3 * H, H, f.qkv_b);
@@ -257,6 +261,8 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
     if (bf) pack_heads_kernel<true><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, x3, w.ptr, t.head_bias + which * 192);
     else pack_heads_kernel<false><<<(192 * H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]], m->w[idx[5]], m->w[idx[7]], V, H, 192, x3, w.ptr, t.head_bias + which * 192);
     int r = make_map(&w.map, w.ptr, 192, (long long)H * cm, (long long)H * cm, kBlockK, 192, bf);
+    if (r != HFT_OK) rc = r;
+    r = make_map(&w.map2, w.ptr, 192, (long long)H * cm, (long long)H * cm, kBlockK, 96, bf);
     if (r != HFT_OK) rc = r;
     return (int)HFT_OK;
   };
@@ -316,25 +322,57 @@ static int ensure_ws(Model* m, TcState& t, int B) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-template <bool BF16, int EPI, int NT>
+template <bool BF16, int EPI, int NT, bool PAIR>
 static int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp, int grid,
                          size_t smem, cudaStream_t s) {
-  auto kern = gemm_kernel<BF16, EPI, NT>;
+  auto kern = gemm_kernel<BF16, EPI, NT, PAIR>;
   static bool attr_set = false;
   if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
-  kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, mr, mo, gp);
+  if (!PAIR) {
+    kern<<<grid, kGemmThreads, smem, s>>>(ma, mw, mr, mo, gp);
+    return HFT_OK;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mr, mo, gp));
   return HFT_OK;
 }
 
-template <bool BF16, int EPI>
+template <bool BF16, int EPI, bool PAIR>
 static int launch_gemm_e(int n_tile, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp,
                          int grid, size_t smem, cudaStream_t s) {
-  if (EPI == EPI_HEADS) return launch_gemm_t<BF16, EPI_HEADS, 192>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 256) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 256>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 128) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 128>(ma, mw, mr, mo, gp, grid, smem, s);
-  if (n_tile == 64) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 64>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (EPI == EPI_HEADS) return launch_gemm_t<BF16, EPI_HEADS, 192, PAIR>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 256) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 256, PAIR>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 128) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 128, PAIR>(ma, mw, mr, mo, gp, grid, smem, s);
+  if (n_tile == 64) return launch_gemm_t<BF16, EPI == EPI_HEADS ? EPI_STORE : EPI, 64, PAIR>(ma, mw, mr, mo, gp, grid, smem, s);
   set_error("tc gemm: unsupported tile width %d", n_tile);
   return HFT_ERR_UNSUPPORTED;
+}
+
+template <bool BF16, bool PAIR>
+static int launch_gemm_p(int epi, int n_tile, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const GemmParams& gp,
+                         int grid, size_t smem, cudaStream_t s) {
+  return epi == EPI_STORE ? launch_gemm_e<BF16, EPI_STORE, PAIR>(n_tile, ma, mw, mr, mo, gp, grid, smem, s)
+       : epi == EPI_RELU  ? launch_gemm_e<BF16, EPI_RELU, PAIR>(n_tile, ma, mw, mr, mo, gp, grid, smem, s)
+       : epi == EPI_LN    ? launch_gemm_e<BF16, EPI_LN, PAIR>(n_tile, ma, mw, mr, mo, gp, grid, smem, s)
+                          : launch_gemm_e<BF16, EPI_HEADS, PAIR>(n_tile, ma, mw, mr, mo, gp, grid, smem, s);
+}
+
+// CTA pairs (cta_group::2) when M is a multiple of 256.  Default: split-operand mode only -- measured on B200 (r01): x3 GEMMs
+// 1406 -> 1168 ms per hour of audio (W streaming halves), single-product bf16 GEMMs 573 -> 591 ms (HBM-bound, W already resident).
+// HFT_TC_PAIR=0 / 1 forces single-CTA tiles / pairs everywhere.
+static bool pair_enabled(bool x3) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_PAIR"); v = !e ? 2 : (e[0] == '0' ? 0 : 1); }
+  return v == 2 ? x3 : v == 1;
 }
 
 // out: STORE tensor map of the output tensor (box 64 x 32: one epilogue warp's rows); resid: LOAD tensor map of the
@@ -342,42 +380,39 @@ static int launch_gemm_e(int n_tile, const CUtensorMap& ma, const CUtensorMap& m
 static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, long long M, GemmParams gp, const CUtensorMap* mo,
                        const CUtensorMap* mr, cudaStream_t s) {
   HFT_REQUIRE(M % kBlockM == 0 && w.K % kBlockK == 0 && w.n_tile > 0, HFT_ERR_UNSUPPORTED, "tc gemm: M=%lld K=%d N=%d unsupported", M, w.K, w.N);
-  gp.m_tiles = (int)(M / kBlockM);
+  static int sms = num_sms();
+  const bool pair = pair_enabled(gp.x3 != 0) && M % (2 * kBlockM) == 0 && sms >= 2 * (w.N / w.n_tile);
+  const int n_rows_w = pair ? w.n_tile / 2 : w.n_tile;
+  gp.m_tiles = (int)(M / (pair ? 2 * kBlockM : kBlockM));
   gp.n_tiles = w.N / w.n_tile;
   gp.k_chunks = w.K / kBlockK;
   gp.bias = w.bias;
   gp.has_resid = (epi == EPI_LN && mr != nullptr) ? 1 : 0;
   if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
-  // W stays resident when its slice fits beside a >= 3-deep A ring, the identity block and the store staging;
-  // otherwise W chunks stream through a 2-deep ring of their own.
-  const size_t w_bytes = (size_t)w.n_tile * w.K * 2 * (gp.x3 ? 2 : 1);
-  const size_t w_chunk = (size_t)w.n_tile * kBlockK * 2;
+  // W stays resident when this CTA's slice fits beside a >= 4-deep A ring, the identity block and the store staging;
+  // otherwise W chunks stream through a ring of their own.
+  const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (gp.x3 ? 2 : 1);
+  const size_t w_chunk = (size_t)n_rows_w * kBlockK * 2;
   const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * (gp.x3 ? 2 : 1) * kWarpStage + kConstBytes + 512;
   const size_t budget = 227 * 1024;
-  gp.w_resident = (w_bytes + fixed + 3 * kChunkA <= budget) ? 1 : 0;
-  gp.w_stages = gp.w_resident ? 0 : 2;
+  gp.w_resident = (w_bytes + fixed + 4 * kChunkA <= budget) ? 1 : 0;
+  gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? 4 : 2);
   const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
   long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
   gp.a_stages = a_st > 8 ? 8 : (int)a_st;
   HFT_REQUIRE(gp.a_stages >= (gp.x3 ? 3 : 2), HFT_ERR_UNSUPPORTED, "tc gemm: no room for the operand rings (N tile %d, K %d)", w.n_tile, w.K);
-  static int sms = num_sms();
-  int grid = (sms / gp.n_tiles) * gp.n_tiles;
-  if (grid > gp.m_tiles * gp.n_tiles) grid = gp.m_tiles * gp.n_tiles;
-  const size_t smem = gemm_smem_bytes(w.n_tile, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid);
+  const int units_max = pair ? sms / 2 : sms;
+  int units = (units_max / gp.n_tiles) * gp.n_tiles;
+  if (units > gp.m_tiles * gp.n_tiles) units = gp.m_tiles * gp.n_tiles;
+  const int grid = pair ? 2 * units : units;
+  const size_t smem = gemm_smem_bytes(n_rows_w, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid);
   HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "tc gemm: %zu bytes of shared memory needed", smem);
   const CUtensorMap& o = mo ? *mo : ma;
   const CUtensorMap& r = mr ? *mr : ma;
+  const CUtensorMap& mw = pair ? w.map2 : w.map;
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  if (bf16) {
-    return epi == EPI_STORE ? launch_gemm_e<true, EPI_STORE>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-         : epi == EPI_RELU  ? launch_gemm_e<true, EPI_RELU>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-         : epi == EPI_LN    ? launch_gemm_e<true, EPI_LN>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-                            : launch_gemm_e<true, EPI_HEADS>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s);
-  }
-  return epi == EPI_STORE ? launch_gemm_e<false, EPI_STORE>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-       : epi == EPI_RELU  ? launch_gemm_e<false, EPI_RELU>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-       : epi == EPI_LN    ? launch_gemm_e<false, EPI_LN>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s)
-                          : launch_gemm_e<false, EPI_HEADS>(w.n_tile, ma, w.map, r, o, gp, grid, smem, s);
+  if (pair) return bf16 ? launch_gemm_p<true, true>(epi, w.n_tile, ma, mw, r, o, gp, grid, smem, s) : launch_gemm_p<false, true>(epi, w.n_tile, ma, mw, r, o, gp, grid, smem, s);
+  return bf16 ? launch_gemm_p<true, false>(epi, w.n_tile, ma, mw, r, o, gp, grid, smem, s) : launch_gemm_p<false, false>(epi, w.n_tile, ma, mw, r, o, gp, grid, smem, s);
 }
 
 template <bool BF16, int DH, int LK, bool PROBS, bool X3>
@@ -582,6 +617,7 @@ extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16
   CUtensorMap ma, mo, mr;
   HFT_TRY(make_map(&ma, a16, M, K, K, kBlockK, kBlockM, bf16 != 0));
   HFT_TRY(make_map(&w.map, w16, N, K, K, kBlockK, w.n_tile, bf16 != 0));
+  HFT_TRY(make_map(&w.map2, w16, N, K, K, kBlockK, w.n_tile / 2, bf16 != 0));
   HFT_TRY(make_map(&mo, out16, M, N, N, 64, 32, bf16 != 0));
   if (epi == 2) HFT_TRY(make_map(&mr, resid16, M, N, N, 64, 128, bf16 != 0));
   GemmParams g{};

@@ -19,6 +19,10 @@
 //   * the residual add of `x = LN(x + f(x))` (model_spec2midi.py:236,242) is folded into the accumulator by the
 //     tensor core: the residual tile arrives through the same TMA ring and is multiplied by a 64x64 identity block
 //     (exact: 1.0 * x accumulates in fp32), so the epilogue has no strided residual reads.
+//   * PAIR mode (cta_group::2): two CTAs of a cluster share one UMMA tile of 256 rows.  Each CTA stages its own 128 rows
+//     of A and only HALF of the W rows (the tensor cores exchange the B halves), which halves the L2 -> shared-memory
+//     traffic and the shared-memory footprint of W; the even CTA issues the MMAs for both, every CTA runs its own
+//     epilogue on its own 128 accumulator rows.
 //   * x3 mode (split operands): A = A_hi + A_lo, W = W_hi + W_lo stored side by side ([rows, 2K]); the accumulator
 //     receives A_hi W_hi + A_lo W_hi + A_hi W_lo, which carries ~22 mantissa bits with fp16 parts (fp32-class result).
 #pragma once
@@ -38,7 +42,7 @@ constexpr int kConstBytes = 3 * 256 * 4;                // bias | gamma | beta o
 enum Epi : int { EPI_STORE = 0, EPI_RELU = 1, EPI_LN = 2, EPI_HEADS = 3 };
 
 struct GemmParams {
-  int m_tiles;            // M / 128
+  int m_tiles;            // M / 128 (PAIR: M / 256)
   int n_tiles;            // N / n_tile
   int k_chunks;           // K / 64
   int w_resident;         // 1: the CTA's W slice stays in shared memory; 0: W chunks stream through the ring with A
@@ -62,19 +66,22 @@ struct GemmParams {
   int n_frame, n_note;
 };
 
-__host__ __device__ constexpr size_t gemm_smem_bytes(int n_tile, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid) {
-  size_t w = w_resident ? (size_t)n_tile * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : (size_t)w_stages * n_tile * kBlockK * 2;
+// n_rows_w: W rows staged per CTA (n_tile, or n_tile / 2 in PAIR mode)
+__host__ __device__ constexpr size_t gemm_smem_bytes(int n_rows_w, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid) {
+  size_t w = w_resident ? (size_t)n_rows_w * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : (size_t)w_stages * n_rows_w * kBlockK * 2;
   return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + (size_t)kEpiWarps * (x3 ? 2 : 1) * kWarpStage /*store staging*/ +
          kConstBytes + 512 /*barriers*/;
 }
 
 // NT = n_tile: UMMA N and the number of accumulator columns every epilogue thread walks.  map_o: box 64 x 32 (one warp's rows).
-template <bool BF16, int EPI, int NT>
+template <bool BF16, int EPI, int NT, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r,
             const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmParams p) {
   constexpr int n_tile = NT;
-  constexpr uint32_t w_chunk = (uint32_t)n_tile * kBlockK * 2;
+  constexpr int n_rows_w = PAIR ? n_tile / 2 : n_tile;                   // W rows staged by this CTA
+  constexpr uint32_t w_chunk = (uint32_t)n_rows_w * kBlockK * 2;
+  constexpr uint32_t kCtas = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int kc_w = p.k_chunks * (p.x3 ? 2 : 1);                         // W chunks held when resident
@@ -95,27 +102,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // persistent schedule: this CTA owns n-tile `nt` and walks m-tiles mt0, mt0 + m_step, ...
-  const int nt = blockIdx.x % p.n_tiles;
-  const int mt0 = blockIdx.x / p.n_tiles;
-  const int m_step = gridDim.x / p.n_tiles;
+  // persistent schedule: this CTA (pair) owns n-tile `nt` and walks m-tiles mt0, mt0 + m_step, ...
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int nt = unit % p.n_tiles;
+  const int mt0 = unit / p.n_tiles;
+  const int m_step = units / p.n_tiles;
+  auto row_tile = [&](int mt) { return PAIR ? 2 * mt + (int)rank : mt; };   // this CTA's 128-row tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
     if (p.has_resid) tma_prefetch_desc(&map_r);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps / 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kCtas * (kEpiWarps / 2)); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   if (p.has_resid) {                     // identity block for the residual MMA: I[n][k] = (n == k), swizzled like a TMA tile
-    const uint16_t one = BF16 ? 0x3F80 : 0x3C00;
-    for (int i = threadIdx.x; i < 64 * 64; i += kGemmThreads) {
+    const uint16_t one = BF16 ? 0x3F80 : 0x3C00;   // PAIR: this CTA holds rows [32 rank, 32 rank + 32) of the 64 x 64 identity
+    const int n_off = PAIR ? 32 * (int)rank : 0;
+    for (int i = threadIdx.x; i < (PAIR ? 32 : 64) * 64; i += kGemmThreads) {
       int n = i >> 6, k = i & 63;
       uint32_t off = n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
-      *reinterpret_cast<uint16_t*>(s_i64 + off) = (n == k) ? one : (uint16_t)0;
+      *reinterpret_cast<uint16_t*>(s_i64 + off) = (n + n_off == k) ? one : (uint16_t)0;
     }
     fence_proxy_async();
   }
@@ -125,6 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
   fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int resid_chunks = p.has_resid ? (n_tile / 64) * (p.x3 ? 2 : 1) : 0;
@@ -135,44 +148,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // PAIR: the loads of both CTAs are counted on the LEADER's barriers (the leader alone waits on them and issues the MMAs)
+      auto load = [&](void* dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
+        if (PAIR) tma_load_2d_2cta(dst, map, col, row, map_to_rank(bar, 0)); else tma_load_2d(dst, map, col, row, bar);
+      };
+      const int w_row = nt * n_tile + (int)rank * n_rows_w;
       if (p.w_resident) {
-        mbar_expect_tx(wbar, (uint32_t)kc_w * w_chunk);
+        if (leader) mbar_expect_tx(wbar, kCtas * (uint32_t)kc_w * w_chunk);
         for (int c = 0; c < kc_w; ++c)
-          tma_load_2d(s_w + (size_t)c * w_chunk, &map_w, (c < p.k_chunks ? c : c - p.k_chunks) * kBlockK + (c < p.k_chunks ? 0 : p.w_lo_off), nt * n_tile, wbar);
+          load(s_w + (size_t)c * w_chunk, &map_w, (c < p.k_chunks ? c : c - p.k_chunks) * kBlockK + (c < p.k_chunks ? 0 : p.w_lo_off), w_row, wbar);
       }
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
       auto load_a = [&](const CUtensorMap* map, int col, int row) {
         mbar_wait(&empty_a[sa], pa ^ 1);
-        mbar_expect_tx(&full_a[sa], kChunkA);
-        tma_load_2d(s_a + (size_t)sa * kChunkA, map, col, row, &full_a[sa]);
+        if (leader) mbar_expect_tx(&full_a[sa], kCtas * kChunkA);
+        load(s_a + (size_t)sa * kChunkA, map, col, row, &full_a[sa]);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       };
       auto load_w = [&](int col) {
         mbar_wait(&empty_w[sw], pw ^ 1);
-        mbar_expect_tx(&full_w[sw], w_chunk);
-        tma_load_2d(s_w + (size_t)sw * w_chunk, &map_w, col, nt * n_tile, &full_w[sw]);
+        if (leader) mbar_expect_tx(&full_w[sw], kCtas * w_chunk);
+        load(s_w + (size_t)sw * w_chunk, &map_w, col, w_row, &full_w[sw]);
         if (++sw == p.w_stages) { sw = 0; pw ^= 1; }
       };
       for (int mt = mt0; mt < p.m_tiles; mt += m_step) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           if (!p.w_resident) load_w(kc * kBlockK);
-          load_a(&map_a, kc * kBlockK, mt * kBlockM);
+          load_a(&map_a, kc * kBlockK, row_tile(mt) * kBlockM);
           if (p.x3) {
-            load_a(&map_a, p.a_lo_off + kc * kBlockK, mt * kBlockM);
+            load_a(&map_a, p.a_lo_off + kc * kBlockK, row_tile(mt) * kBlockM);
             if (!p.w_resident) load_w(p.w_lo_off + kc * kBlockK);
           }
         }
-        const int r_row = (p.resid_period > 0 ? (mt % p.resid_period) : mt) * kBlockM;
+        const int r_row = (p.resid_period > 0 ? (row_tile(mt) % p.resid_period) : row_tile(mt)) * kBlockM;
         for (int rc = 0; rc < resid_chunks; ++rc)                        // residual tile (hi chunks, then lo chunks)
           load_a(&map_r, (rc % (n_tile / 64)) * 64 + (rc >= n_tile / 64 ? p.out_lo_off : 0), r_row);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBlockM, n_tile, BF16, false, false);
-      const uint32_t idesc64 = make_idesc(kBlockM, 64, BF16, false, false);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc(kCtas * kBlockM, n_tile, BF16, false, false);
+      const uint32_t idesc64 = make_idesc(kCtas * kBlockM, 64, BF16, false, false);
+      auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_2cta(bar); else umma_commit(bar); };
       const uint32_t i64_addr = smem_u32(s_i64);
       if (p.w_resident) { mbar_wait(wbar, 0); fence_after_sync(); }
       int sa = 0, sw = 0;
@@ -182,7 +201,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id) {
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          umma_f16(d, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(b_addr + k * 32, 16, 1024, kSwz128), id, first ? 0u : 1u);
+          const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), db = make_sdesc(b_addr + k * 32, 16, 1024, kSwz128);
+          if (PAIR) umma_f16_2cta(d, da, db, id, first ? 0u : 1u); else umma_f16(d, da, db, id, first ? 0u : 1u);
           first = 0;
         }
       };
@@ -192,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         return smem_u32(s_a + (size_t)sa * kChunkA);
       };
       auto free_a = [&]() {                              // release the oldest held A slot once the MMAs issued so far retire
-        umma_commit(&empty_a[sa]);
+        commit(&empty_a[sa]);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       };
       auto wait_w = [&]() -> uint32_t {
@@ -201,7 +221,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         return smem_u32(s_w + (size_t)sw * w_chunk);
       };
       auto free_w = [&]() {
-        umma_commit(&empty_w[sw]);
+        commit(&empty_w[sw]);
         if (++sw == p.w_stages) { sw = 0; pw ^= 1; }
       };
       for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
@@ -225,12 +245,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             const uint32_t al = wait_a();
             mma4(d_tmem, al, wh, idesc);
-            umma_commit(&empty_a[sa]);                  // Al done
+            commit(&empty_a[sa]);                  // Al done
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             if (!p.w_resident) free_w();                // Wh done
             const uint32_t wl = p.w_resident ? smem_u32(s_w + (size_t)(p.k_chunks + kc) * w_chunk) : wait_w();
             mma4(d_tmem, ah, wl, idesc);
-            umma_commit(&empty_a[sa_hi]);               // Ah done
+            commit(&empty_a[sa_hi]);               // Ah done
             (void)pa_hi;
             if (!p.w_resident) free_w();                // Wl done
           }
@@ -241,7 +261,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           mma4(d_tmem + col, a_addr, i64_addr, idesc64);
           free_a();
         }
-        umma_commit(&tfull[ab]);                        // accumulator complete
+        commit(&tfull[ab]);                        // accumulator complete
       }
     }
   } else {
@@ -273,6 +293,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         tma_store_commit();
       }
     };
+    // accumulator buffer drained: tell the MMA issuer (PAIR: the leader CTA's barrier collects both CTAs' warps)
+    auto release_acc = [&]() { if (PAIR) mbar_arrive_cluster(map_to_rank(&tempty[wg], 0)); else mbar_arrive(&tempty[wg]); };
     int it = 0;
     for (int mt = mt0; mt < p.m_tiles; mt += m_step, ++it) {
       if ((it & 1) != wg) continue;
@@ -280,8 +302,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tfull[wg], aphase);
       fence_after_sync();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * 256;
-      const long long row = (long long)mt * kBlockM + row_in_tile;
-      const int row0 = mt * kBlockM + quarter * 32;             // first row of this warp's store boxes
+      const long long row = (long long)row_tile(mt) * kBlockM + row_in_tile;
+      const int row0 = row_tile(mt) * kBlockM + quarter * 32;   // first row of this warp's store boxes
       const int col_base = p.out_col0 + nt * NT;                // first output column of this CTA's slice
 
       if (EPI == EPI_STORE || EPI == EPI_RELU) {
@@ -295,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (blk == NT / 64 - 1) {                             // accumulator fully read: hand the TMEM buffer back
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[wg]);
+            if (lane == 0) release_acc();
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -354,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (blk == NT / 64 - 1) {
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[wg]);
+            if (lane == 0) release_acc();
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -416,13 +438,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[wg]);
+      if (lane == 0) release_acc();
     }
     if (lane == 0) tma_store_wait_all();                // all stores landed before exit
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (PAIR) cluster_sync_all();          // no CTA of the pair leaves while the other may still signal its barriers / read its operands
+  if (warp == 1) { if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace tc
