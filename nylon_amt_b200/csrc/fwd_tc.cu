@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "model.h"
 #include "tc_attn.cuh"
+#include "tc_attn2.cuh"
 #include "tc_gemm.cuh"
 
 #include <cudaTypedefs.h>
@@ -179,7 +180,7 @@ struct TcState {
   uint16_t* ws = nullptr;
   uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
   CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands / TMA-store targets, box 64 x 128
-  CUtensorMap sX, sHID, sT, sU, sQKV, sDQ;          // TMA-store targets of the projections, box 64 x 32 (one epilogue warp)
+  CUtensorMap sX, sHID, sT, sU, sQKV, sDQ, sCTX;    // TMA-store targets (projections, attention context), box 64 x 32 (one epilogue warp)
   CUtensorMap mPosRep;                              // repeated pitch-query table (residual of layer zero)
   uint16_t* pos_rep = nullptr;                      // [11*128, H]: pos_embedding_freq[row % 88] (lcm(88,128) = 1408 rows)
   CUtensorMap mQKV_q, mQKV_kv, mDQ_q, mDQ_kv, mQ0;  // attention operands, box dh x {128, Lk}
@@ -315,6 +316,7 @@ static int ensure_ws(Model* m, TcState& t, int B) {
   chk(make_map(&t.sU, t.U, Rd, h1, h1, 64, 32, bf));
   chk(make_map(&t.sQKV, t.QKV, Re, h3, h3, 64, 32, bf));
   chk(make_map(&t.sDQ, t.DQ, Rd, h3, h3, 64, 32, bf));
+  chk(make_map(&t.sCTX, t.CTX, Re, h1, h1, 64, 32, bf));
   chk(make_map(&t.mPosRep, t.pos_rep, 11 * 128, h1, h1, 64, 128, bf));
   if (rc != HFT_OK) return rc;
   t.ws_batch = B;
@@ -389,13 +391,14 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   gp.bias = w.bias;
   gp.has_resid = (epi == EPI_LN && mr != nullptr) ? 1 : 0;
   if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
-  // W stays resident when this CTA's slice fits beside a >= 4-deep A ring, the identity block and the store staging;
-  // otherwise W chunks stream through a ring of their own.
+  // W stays resident when this CTA's slice fits beside a >= 3-deep A ring, the identity block and the store staging
+  // (measured r01, bf16 K = 256: resident W + 3 A slots 573 ms/h vs streamed W 665 ms/h); otherwise W chunks stream
+  // through a ring of their own.
   const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (gp.x3 ? 2 : 1);
   const size_t w_chunk = (size_t)n_rows_w * kBlockK * 2;
   const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * (gp.x3 ? 2 : 1) * kWarpStage + kConstBytes + 512;
   const size_t budget = 227 * 1024;
-  gp.w_resident = (w_bytes + fixed + 4 * kChunkA <= budget) ? 1 : 0;
+  gp.w_resident = (w_bytes + fixed + 3 * kChunkA <= budget) ? 1 : 0;
   gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? 4 : 2);
   const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
   long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
@@ -456,6 +459,56 @@ static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUte
   return bf16 ? launch_attn_dh<true, 32, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s) : launch_attn_dh<false, 32, false>(LK, probs, mq, mkv, mkv, mo_, ap, items, s);
 }
 
+// ---- pipelined attention (tc_attn2.cuh): dh = 64, no probabilities -------------------------------------------------------
+template <bool BF16, int NKEY, int NH, bool X3>
+static int launch_attn2_t(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const Attn2Params& ap, cudaStream_t s) {
+  auto kern = attn2_kernel<BF16, 64, NKEY, NH, X3>;
+  static bool attr_set = false;
+  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem<64, X3>::total)); attr_set = true; }
+  static int sms = num_sms();
+  const int grid = ap.n_rounds < sms ? ap.n_rounds : sms;
+  kern<<<grid, kAttn2Threads, Attn2Smem<64, X3>::total, s>>>(mq, mkv, mo, ap);
+  return HFT_OK;
+}
+
+template <bool BF16, bool X3>
+static int launch_attn2_k(int LK, const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const Attn2Params& ap, cudaStream_t s) {
+  if (LK == 256) return launch_attn2_t<BF16, 128, 2, X3>(mq, mkv, mo, ap, s);
+  if (LK == 128) return launch_attn2_t<BF16, 128, 1, X3>(mq, mkv, mo, ap, s);
+  if (LK == 96) return launch_attn2_t<BF16, 96, 1, X3>(mq, mkv, mo, ap, s);
+  set_error("tc attention: unsupported key tile %d", LK);
+  return HFT_ERR_UNSUPPORTED;
+}
+
+// mkv_unit: tensor map of the K/V tensor with box dh x 128 (LK 256 / 128) or dh x 96; mo: store map of ctx, box 64 x 32
+static int launch_attn2(int heads, bool bf16, bool x3, int LK, const CUtensorMap& mq, const CUtensorMap& mkv_unit, const CUtensorMap& mo, const AttnParams& a,
+                        long long n_seq, cudaStream_t s) {
+  Attn2Params ap{};
+  ap.lq = a.lq; ap.lk = a.lk; ap.q_seq_rows = a.q_seq_rows; ap.q_tiles = (a.lq + 127) / 128; ap.heads = heads;
+  ap.q_col0 = a.q_col0; ap.k_col0 = a.k_col0; ap.v_col0 = a.v_col0;
+  ap.scale_log2e = 1.4426950408889634f / sqrtf(64.f);
+  ap.ctx = a.ctx; ap.ld_ctx = a.ld_ctx; ap.q_lo_off = a.q_lo_off; ap.kv_lo_off = a.kv_lo_off; ap.ctx_lo_off = a.ctx_lo_off;
+  ap.tma_store = (a.lq % 128 == 0) ? 1 : 0;
+  const long long items = n_seq * heads * ap.q_tiles;
+  HFT_REQUIRE(items < (1ll << 30) && ap.q_tiles <= 2, HFT_ERR_UNSUPPORTED, "tc attention: %lld work items / %d query tiles unsupported", items, ap.q_tiles);
+  ap.n_items = (int)items;
+  ap.n_rounds = (int)((items + 1) / 2);
+  ap.shared_kv = ap.q_tiles == 2 ? 1 : 0;
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  if (x3) {
+    HFT_REQUIRE(!bf16, HFT_ERR_UNSUPPORTED, "x3 attention is built for fp16 parts");
+    return launch_attn2_k<false, true>(LK, mq, mkv_unit, mo, ap, s);
+  }
+  return bf16 ? launch_attn2_k<true, false>(LK, mq, mkv_unit, mo, ap, s) : launch_attn2_k<false, false>(LK, mq, mkv_unit, mo, ap, s);
+}
+
+// 1 (default): pipelined kernel wherever it applies (dh 64, no probabilities); HFT_TC_ATTN2=0 keeps the one-tile-per-CTA kernel
+static bool attn2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_ATTN2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 #define HFT_TRY(x) do { int _rc = (x); if (_rc != HFT_OK) return _rc; } while (0)
 
 // one projection launch: out[:, out_col0 ..] = epilogue(A * W^T); out_width = columns of the output tensor's hi block
@@ -470,22 +523,25 @@ static int linear(TcState& t, cudaStream_t s, int epi, const CUtensorMap& a, con
   return launch_gemm(t.bf16, epi, a, w, M, g, &out, resid, s);
 }
 
-static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, AttnParams a, long long n_seq, int q_width) {
+// mkv: K/V tensor map with box dh x LK (one-tile kernel); mkv_unit: box dh x 128 (or dh x 96) for the pipelined kernel
+static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mkv_unit, AttnParams a,
+                     long long n_seq, int q_width) {
   a.q_lo_off = q_width;            // hi-block width of the Q tensor (3H for fused QKV buffers, H for the pitch-query table)
   a.kv_lo_off = 3 * m->H;
   a.ctx = t.CTX; a.ld_ctx = m->H * t.cm(); a.ctx_lo_off = m->H;
+  if (m->dh == 64 && a.probs == nullptr && attn2_enabled()) return launch_attn2(m->heads, t.bf16, t.x3, LK, mq, mkv_unit, t.sCTX, a, n_seq, s);
   return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }
 
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
 static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, const CUtensorMap& sqkv, const CUtensorMap& mq,
-                            const CUtensorMap& mkv, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
+                            const CUtensorMap& mkv, const CUtensorMap& mkv_unit, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
   const int H = m->H, P = m->P;
   const long long R = S * L;
   HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, sqkv, 0, 3 * H));
   AttnParams a{};
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
-  HFT_TRY(attention(m, t, s, LK, mq, mkv, a, S, 3 * H));
+  HFT_TRY(attention(m, t, s, LK, mq, mkv, mkv_unit, a, S, 3 * H));
   HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
   HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P));
   HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
@@ -538,7 +594,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
   }
   for (size_t l = 0; l < m->enc.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.sX, t.sQKV, t.mQKV_q, t.mQKV_kv, 256, Se, NB, t.enc[l], m->enc[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.sX, t.sQKV, t.mQKV_q, t.mQKV_kv, t.mQKV_q, 256, Se, NB, t.enc[l], m->enc[l].ln));
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
@@ -552,13 +608,13 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = probs; a.q_col0 = 0;
     if (zero) {
       a.q_seq_rows = 0;
-      HFT_TRY(attention(m, t, s, 256, t.mQ0, t.mQKV_kv, a, Se, H));
+      HFT_TRY(attention(m, t, s, 256, t.mQ0, t.mQKV_kv, t.mQKV_q, a, Se, H));
       // t = LN(pos_embedding_freq + fc_o(ctx)): the residual is the constant pitch-query table, period lcm(88,128)/128 = 11 tiles
       HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.sT, 0, H, &t.mPosRep, &ln, m, 11));
     } else {
       HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.ca_q, Rd, t.sDQ, 0, 3 * H));
       a.q_seq_rows = NN;
-      HFT_TRY(attention(m, t, s, 256, t.mDQ_q, t.mQKV_kv, a, Se, 3 * H));
+      HFT_TRY(attention(m, t, s, 256, t.mDQ_q, t.mQKV_kv, t.mQKV_q, a, Se, 3 * H));
       HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.ca_o, Rd, t.sT, 0, H, &t.mT, &ln, m));
     }
     return HFT_OK;
@@ -571,7 +627,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.sa_qkv, Rd, t.sDQ, 0, 3 * H));
     AttnParams a{};
     a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H;
-    HFT_TRY(attention(m, t, s, 96, t.mDQ_q, t.mDQ_kv, a, Se, 3 * H));
+    HFT_TRY(attention(m, t, s, 96, t.mDQ_q, t.mDQ_kv, t.mDQ_kv, a, Se, 3 * H));
     HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.sa_o, Rd, t.sT, 0, H, &t.mT, &ln, m));
     HFT_TRY(cross(lw, ln, false, ((int)l + 2 == n_cross) ? o->attention : nullptr));
     HFT_TRY(ffn(lw, ln));
@@ -590,7 +646,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, t.x3, total8, t.U);
   }
   for (size_t l = 0; l < m->tim.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
   {
     GemmParams g{};
     g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
@@ -641,5 +697,11 @@ extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void*
   const bool use_tma = dh == 64 && L % 128 == 0;
   if (use_tma) HFT_TRY(make_map(&mo, ctx16, n_seq * L, H, H, 64, 128, bf16 != 0));
   reset_launch_count();
+  if (dh == 64 && !probs && attn2_enabled()) {          // pipelined kernel (tc_attn2.cuh)
+    CUtensorMap mku, so;
+    HFT_TRY(make_map(&mku, qkv16, n_seq * L, 3 * H, 3 * H, dh, LK == 96 ? 96 : 128, bf16 != 0));
+    HFT_TRY(make_map(&so, ctx16, n_seq * L, H, H, 64, 32, bf16 != 0));
+    return launch_attn2(heads, bf16 != 0, false, LK, mq, mku, so, a, n_seq, (cudaStream_t)stream);
+  }
   return launch_attn(heads, dh, bf16 != 0, false, LK, mq, mkv, use_tma ? &mo : nullptr, a, n_seq, (cudaStream_t)stream);
 }

@@ -1,0 +1,372 @@
+// Persistent, pipelined tcgen05 attention:  softmax(Q K^T / sqrt(dh)) V   for the hFT sequences (Lk <= 256, dh = 64)
+// (reference MultiHeadAttentionLayer.forward, model_spec2midi.py:342-348).
+//
+// One CTA per SM walks "rounds" of two 128-query tiles.  Roles:
+//   warp 0      TMA producer   Q tiles (one buffer per softmax warpgroup) and a ring of K / V half-tiles (128 keys x dh)
+//   warp 1      MMA issuer     S = Q K^T into TMEM; O = P V with P read straight from TMEM (tcgen05.mma A-from-TMEM)
+//   warps 2..5  softmax warpgroup 0, warps 6..9 softmax warpgroup 1: one thread per query row (TMEM lane), so the row
+//               maximum / sum need no cross-thread exchange
+// A tile's keys are processed in halves of 128 ("units").  Each unit has its own maximum and sum (split softmax):
+//   S_u = Q K_u^T (128 TMEM columns) -> P_u = exp2(S_u c - m_u) written IN PLACE over S_u as 16-bit pairs
+//   -> O_u = P_u V_u into its own 64 accumulator columns;  the epilogue merges  O = (O_a f_a + O_b f_b) / (l_a f_a + l_b f_b),
+//   f_u = exp2(m_u - max(m_a, m_b)),
+// so a warpgroup never holds more than 256 TMEM columns (S/P 128 | O_a 64 | O_b 64) and the two warpgroups ping-pong: while
+// one waits for its MMAs the other runs exp2 on the CUDA cores.  With 256-query sequences (encoder) the two warpgroups
+// take the two query tiles of the same (sequence, head) and SHARE every K / V half-tile in the ring, which halves the
+// L2 -> shared-memory traffic; otherwise they work on different (sequence, head) items.
+// x3 mode (split operands): S = Qh Kh + Ql Kh + Qh Kl;  P = Ph + Pl (both in TMEM, [hi 16 cols | lo 16 cols] per 32 keys);
+// O = Ph Vh + Pl Vh + Ph Vl;  ctx stored hi | lo.
+// The probabilities-returning variant (last decoder layer) stays on tc_attn.cuh.
+#pragma once
+#include "tc_attn.cuh"
+
+namespace hft {
+namespace tc {
+
+struct Attn2Params {
+  int lq;                 // valid query rows per sequence
+  int lk;                 // valid keys per sequence
+  int q_seq_rows;         // rows between consecutive sequences in the Q tensor (0 = the same queries for every sequence)
+  int q_tiles;            // ceil(lq / 128): 1 or 2
+  int heads;
+  int q_col0, k_col0, v_col0;
+  float scale_log2e;
+  void* ctx;              // 16-bit [n_seq * lq, ld_ctx]
+  int ld_ctx;
+  int q_lo_off, kv_lo_off, ctx_lo_off;
+  int tma_store;          // 1: ctx written by per-warp TMA stores (lq % 128 == 0)
+  int n_items;            // n_seq * heads * q_tiles
+  int n_rounds;           // ceil(n_items / 2)
+  int shared_kv;          // 1: q_tiles == 2, both warpgroups use the same K / V half-tiles
+};
+
+template <int DH, bool X3>
+struct Attn2Smem {
+  static constexpr int parts = X3 ? 2 : 1;
+  static constexpr int tile_bytes = 128 * DH * 2;                 // one 128-row x dh operand part
+  static constexpr int q_bytes = tile_bytes * parts;              // per warpgroup
+  static constexpr int slot_bytes = tile_bytes * parts;           // one K or V half-tile (hi | lo)
+  static constexpr int n_slots = X3 ? 4 : 8;
+  static constexpr int stage_bytes = 8 * 32 * DH * 2;             // per warp one 32-row block (hi, then lo)
+  static constexpr int total = 1024 + 2 * q_bytes + n_slots * slot_bytes + stage_bytes + 512;
+};
+
+constexpr int kAttn2Threads = 64 + 256;
+
+// NKEY: keys per unit (128, or 96 for the 88-key decoder self-attention); NH: units per tile (Lk = NH * NKEY)
+template <bool BF16, int DH, int NKEY, int NH, bool X3>
+__global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                                                                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ Attn2Params p) {
+  using L = Attn2Smem<DH, X3>;
+  static_assert(DH == 64, "attn2 is built for head_dim 64");
+  static_assert((NKEY == 128 || NKEY == 96) && (NH == 1 || NH == 2), "unsupported key tiling");
+  constexpr int kParts = X3 ? 2 : 1;
+  constexpr int NS = L::n_slots;
+  constexpr uint32_t kRowBytes = DH * 2;                  // 128
+  constexpr uint32_t kAtom = 8 * kRowBytes;               // 1024
+  constexpr uint32_t kOCol = 128;                         // O_a at +128, O_b at +192 inside a warpgroup's 256 columns
+  constexpr int kChunks = NKEY / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_q = smem;                                                   // [2 warpgroups][parts][128 x dh]
+  uint8_t* s_ring = s_q + 2 * L::q_bytes;                                // [NS][parts][128 x dh]
+  uint8_t* s_stage = s_ring + NS * L::slot_bytes;                        // [8 warps][32 x dh]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + L::stage_bytes);
+  uint64_t* ring_full = bars;            // [8]
+  uint64_t* ring_empty = bars + 8;       // [8]
+  uint64_t* q_full = bars + 16;          // [2]
+  uint64_t* q_empty = bars + 18;         // [2]
+  uint64_t* s_ready = bars + 20;         // [2]  S unit complete (MMA -> softmax)
+  uint64_t* p_ready = bars + 22;         // [2]  P unit written (softmax -> MMA), 4 warp arrivals
+  uint64_t* o_ready = bars + 24;         // [2]  all PV MMAs of the tile complete (MMA -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_o);
+    for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool shared = p.shared_kv != 0;
+
+  // tile index -> (sequence, head, query tile)
+  auto decode = [&](int tile, int& seq, int& head, int& qt) {
+    qt = tile % p.q_tiles;
+    head = (tile / p.q_tiles) % p.heads;
+    seq = tile / (p.q_tiles * p.heads);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0, qph[2] = {0, 0};
+      auto load_kv = [&](int tile, int col0, int half) {                  // one K or V half-tile into the next ring slot
+        int seq, head, qt;
+        decode(tile, seq, head, qt);
+        mbar_wait(&ring_empty[slot], ph ^ 1);
+        mbar_expect_tx(&ring_full[slot], (uint32_t)(NKEY * DH * 2 * kParts));
+#pragma unroll
+        for (int part = 0; part < kParts; ++part)
+          tma_load_2d(s_ring + (size_t)slot * L::slot_bytes + part * L::tile_bytes, &map_kv, part * p.kv_lo_off + col0 + head * DH, seq * p.lk + half * NKEY,
+                      &ring_full[slot]);
+        if (++slot == NS) { slot = 0; ph ^= 1; }
+      };
+      auto load_q = [&](int w, int tile) {
+        int seq, head, qt;
+        decode(tile, seq, head, qt);
+        mbar_wait(&q_empty[w], qph[w] ^ 1);
+        mbar_expect_tx(&q_full[w], (uint32_t)(L::tile_bytes * kParts));
+#pragma unroll
+        for (int part = 0; part < kParts; ++part)
+          tma_load_2d(s_q + (size_t)w * L::q_bytes + part * L::tile_bytes, &map_q, part * p.q_lo_off + p.q_col0 + head * DH, seq * p.q_seq_rows + qt * 128, &q_full[w]);
+        qph[w] ^= 1;
+      };
+      int prev[2] = {-1, -1};
+      for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
+        int tile[2] = {2 * round, 2 * round + 1 < p.n_items ? 2 * round + 1 : -1};
+        for (int w = 0; w < 2; ++w) {                                     // phase A: last V half of the previous tile, first K half of the new one
+          if (prev[w] >= 0 && (!shared || w == 0)) load_kv(prev[w], p.v_col0, NH - 1);
+          if (tile[w] >= 0) {
+            load_q(w, tile[w]);
+            if (!shared || w == 0) load_kv(tile[w], p.k_col0, 0);
+          }
+        }
+        if (NH == 2) {
+          for (int w = 0; w < 2; ++w)                                     // phase B: first V half, second K half
+            if (tile[w] >= 0 && (!shared || w == 0)) { load_kv(tile[w], p.v_col0, 0); load_kv(tile[w], p.k_col0, 1); }
+        }
+        prev[0] = tile[0]; prev[1] = tile[1];
+      }
+      for (int w = 0; w < 2; ++w)
+        if (prev[w] >= 0 && (!shared || w == 0)) load_kv(prev[w], p.v_col0, NH - 1);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, NKEY, BF16, false, false);   // S = Q K^T, both K-major
+      const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);      // O = P V, A from TMEM, B = V MN-major
+      int slot = 0;
+      uint32_t ph = 0, qph[2] = {0, 0}, pph[2] = {0, 0};
+      auto take = [&]() -> int {
+        mbar_wait(&ring_full[slot], ph);
+        fence_after_sync();
+        const int s = slot;
+        if (++slot == NS) { slot = 0; ph ^= 1; }
+        return s;
+      };
+      auto issue_s = [&](int w, int kslot) {                                // S(w)[128, NKEY] = Q(w) K^T;  x3: Qh Kh + Ql Kh + Qh Kl
+        const uint32_t qa = smem_u32(s_q + (size_t)w * L::q_bytes), ka = smem_u32(s_ring + (size_t)kslot * L::slot_bytes);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int part = 0; part < (X3 ? 3 : 1); ++part) {
+          const uint32_t qp = qa + (part == 1 ? L::tile_bytes : 0), kp = ka + (part == 2 ? L::tile_bytes : 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) {
+            umma_f16(tmem_base + w * 256, make_sdesc(qp + k * 32, 16, kAtom, kSwz128), make_sdesc(kp + k * 32, 16, kAtom, kSwz128), idesc_s, acc);
+            acc = 1;
+          }
+        }
+      };
+      auto issue_pv = [&](int w, uint32_t ocol, int vslot) {                // O_u(w)[128, dh] = P V;  x3: Ph Vh + Pl Vh + Ph Vl
+        const uint32_t va = smem_u32(s_ring + (size_t)vslot * L::slot_bytes);
+        const uint32_t tp = tmem_base + w * 256;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int part = 0; part < (X3 ? 3 : 1); ++part) {
+          const uint32_t vp = va + (part == 2 ? L::tile_bytes : 0);
+#pragma unroll
+          for (int k = 0; k < NKEY / 16; ++k) {
+            // P columns: x3 [hi 16 | lo 16] per 32 keys; single product 8 columns per 16 keys
+            const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
+            umma_f16_ts(tp + ocol, tp + pcol, make_sdesc(vp + k * 16 * kRowBytes, kAtom, kAtom, kSwz128), idesc_o, acc);
+            acc = 1;
+          }
+        }
+      };
+      int prev[2] = {-1, -1};
+      int held_v = 0, held_k = 0;
+      auto finish_prev = [&](int w) {                                        // PV of the previous tile's last unit
+        if (!shared || w == 0) held_v = take();
+        mbar_wait(&p_ready[w], pph[w]); pph[w] ^= 1;
+        fence_after_sync();
+        issue_pv(w, NH == 2 ? kOCol + 64 : kOCol, held_v);
+        umma_commit(&o_ready[w]);
+        if (!shared || w == 1) umma_commit(&ring_empty[held_v]);
+      };
+      for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
+        int tile[2] = {2 * round, 2 * round + 1 < p.n_items ? 2 * round + 1 : -1};
+        for (int w = 0; w < 2; ++w) {
+          if (prev[w] >= 0) finish_prev(w);
+          if (tile[w] >= 0) {
+            if (!shared || w == 0) held_k = take();
+            mbar_wait(&q_full[w], qph[w]); qph[w] ^= 1;
+            fence_after_sync();
+            issue_s(w, held_k);
+            umma_commit(&s_ready[w]);
+            if (NH == 1) umma_commit(&q_empty[w]);
+            if (!shared || w == 1) umma_commit(&ring_empty[held_k]);
+          }
+        }
+        if (NH == 2) {
+          for (int w = 0; w < 2; ++w) {
+            if (tile[w] < 0) continue;
+            if (!shared || w == 0) { held_v = take(); held_k = take(); }
+            mbar_wait(&p_ready[w], pph[w]); pph[w] ^= 1;
+            fence_after_sync();
+            issue_pv(w, kOCol, held_v);
+            issue_s(w, held_k);                                              // overwrites P_a: the MMA pipe runs in issue order
+            umma_commit(&s_ready[w]);
+            umma_commit(&q_empty[w]);
+            if (!shared || w == 1) { umma_commit(&ring_empty[held_v]); umma_commit(&ring_empty[held_k]); }
+          }
+        }
+        prev[0] = tile[0]; prev[1] = tile[1];
+      }
+      for (int w = 0; w < 2; ++w)
+        if (prev[w] >= 0) finish_prev(w);
+    }
+  } else {
+    // ===================== softmax + epilogue warpgroups =====================
+    const int w = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // query row inside the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + w * 256;
+    uint8_t* my_stage = s_stage + (size_t)(warp - 2) * (32 * DH * 2);
+    uint32_t sph = 0, oph = 0;
+    for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
+      const int tile = 2 * round + w;
+      if (tile >= p.n_items) continue;
+      int seq, head, qt;
+      decode(tile, seq, head, qt);
+      float mx[NH], sum[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        mbar_wait(&s_ready[w], sph); sph ^= 1;
+        fence_after_sync();
+        const int kvalid = p.lk - h * NKEY;                  // valid keys in this unit (only the 88-key sequences are padded)
+        const bool mask = kvalid < NKEY;
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (mask) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < kvalid) m = fmaxf(m, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+        }
+        const float ms = m * p.scale_log2e;
+        float s = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pw[32];                                   // x3: [hi 16 | lo 16]; single product: first 16 used
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -ms));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -ms));
+            if (mask) {
+              if (c * 32 + 2 * j >= kvalid) e0 = 0.f;
+              if (c * 32 + 2 * j + 1 >= kvalid) e1 = 0.f;
+            }
+            s += e0 + e1;
+            if (X3) split_pack<BF16>(e0, e1, pw[j], pw[16 + j]);
+            else pw[j] = Op16<BF16>::pack(e0, e1);
+          }
+          if (X3) {
+            tmem_st32(t_row + c * 32, pw);
+          } else {
+            uint32_t ph16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph16[j] = pw[j];
+            tmem_st16(t_row + c * 16, ph16);
+          }
+        }
+        mx[h] = ms;
+        sum[h] = s;
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[w]);
+      }
+      // ---- epilogue: merge the units, normalise, store ----
+      float f0 = 1.f, f1 = 0.f;
+      if (NH == 2) {
+        const float mm = fmaxf(mx[0], mx[NH - 1]);
+        f0 = ex2_approx(mx[0] - mm);
+        f1 = ex2_approx(mx[NH - 1] - mm);
+      }
+      const float inv = 1.f / (NH == 2 ? sum[0] * f0 + sum[NH - 1] * f1 : sum[0]);
+      f0 *= inv; f1 *= inv;
+      mbar_wait(&o_ready[w], oph); oph ^= 1;
+      fence_after_sync();
+      const int qrow = qt * 128 + r;
+      uint32_t hi[32], lo[32];                               // the row's dh = 64 outputs as 16-bit pairs
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t oa[32], ob[32];
+        tmem_ld32(t_row + kOCol + c * 32, oa);
+        if (NH == 2) tmem_ld32(t_row + kOCol + 64 + c * 32, ob);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(oa[2 * j]) * f0, b = __uint_as_float(oa[2 * j + 1]) * f0;
+          if (NH == 2) { a = fmaf(__uint_as_float(ob[2 * j]), f1, a); b = fmaf(__uint_as_float(ob[2 * j + 1]), f1, b); }
+          if (X3) split_pack<BF16>(a, b, hi[c * 16 + j], lo[c * 16 + j]);
+          else hi[c * 16 + j] = Op16<BF16>::pack(a, b);
+        }
+      }
+      if (p.tma_store) {
+        const int row0 = seq * p.lq + qt * 128 + quarter * 32;
+#pragma unroll
+        for (int part = 0; part < kParts; ++part) {
+          if (lane == 0) tma_store_wait_read();              // the warp's previous store has read the staging block
+          __syncwarp();
+          uint8_t* dst = my_stage + lane * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(dst + ((q ^ (lane & 7)) << 4)) =
+                part ? make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]) : make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_o, my_stage, part * p.ctx_lo_off + head * DH, row0);
+            tma_store_commit();
+          }
+        }
+      } else if (qrow < p.lq) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.ctx) + ((long long)seq * p.lq + qrow) * p.ld_ctx + head * DH);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (X3) *reinterpret_cast<uint4*>(dst + p.ctx_lo_off / 2 + q * 4) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+}  // namespace hft

@@ -64,6 +64,7 @@ def test_linear_residual_layernorm(kind, M, N, K):
 
 @pytest.mark.parametrize("kind", ["bf16", "fp16"])
 @pytest.mark.parametrize("dh,heads,L,n_seq,probs", [(64, 4, 256, 3, True), (64, 4, 256, 2, False), (64, 4, 128, 5, False), (64, 4, 88, 7, False),
+                                                    (64, 4, 256, 80, False), (64, 4, 128, 100, False), (64, 1, 88, 301, False), (64, 2, 256, 1, False),
                                                     (32, 2, 256, 3, True), (32, 2, 128, 3, False), (32, 2, 88, 5, False)])
 def test_attention(kind, dh, heads, L, n_seq, probs):
     H = dh * heads
