@@ -167,6 +167,47 @@ int hft_tc_linear(int bf16, int epi, const void* a16_dev, const void* w16_dev, c
 int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16_dev, int64_t n_seq, int32_t L, void* ctx16_dev,
                      float* probs_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 5: reduced hFT, batch 8 per GPU, Adam lr 1e-4, data parallel).
+ * Replaces: the body of train() -- reference hftt_code/training/train.py:89-160 (model(input) in train mode, BCELoss on
+ *           the six sigmoid outputs + CrossEntropyLoss on the two velocity logit tensors, loss = weight_A * loss_A +
+ *           weight_B * loss_B, loss.backward(), optimizer.step()) with torch.optim.Adam(lr) of
+ *           hftt_code/training/m_training.py:146.  fp32 CUDA-core kernels; dropout p = 0 only (the parity configuration).
+ * Parameters and gradients are ONE flat fp32 vector each: the tensors of the state_dict in schema order, every tensor
+ * padded to a multiple of 4 floats (hft_model_param_offset).  The flat gradient is the single bucket the data-parallel
+ * configuration all-reduces over NCCL between hft_train_forward_backward and hft_adam_step.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hft_trainer hft_trainer;
+
+/* Length of the flat parameter / gradient vectors and the offset of tensor `index` inside them. */
+int64_t hft_model_param_floats(const hft_model* model);
+int64_t hft_model_param_offset(const hft_model* model, int index);
+/* Device pointer to the model's own flat parameter vector (what hft_model_set_weights filled). */
+float* hft_model_params(hft_model* model);
+/* Copy the flat parameters into a caller-owned device buffer of hft_model_param_floats floats (checkpointing: the host
+ * mirror writes them back into its nn.Parameters, m_training.py:275). */
+int hft_model_get_params(hft_model* model, float* params_out_dev, void* stream);
+/* Re-derive what the kernels consume (collapsed front filter, fused QKV, 16-bit copies) after the flat parameters were
+ * updated in place (hft_adam_step on hft_model_params). */
+int hft_model_refresh(hft_model* model, void* stream);
+
+/* Activation tape and gradient work space for `batch` segments per step. */
+int hft_trainer_create(hft_trainer** trainer, hft_model* model, int32_t batch);
+int hft_trainer_destroy(hft_trainer* trainer);
+
+/* Forward (train.py:90), loss (:139-151) and backward (:157) for one batch of `batch` segments:
+ *   spec_dev [batch][n_bin][n_margin + n_frame + n_margin] fp32 (element strides given),
+ *   label_onset/offset/mpe_dev [batch][n_frame][n_note] fp32 in [0, 1], label_velocity_dev [batch][n_frame][n_note] int64 in [0, n_velocity).
+ * loss_dev[0] receives the scalar loss; grads_dev (hft_model_param_floats floats) is overwritten with dLoss/dParam. */
+int hft_train_forward_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                               const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
+                               const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream);
+
+/* torch.optim.Adam (no weight decay, no amsgrad) on flat vectors: grads are multiplied by grad_scale first (1 / world size
+ * after a sum all-reduce); step counts from 1. */
+int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,9 @@ def __getattr__(name):
     if name in ("Model_SPEC2MIDI", "Encoder_SPEC2MIDI", "Decoder_SPEC2MIDI"):
         from . import model_spec2midi
         return getattr(model_spec2midi, name)
+    if name == "training":
+        import importlib
+        return importlib.import_module(".training", __name__)
     raise AttributeError(name)
 
 

@@ -47,6 +47,18 @@ SYMBOLS = {
                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "hft_tc_attention": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_model_param_floats": (ctypes.c_int64, [ctypes.c_void_p]),
+    "hft_model_param_offset": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
+    "hft_model_params": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "hft_model_refresh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_model_get_params": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_trainer_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int32]),
+    "hft_trainer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "hft_train_forward_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_float, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]),
     "hft_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "hft_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 }
@@ -73,3 +85,4 @@ def check(rc, what):
     if rc != 0:
         msg = lib().hft_last_error()
         raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+

@@ -3,264 +3,12 @@
 // cross-check of the tensor-core path.  Kernels: collapsed front filter, tiled SGEMM (+bias, +ReLU), two-pass
 // softmax attention, residual+LayerNorm, time re-layout, head finish.
 #include "common.cuh"
+#include "f32_kernels.cuh"
 #include "model.h"
 
 #include <math.h>
 
 namespace hft {
-
-// ------------------------------------------------------------------------------------------------------------
-// front: unfold(65) -> conv(1,C,(1,kw)) -> Linear -> *sqrt(H) + pos  (model_spec2midi.py:65-95), collapsed to one
-// 65-tap filter per hidden unit.  grid (n_bin, B); X[((b*F+f)*NB+bin)*H + h].
-// ------------------------------------------------------------------------------------------------------------
-template <int NPROC>
-__global__ void __launch_bounds__(256) front_f32_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st,
-                                                        const float* __restrict__ Wc, const float* __restrict__ bc, const float* __restrict__ pos,
-                                                        float scale, int H, int F, int NB, float* __restrict__ X) {
-  __shared__ float s_row[256];
-  const int bin = blockIdx.x, b = blockIdx.y;
-  const int W = F + NPROC - 1;
-  for (int i = threadIdx.x; i < W; i += blockDim.x) s_row[i] = spec[b * sb + bin * sbin + i * st];
-  __syncthreads();
-  const int groups = blockDim.x / H;
-  const int h = threadIdx.x % H, g = threadIdx.x / H;
-  if (g >= groups) return;
-  float w[NPROC];
-#pragma unroll
-  for (int j = 0; j < NPROC; ++j) w[j] = Wc[h * NPROC + j];
-  const float bias = bc[h], pe = pos[bin * H + h];
-  const int fpg = F / groups;
-  for (int f0 = g * fpg; f0 < (g + 1) * fpg; f0 += 8) {
-    float acc[8], sv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = 0.f; sv[i] = s_row[f0 + i]; }
-#pragma unroll
-    for (int j = 0; j < NPROC; ++j) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[j], sv[i], acc[i]);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) sv[i] = sv[i + 1];
-      sv[7] = (j + 1 < NPROC) ? s_row[f0 + j + 8] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) X[(((long long)b * F + f0 + i) * NB + bin) * H + h] = (acc[i] + bias) * scale + pe;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// C[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU).  128x128x16 tiles, 256 threads, 8x8 micro-tile.  K % 16 == 0.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int GBM = 128, GBN = 128, GBK = 16, GPAD = 4;
-
-template <bool RELU>
-__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int ldw,
-                                                       const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
-  __shared__ __align__(16) float As[GBK][GBM + GPAD];
-  __shared__ __align__(16) float Ws[GBK][GBN + GPAD];
-  const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  const int lrow = tid >> 1, lk = (tid & 1) * 8;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const bool a_ok = (m0 + lrow) < M, w_ok = (n0 + lrow) < N;
-  const float* ap = A + (long long)(m0 + lrow) * lda + lk;
-  const float* wp = Wt + (long long)(n0 + lrow) * ldw + lk;
-  float4 a0, a1, w0, w1;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  a0 = a_ok ? *reinterpret_cast<const float4*>(ap) : z;
-  a1 = a_ok ? *reinterpret_cast<const float4*>(ap + 4) : z;
-  w0 = w_ok ? *reinterpret_cast<const float4*>(wp) : z;
-  w1 = w_ok ? *reinterpret_cast<const float4*>(wp + 4) : z;
-  for (int k0 = 0; k0 < K; k0 += GBK) {
-    As[lk + 0][lrow] = a0.x; As[lk + 1][lrow] = a0.y; As[lk + 2][lrow] = a0.z; As[lk + 3][lrow] = a0.w;
-    As[lk + 4][lrow] = a1.x; As[lk + 5][lrow] = a1.y; As[lk + 6][lrow] = a1.z; As[lk + 7][lrow] = a1.w;
-    Ws[lk + 0][lrow] = w0.x; Ws[lk + 1][lrow] = w0.y; Ws[lk + 2][lrow] = w0.z; Ws[lk + 3][lrow] = w0.w;
-    Ws[lk + 4][lrow] = w1.x; Ws[lk + 5][lrow] = w1.y; Ws[lk + 6][lrow] = w1.z; Ws[lk + 7][lrow] = w1.w;
-    __syncthreads();
-    if (k0 + GBK < K) {                            // register prefetch of the next K slab
-      a0 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK) : z;
-      a1 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK + 4) : z;
-      w0 = w_ok ? *reinterpret_cast<const float4*>(wp + k0 + GBK) : z;
-      w1 = w_ok ? *reinterpret_cast<const float4*>(wp + k0 + GBK + 4) : z;
-    }
-#pragma unroll
-    for (int k = 0; k < GBK; ++k) {
-      float4 ra0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      float4 ra1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      float4 rb0 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-      float4 rb1 = *reinterpret_cast<const float4*>(&Ws[k][64 + tx * 4]);
-      float ra[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
-      float rb[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
-    if (row >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-      if (col >= N) continue;
-      float v = acc[i][j] + (bias ? bias[col] : 0.f);
-      if (RELU) v = fmaxf(v, 0.f);
-      C[(long long)row * ldc + col] = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// attention for one (sequence, head): softmax(Q K^T / sqrt(dh)) V  (model_spec2midi.py:342-348), two passes over
-// the keys (max+sum, then normalised PV); optionally writes the probabilities [S,heads,Lq,Lk] (:360).
-// One thread per query row; the head's K and V slices live in shared memory.
-// ------------------------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride,
-                                                       const float* __restrict__ Kp, const float* __restrict__ Vp, int ldkv, int Lq, int Lk,
-                                                       int heads, float inv_scale, float* __restrict__ ctx, int ldc, float* __restrict__ probs) {
-  extern __shared__ __align__(16) float smem_attn[];
-  float* sK = smem_attn;
-  float* sV = smem_attn + (size_t)Lk * DH;
-  const int seq = blockIdx.x, head = blockIdx.y;
-  const float* kbase = Kp + (long long)seq * Lk * ldkv + head * DH;
-  const float* vbase = Vp + (long long)seq * Lk * ldkv + head * DH;
-  for (int i = threadIdx.x; i < Lk * (DH / 4); i += blockDim.x) {
-    int j = i / (DH / 4), c = i % (DH / 4);
-    reinterpret_cast<float4*>(sK)[i] = *reinterpret_cast<const float4*>(kbase + (long long)j * ldkv + c * 4);
-    reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(vbase + (long long)j * ldkv + c * 4);
-  }
-  __syncthreads();
-  const int r = threadIdx.x;
-  if (r >= Lq) return;
-  float q[DH];
-  const float* qp = Q + (long long)seq * q_seq_stride + (long long)r * ldq + head * DH;
-#pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    float4 t = *reinterpret_cast<const float4*>(qp + c * 4);
-    q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
-  }
-  float mx = -INFINITY, sum = 0.f;
-  for (int j = 0; j < Lk; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < DH / 4; ++c) {
-      float4 t = kr[c];
-      s = fmaf(q[c * 4], t.x, s); s = fmaf(q[c * 4 + 1], t.y, s); s = fmaf(q[c * 4 + 2], t.z, s); s = fmaf(q[c * 4 + 3], t.w, s);
-    }
-    s *= inv_scale;
-    if (s > mx) { sum *= expf(mx - s); mx = s; }
-    sum += expf(s - mx);
-  }
-  const float inv_sum = 1.f / sum;
-  float acc[DH];
-#pragma unroll
-  for (int c = 0; c < DH; ++c) acc[c] = 0.f;
-  float* prow = probs ? probs + (((long long)seq * heads + head) * Lq + r) * Lk : nullptr;
-  for (int j = 0; j < Lk; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < DH / 4; ++c) {
-      float4 t = kr[c];
-      s = fmaf(q[c * 4], t.x, s); s = fmaf(q[c * 4 + 1], t.y, s); s = fmaf(q[c * 4 + 2], t.z, s); s = fmaf(q[c * 4 + 3], t.w, s);
-    }
-    const float p = expf(s * inv_scale - mx) * inv_sum;
-    if (prow) prow[j] = p;
-    const float4* vr = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
-#pragma unroll
-    for (int c = 0; c < DH / 4; ++c) {
-      float4 t = vr[c];
-      acc[c * 4] = fmaf(p, t.x, acc[c * 4]); acc[c * 4 + 1] = fmaf(p, t.y, acc[c * 4 + 1]);
-      acc[c * 4 + 2] = fmaf(p, t.z, acc[c * 4 + 2]); acc[c * 4 + 3] = fmaf(p, t.w, acc[c * 4 + 3]);
-    }
-  }
-  float* op = ctx + ((long long)seq * Lq + r) * ldc + head * DH;
-#pragma unroll
-  for (int c = 0; c < DH / 4; ++c) *reinterpret_cast<float4*>(op + c * 4) = make_float4(acc[c * 4], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// y = LayerNorm(x + r) * g + b, eps 1e-5 (model_spec2midi.py:236,242: one LayerNorm module shared by the sites of
-// a layer).  One warp per row.  r is indexed by (row % r_rows) so the constant pitch queries can be broadcast.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) add_ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ r, long long r_rows,
-                                                         const float* __restrict__ g, const float* __restrict__ b, int H, long long rows,
-                                                         float* __restrict__ y) {
-  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const float* xp = x + row * H;
-  const float* rp = r + (row % r_rows) * H;
-  float v[8];
-  float s = 0.f;
-  const int per = H >> 5;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < per) { v[i] = xp[lane + 32 * i] + rp[lane + 32 * i]; s += v[i]; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)H;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < per) { float d = v[i] - mean; q = fmaf(d, d, q); }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)H + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < per) { int c = lane + 32 * i; y[row * H + c] = (v[i] - mean) * rstd * g[c] + b[c]; }
-}
-
-// U[((b*NN+n)*F+f)*H+h] = T[((b*F+f)*NN+n)*H+h] * sqrt(H) + pos_time[f*H+h]   (model_spec2midi.py:189-191)
-__global__ void time_relayout_f32_kernel(const float* __restrict__ T, const float* __restrict__ pos, float scale, int F, int NN, int H,
-                                         long long total, float* __restrict__ U) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int h = (int)(i % H);
-  long long r = i / H;
-  int f = (int)(r % F);
-  long long bn = r / F;
-  int n = (int)(bn % NN);
-  long long b = bn / NN;
-  U[i] = T[(((b * F + f) * NN + n)) * H + h] * scale + pos[f * H + h];
-}
-
-// heads (model_spec2midi.py:172-175 / :203-206): HT[row][0..2] -> sigmoid -> onset/offset/mpe, HT[row][3..] -> velocity.
-// time_major: rows are (b,n,f) and outputs are permuted back to [B,F,NN(,V)].
-__global__ void heads_finish_f32_kernel(const float* __restrict__ HT, int ldh, int V, int F, int NN, long long rows, bool time_major,
-                                        float* __restrict__ onset, float* __restrict__ offset, float* __restrict__ mpe,
-                                        float* __restrict__ velocity) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cols = 3 + V;
-  if (i >= rows * cols) return;
-  long long row = i / cols;
-  int c = (int)(i % cols);
-  long long orow = row;
-  if (time_major) {
-    int f = (int)(row % F);
-    long long bn = row / F;
-    int n = (int)(bn % NN);
-    long long b = bn / NN;
-    orow = (b * F + f) * NN + n;
-  }
-  float v = HT[row * ldh + c];
-  if (c < 3) {
-    float* dst = c == 0 ? onset : (c == 1 ? offset : mpe);
-    if (dst) dst[orow] = 1.f / (1.f + expf(-v));
-  } else if (velocity) {
-    velocity[orow * V + (c - 3)] = v;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // host orchestration

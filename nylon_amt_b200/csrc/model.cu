@@ -185,6 +185,8 @@ static int derive_weights(Model* m, cudaStream_t s) {
   return HFT_OK;
 }
 
+int derive_weights_public(Model* m, cudaStream_t s) { return derive_weights(m, s); }   // after in-place parameter updates (train_f32.cu)
+
 }  // namespace hft
 
 using namespace hft;

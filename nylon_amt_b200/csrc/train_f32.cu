@@ -1,0 +1,501 @@
+// Training step of Model_SPEC2MIDI on sm_100a, fp32 CUDA-core kernels (reference hftt_code/training/train.py:89-160:
+// forward in train mode, the 8-term loss, loss.backward(), optimizer.step(); optimiser and initialisation
+// hftt_code/training/m_training.py:31-33,141,146).  The forward keeps a tape (layer inputs, fused Q|K|V, attention row
+// log-sum-exps, contexts, pre-LayerNorm sums, FFN hidden activations); the backward recomputes the attention
+// probabilities from Q, K and the log-sum-exp instead of storing [S, heads, Lq, Lk].
+// Gradients land in one flat fp32 vector laid out like the model's parameter arena (state_dict order, every tensor
+// padded to 4 floats) so that the data-parallel configuration all-reduces ONE bucket over NCCL.
+// Dropout: the reference trains with p = 0.1; this step implements p = 0 (the parity configuration of SURVEY.md 8d
+// config 5) and the host mirror refuses any other value.
+#include "common.cuh"
+#include "model.h"
+#include "train_kernels.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace hft {
+
+#define HFT_TRY(x) do { int _rc = (x); if (_rc != HFT_OK) return _rc; } while (0)
+
+struct LayerTape {           // EncoderLayer / the blocks of a DecoderLayer
+  float *xin, *qkv, *lse, *ctx, *s1, *x1, *hid, *s2;
+};
+struct DecTape {
+  // self-attention block (layers >= 1)
+  float *tin, *qkv, *lse_s, *ctx_s, *s0, *t0;
+  // cross-attention block
+  float *qc, *kv, *lse_c, *ctx_c, *s1, *t1;
+  // FFN block
+  float *hid, *s2;
+};
+
+struct Trainer {
+  Model* m = nullptr;
+  int B = 0;
+  float* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<LayerTape> enc, tim;
+  std::vector<DecTape> dec;      // index 0 = layer zero
+  float *x_enc = nullptr, *t_out = nullptr, *u0 = nullptr, *u_out = nullptr;
+  float *logits_a = nullptr, *logits_b = nullptr;
+  float *head_w[2] = {nullptr, nullptr}, *head_b[2] = {nullptr, nullptr}, *g_head_w = nullptr, *g_head_b = nullptr;
+  float *g_front_w = nullptr, *g_front_b = nullptr;
+  // gradient work buffers
+  float *gX = nullptr, *gBIG = nullptr, *gCTX = nullptr, *gHID = nullptr, *gT = nullptr, *gDQ = nullptr, *gU = nullptr, *gLOG = nullptr, *dD = nullptr, *gQ0 = nullptr;
+  int NP = 144;                  // padded head width (3 + V = 131 -> multiple of 16)
+};
+
+// ---- launch helpers -------------------------------------------------------------------------------------------------
+static int gemm_tn(cudaStream_t s, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc, long long M, int N, int K,
+                   bool relu, bool accum = false) {
+  HFT_REQUIRE(K % GBK == 0 && lda % 4 == 0 && ldw % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_tn: K=%d lda=%d ldw=%d", K, lda, ldw);
+  dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  if (relu) sgemm_tn_kernel<true><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+  else sgemm_tn_kernel<false><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+  return HFT_OK;
+}
+// C[M,N] (+)= A[M,K] * W[K,N]
+static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int ldb, float* C, int ldc, long long M, int N, int K, bool accum,
+                   const float* mask = nullptr, int ldm = 0) {
+  HFT_REQUIRE(K % GBK == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_nn: N=%d K=%d lda=%d ldb=%d", N, K, lda, ldb);
+  dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  sgemm_nn_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm);
+  return HFT_OK;
+}
+// dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)
+static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, long long M, int N, int K) {
+  HFT_REQUIRE(ldy % 4 == 0 && ldx % 4 == 0, HFT_ERR_UNSUPPORTED, "train dw gemm: ldy=%d ldx=%d", ldy, ldx);
+  const int gx = (N + DWT - 1) / DWT, gy = (K + DWT - 1) / DWT;
+  long long splits = (M + 2047) / 2048;
+  const long long cap = 2048 / (gx * gy) > 1 ? 2048 / (gx * gy) : 1;      // bound the number of atomic waves
+  if (splits > cap) splits = cap;
+  long long rps = ((M + splits - 1) / splits + DWR - 1) / DWR * DWR;
+  splits = (M + rps - 1) / rps;
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), 256, 0, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
+  return HFT_OK;
+}
+static void ln_fwd(Model* m, cudaStream_t s, const float* x, const float* r, long long r_rows, const LnW& ln, long long rows, float* y, float* sum_out) {
+  LaunchScope ls(HFT_KCLASS_NORM, s);
+  add_ln_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, r, r_rows, m->w[ln.g], m->w[ln.b], m->H, rows, y, sum_out);
+}
+static void ln_bwd(Model* m, cudaStream_t s, const float* dy, const float* sum, const LnW& ln, long long rows, float* ds, float* G) {
+  LaunchScope ls(HFT_KCLASS_NORM, s);
+  ln_bwd_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(dy, sum, m->w[ln.g], m->H, rows, ds, G + (m->w[ln.g] - m->arena), G + (m->w[ln.b] - m->arena));
+}
+static void colsum(cudaStream_t s, const float* in, long long rows, long long cols, float* out) {
+  long long splits = rows >= 64 ? 16 : 1;
+  long long rps = (rows + splits - 1) / splits;
+  LaunchScope ls(HFT_KCLASS_NORM, s);
+  colsum_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)splits), 256, 0, s>>>(in, rows, cols, rps, out);
+}
+
+static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
+                    int Lq, int Lk, float* ctx, float* lse) {
+  const int dh = m->dh;
+  size_t smem = (size_t)2 * Lk * dh * sizeof(float);
+  int threads = (Lq + 31) / 32 * 32;
+  HFT_REQUIRE(threads <= 256 && smem <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention: Lq=%d Lk=%d unsupported", Lq, Lk);
+  dim3 grid((unsigned)S, m->heads);
+  const float inv_scale = 1.f / sqrtf((float)dh);
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  if (dh == 64) {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse);
+  } else {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse);
+  }
+  return HFT_OK;
+}
+
+template <int DH>
+static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO,
+                      const float* O, const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf) {
+  const float c = 1.f / sqrtf((float)DH);
+  dim3 grid((unsigned)S, m->heads);
+  const size_t smem1 = (size_t)2 * Lk * DH * sizeof(float);
+  const size_t smem2 = ((size_t)2 * Lq * DH + 2 * Lq) * sizeof(float);
+  const int t1 = (Lq + 31) / 32 * 32, t2 = (Lk + 31) / 32 * 32;
+  HFT_REQUIRE(t1 <= 256 && t2 <= 256 && smem1 <= 200 * 1024 && smem2 <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention backward: Lq=%d Lk=%d", Lq, Lk);
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf);
+  if (DH <= 32) {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
+  } else {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_bwd_dkv_kernel<DH, 1><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
+    attn_bwd_dkv_kernel<DH, 2><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
+  }
+  return HFT_OK;
+}
+static int attn_bwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO, const float* O,
+                    const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf) {
+  if (m->dh == 64) return attn_bwd_t<64>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf);
+  return attn_bwd_t<32>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf);
+}
+
+// gradient slot of a registered parameter inside the flat gradient vector
+static inline float* gof(Model* m, float* G, int idx) { return G + (m->w[idx] - m->arena); }
+
+// ---- tape allocation ------------------------------------------------------------------------------------------------
+static int alloc_tape(Trainer& t) {
+  Model* m = t.m;
+  const long long Re = (long long)t.B * m->nframe * m->nbin, Rd = (long long)t.B * m->nframe * m->nnote;
+  const long long H = m->H, P = m->P, heads = m->heads;
+  const long long Se = (long long)t.B * m->nframe, St = (long long)t.B * m->nnote;
+  const size_t n_enc = m->enc.size(), n_tim = m->tim.size(), n_dec = 1 + m->dec.size();
+  auto layer_floats = [&](long long R, long long S, long long L) { return R * (8 * H + P) + S * heads * L + 64 * 8; };
+  size_t fl = 0;
+  fl += n_enc * layer_floats(Re, Se, m->nbin) + Re * H;                                   // encoder layers + encoder output
+  fl += n_tim * layer_floats(Rd, St, m->nframe) + 2 * Rd * H;                             // time layers + u0 / u_out
+  fl += n_dec * (Rd * (12 * H + P) + Re * 2 * H + 2 * Se * heads * m->nnote + 64 * 16) + Rd * H;   // decoder layers + t_out
+  fl += 2 * Rd * t.NP + 2 * ((size_t)t.NP * H + t.NP) + (size_t)t.NP * H + t.NP + (size_t)H * m->nproc + H + 64 * 16;
+  fl += Re * (H + 3 * H + H + P) + Rd * (H + 3 * H + H) + Rd * t.NP + Re + (size_t)m->nnote * H + 64 * 12;              // gradient work buffers
+  t.arena_bytes = fl * sizeof(float);
+  HFT_CHECK_CUDA(cudaMalloc(&t.arena, t.arena_bytes));
+  float* p = t.arena;
+  auto take = [&](long long n) { float* r = p; p += (n + 63) & ~63ll; return r; };
+  auto mk_layer = [&](LayerTape& L, long long R, long long S, long long Lq) {
+    L.xin = take(R * H); L.qkv = take(R * 3 * H); L.lse = take(S * heads * Lq); L.ctx = take(R * H); L.s1 = take(R * H); L.x1 = take(R * H);
+    L.hid = take(R * P); L.s2 = take(R * H);
+  };
+  t.enc.resize(n_enc); t.tim.resize(n_tim); t.dec.resize(n_dec);
+  for (auto& L : t.enc) mk_layer(L, Re, Se, m->nbin);
+  t.x_enc = take(Re * H);
+  for (size_t i = 0; i < n_dec; ++i) {
+    DecTape& D = t.dec[i];
+    D.tin = take(Rd * H); D.qkv = take(Rd * 3 * H); D.lse_s = take(Se * heads * m->nnote); D.ctx_s = take(Rd * H); D.s0 = take(Rd * H); D.t0 = take(Rd * H);
+    D.qc = take(Rd * H); D.kv = take(Re * 2 * H); D.lse_c = take(Se * heads * m->nnote); D.ctx_c = take(Rd * H); D.s1 = take(Rd * H); D.t1 = take(Rd * H);
+    D.hid = take(Rd * P); D.s2 = take(Rd * H);
+  }
+  t.t_out = take(Rd * H);
+  t.u0 = take(Rd * H);
+  for (auto& L : t.tim) mk_layer(L, Rd, St, m->nframe);
+  t.u_out = take(Rd * H);
+  t.logits_a = take(Rd * t.NP); t.logits_b = take(Rd * t.NP);
+  for (int i = 0; i < 2; ++i) { t.head_w[i] = take((long long)t.NP * H); t.head_b[i] = take(t.NP); }
+  t.g_head_w = take((long long)t.NP * H); t.g_head_b = take(t.NP);
+  t.g_front_w = take(H * m->nproc); t.g_front_b = take(H);
+  t.gX = take(Re * H); t.gBIG = take(Re * 3 * H); t.gCTX = take(Re * H); t.gHID = take(Re * P);
+  t.gT = take(Rd * H); t.gDQ = take(Rd * 3 * H); t.gU = take(Rd * H); t.gLOG = take(Rd * t.NP); t.dD = take(Re); t.gQ0 = take((long long)m->nnote * H);
+  HFT_REQUIRE((size_t)(p - t.arena) * sizeof(float) <= t.arena_bytes, HFT_ERR_STATE, "trainer tape overflow (%zu > %zu)", (size_t)(p - t.arena) * sizeof(float), t.arena_bytes);
+  return HFT_OK;
+}
+
+// ---- forward with tape ----------------------------------------------------------------------------------------------
+// EncoderLayer (model_spec2midi.py:230-245): x = L.xin -> out
+static int enc_layer_fwd(Model* m, cudaStream_t s, LayerTape& L, long long S, int Lq, const EncLayerW& lw, const FusedAttn& qkv, float* out, float* tmp) {
+  const int H = m->H, P = m->P;
+  const long long R = S * Lq;
+  HFT_TRY(gemm_tn(s, L.xin, H, qkv.qkv_w, H, qkv.qkv_b, L.qkv, 3 * H, R, 3 * H, H, false));
+  HFT_TRY(attn_fwd(m, s, L.qkv, 3 * H, (long long)Lq * 3 * H, L.qkv + H, L.qkv + 2 * H, 3 * H, S, Lq, Lq, L.ctx, L.lse));
+  HFT_TRY(gemm_tn(s, L.ctx, H, m->w[lw.sa.o_w], H, m->w[lw.sa.o_b], tmp, H, R, H, H, false));
+  ln_fwd(m, s, L.xin, tmp, R, lw.ln, R, L.x1, L.s1);
+  HFT_TRY(gemm_tn(s, L.x1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], L.hid, P, R, P, H, true));
+  HFT_TRY(gemm_tn(s, L.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, R, H, P, false));
+  ln_fwd(m, s, L.x1, tmp, R, lw.ln, R, out, L.s2);
+  return HFT_OK;
+}
+
+// EncoderLayer backward: g = dL/d(out) on entry, dL/d(xin) on exit (in place)
+static int enc_layer_bwd(Trainer& t, cudaStream_t s, LayerTape& L, long long S, int Lq, const EncLayerW& lw, const FusedAttn& qkv, float* g, float* gqkv, float* gctx,
+                         float* ghid, float* G) {
+  Model* m = t.m;
+  const int H = m->H, P = m->P;
+  const long long R = S * Lq;
+  ln_bwd(m, s, g, L.s2, lw.ln, R, g, G);
+  HFT_TRY(gemm_dw(s, g, H, L.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), R, H, P));
+  HFT_TRY(gemm_nn(s, g, H, m->w[lw.ff.w2], P, ghid, P, R, P, H, false, L.hid, P));          // through fc_2 and the ReLU
+  HFT_TRY(gemm_dw(s, ghid, P, L.x1, H, gof(m, G, lw.ff.w1), H, gof(m, G, lw.ff.b1), R, P, H));
+  HFT_TRY(gemm_nn(s, ghid, P, m->w[lw.ff.w1], H, g, H, R, H, P, true));                     // + residual path already in g
+  ln_bwd(m, s, g, L.s1, lw.ln, R, g, G);
+  HFT_TRY(gemm_dw(s, g, H, L.ctx, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), R, H, H));
+  HFT_TRY(gemm_nn(s, g, H, m->w[lw.sa.o_w], H, gctx, H, R, H, H, false));
+  HFT_TRY(attn_bwd(m, s, L.qkv, 3 * H, (long long)Lq * 3 * H, L.qkv + H, L.qkv + 2 * H, 3 * H, gctx, L.ctx, L.lse, S, Lq, Lq, gqkv, 3 * H, gqkv + H, gqkv + 2 * H,
+                   3 * H, t.dD));
+  HFT_TRY(gemm_dw(s, gqkv, 3 * H, L.xin, H, gof(m, G, lw.sa.q_w), H, gof(m, G, lw.sa.q_b), R, H, H));
+  HFT_TRY(gemm_dw(s, gqkv + H, 3 * H, L.xin, H, gof(m, G, lw.sa.k_w), H, gof(m, G, lw.sa.k_b), R, H, H));
+  HFT_TRY(gemm_dw(s, gqkv + 2 * H, 3 * H, L.xin, H, gof(m, G, lw.sa.v_w), H, gof(m, G, lw.sa.v_b), R, H, H));
+  HFT_TRY(gemm_nn(s, gqkv, 3 * H, qkv.qkv_w, H, g, H, R, H, 3 * H, true));
+  return HFT_OK;
+}
+
+static int pack_heads(Trainer& t, cudaStream_t s) {
+  Model* m = t.m;
+  for (int i = 0; i < 2; ++i) {
+    const int* idx = i == 0 ? m->head_freq : m->head_time;
+    pack_heads_f32_kernel<<<(t.NP * m->H + 255) / 256, 256, 0, s>>>(m->w[idx[0]], m->w[idx[2]], m->w[idx[4]], m->w[idx[6]], m->w[idx[1]], m->w[idx[3]],
+                                                                     m->w[idx[5]], m->w[idx[7]], m->nvel, m->H, t.NP, t.head_w[i], t.head_b[i]);
+  }
+  return HFT_OK;
+}
+
+static int train_forward(Trainer& t, const float* spec, long long sb, long long sbin, long long st, cudaStream_t s) {
+  Model* m = t.m;
+  const int B = t.B, H = m->H, P = m->P, F = m->nframe, NB = m->nbin, NN = m->nnote;
+  const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
+  const float sqrtH = sqrtf((float)H);
+  float* tmp = t.gX;                                      // scratch [Re, H] (the gradient buffers are idle during the forward)
+  {
+    LaunchScope ls(HFT_KCLASS_FRONT, s);
+    front_f32_kernel<65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.enc[0].xin);
+  }
+  for (size_t l = 0; l < m->enc.size(); ++l)
+    HFT_TRY(enc_layer_fwd(m, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], l + 1 < m->enc.size() ? t.enc[l + 1].xin : t.x_enc, tmp));
+  // decoder layer zero (model_spec2midi.py:255-272)
+  {
+    DecTape& D = t.dec[0];
+    const DecLayerW& lw = m->dec0;
+    HFT_TRY(gemm_tn(s, t.x_enc, H, m->dec_ca_kv[0].qkv_w, H, m->dec_ca_kv[0].qkv_b, D.kv, 2 * H, Re, 2 * H, H, false));
+    HFT_TRY(attn_fwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c));
+    HFT_TRY(gemm_tn(s, D.ctx_c, H, m->w[lw.ca.o_w], H, m->w[lw.ca.o_b], tmp, H, Rd, H, H, false));
+    ln_fwd(m, s, tmp, m->w[m->dec_pos_freq], NN, lw.ln, Rd, D.t1, D.s1);
+    HFT_TRY(gemm_tn(s, D.t1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], D.hid, P, Rd, P, H, true));
+    HFT_TRY(gemm_tn(s, D.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, Rd, H, P, false));
+    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, m->dec.empty() ? t.t_out : t.dec[1].tin, D.s2);
+  }
+  for (size_t l = 0; l < m->dec.size(); ++l) {               // model_spec2midi.py:283-306
+    DecTape& D = t.dec[l + 1];
+    const DecLayerW& lw = m->dec[l];
+    float* out = l + 1 < m->dec.size() ? t.dec[l + 2].tin : t.t_out;
+    HFT_TRY(gemm_tn(s, D.tin, H, m->dec_sa_qkv[l].qkv_w, H, m->dec_sa_qkv[l].qkv_b, D.qkv, 3 * H, Rd, 3 * H, H, false));
+    HFT_TRY(attn_fwd(m, s, D.qkv, 3 * H, (long long)NN * 3 * H, D.qkv + H, D.qkv + 2 * H, 3 * H, Se, NN, NN, D.ctx_s, D.lse_s));
+    HFT_TRY(gemm_tn(s, D.ctx_s, H, m->w[lw.sa.o_w], H, m->w[lw.sa.o_b], tmp, H, Rd, H, H, false));
+    ln_fwd(m, s, D.tin, tmp, Rd, lw.ln, Rd, D.t0, D.s0);
+    HFT_TRY(gemm_tn(s, D.t0, H, m->w[lw.ca.q_w], H, m->w[lw.ca.q_b], D.qc, H, Rd, H, H, false));
+    HFT_TRY(gemm_tn(s, t.x_enc, H, m->dec_ca_kv[l + 1].qkv_w, H, m->dec_ca_kv[l + 1].qkv_b, D.kv, 2 * H, Re, 2 * H, H, false));
+    HFT_TRY(attn_fwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c));
+    HFT_TRY(gemm_tn(s, D.ctx_c, H, m->w[lw.ca.o_w], H, m->w[lw.ca.o_b], tmp, H, Rd, H, H, false));
+    ln_fwd(m, s, D.t0, tmp, Rd, lw.ln, Rd, D.t1, D.s1);
+    HFT_TRY(gemm_tn(s, D.t1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], D.hid, P, Rd, P, H, true));
+    HFT_TRY(gemm_tn(s, D.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, Rd, H, P, false));
+    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, out, D.s2);
+  }
+  HFT_TRY(pack_heads(t, s));
+  HFT_TRY(gemm_tn(s, t.t_out, H, t.head_w[0], H, t.head_b[0], t.logits_a, t.NP, Rd, t.NP, H, false));
+  {
+    LaunchScope ls(HFT_KCLASS_NORM, s);
+    time_relayout_f32_kernel<<<(unsigned)((Rd * H + 255) / 256), 256, 0, s>>>(t.t_out, m->w[m->pos_time], sqrtH, F, NN, H, Rd * H, t.tim.empty() ? t.u_out : t.tim[0].xin);
+  }
+  for (size_t l = 0; l < m->tim.size(); ++l)
+    HFT_TRY(enc_layer_fwd(m, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], l + 1 < m->tim.size() ? t.tim[l + 1].xin : t.u_out, tmp));
+  HFT_TRY(gemm_tn(s, t.u_out, H, t.head_w[1], H, t.head_b[1], t.logits_b, t.NP, Rd, t.NP, H, false));
+  return HFT_OK;
+}
+
+// ---- backward -------------------------------------------------------------------------------------------------------
+static int heads_bwd(Trainer& t, cudaStream_t s, int which, const float* x, float* gx, bool accum, float* G) {
+  Model* m = t.m;
+  const int H = m->H;
+  const long long Rd = (long long)t.B * m->nframe * m->nnote;
+  const int* idx = which == 0 ? m->head_freq : m->head_time;
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.g_head_w, 0, (size_t)t.NP * H * sizeof(float), s));
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.g_head_b, 0, (size_t)t.NP * sizeof(float), s));
+  HFT_TRY(gemm_dw(s, t.gLOG, t.NP, x, H, t.g_head_w, H, t.g_head_b, Rd, t.NP, H));
+  unpack_heads_grad_kernel<<<((3 + m->nvel) * H + 255) / 256, 256, 0, s>>>(t.g_head_w, t.g_head_b, m->nvel, H, gof(m, G, idx[0]), gof(m, G, idx[2]), gof(m, G, idx[4]),
+                                                                           gof(m, G, idx[6]), gof(m, G, idx[1]), gof(m, G, idx[3]), gof(m, G, idx[5]), gof(m, G, idx[7]));
+  HFT_TRY(gemm_nn(s, t.gLOG, t.NP, t.head_w[which], H, gx, H, Rd, H, t.NP, accum));
+  return HFT_OK;
+}
+
+// FFN + LayerNorm block of a decoder layer: g = dL/d(out) -> dL/d(t1)
+static int dec_ffn_bwd(Trainer& t, cudaStream_t s, DecTape& D, const DecLayerW& lw, long long Rd, float* g, float* G) {
+  Model* m = t.m;
+  const int H = m->H, P = m->P;
+  ln_bwd(m, s, g, D.s2, lw.ln, Rd, g, G);
+  HFT_TRY(gemm_dw(s, g, H, D.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), Rd, H, P));
+  HFT_TRY(gemm_nn(s, g, H, m->w[lw.ff.w2], P, t.gHID, P, Rd, P, H, false, D.hid, P));
+  HFT_TRY(gemm_dw(s, t.gHID, P, D.t1, H, gof(m, G, lw.ff.w1), H, gof(m, G, lw.ff.b1), Rd, P, H));
+  HFT_TRY(gemm_nn(s, t.gHID, P, m->w[lw.ff.w1], H, g, H, Rd, H, P, true));
+  return HFT_OK;
+}
+
+static int train_backward(Trainer& t, const float* spec, long long sb, long long sbin, long long st, const float* y_on, const float* y_off, const float* y_mpe,
+                          const long long* y_vel, float wA, float wB, float* loss, float* G, cudaStream_t s) {
+  Model* m = t.m;
+  const int B = t.B, H = m->H, F = m->nframe, NB = m->nbin, NN = m->nnote, V = m->nvel;
+  const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
+  const float sqrtH = sqrtf((float)H);
+  HFT_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  // ---- heads B + time stack ----
+  {
+    LaunchScope ls(HFT_KCLASS_HEADS, s);
+    loss_grad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t.logits_b, t.NP, V, F, NN, Rd, true, y_on, y_off, y_mpe, y_vel, wB, t.gLOG, loss);
+  }
+  HFT_TRY(heads_bwd(t, s, 1, t.u_out, t.gU, false, G));
+  for (int l = (int)m->tim.size() - 1; l >= 0; --l)
+    HFT_TRY(enc_layer_bwd(t, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], t.gU, t.gDQ, t.gCTX, t.gHID, G));
+  colsum(s, t.gU, (long long)B * NN, (long long)F * H, gof(m, G, m->pos_time));          // pos_embedding_time
+  // ---- heads A + re-layout ----
+  {
+    LaunchScope ls(HFT_KCLASS_HEADS, s);
+    loss_grad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t.logits_a, t.NP, V, F, NN, Rd, false, y_on, y_off, y_mpe, y_vel, wA, t.gLOG, loss);
+  }
+  HFT_TRY(heads_bwd(t, s, 0, t.t_out, t.gT, false, G));
+  {
+    LaunchScope ls(HFT_KCLASS_NORM, s);
+    time_relayout_bwd_kernel<<<(unsigned)((Rd * H + 255) / 256), 256, 0, s>>>(t.gU, sqrtH, F, NN, H, Rd * H, t.gT);
+  }
+  // ---- decoder ----
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.gX, 0, (size_t)Re * H * sizeof(float), s));          // dL/d(encoder output), summed over the cross-attentions
+  float* gkv = t.gBIG;                                                                  // [Re, 2H]
+  auto cross_kv_bwd = [&](DecTape& D, const DecLayerW& lw, const FusedAttn& kv) -> int {
+    HFT_TRY(gemm_dw(s, gkv, 2 * H, t.x_enc, H, gof(m, G, lw.ca.k_w), H, gof(m, G, lw.ca.k_b), Re, H, H));
+    HFT_TRY(gemm_dw(s, gkv + H, 2 * H, t.x_enc, H, gof(m, G, lw.ca.v_w), H, gof(m, G, lw.ca.v_b), Re, H, H));
+    HFT_TRY(gemm_nn(s, gkv, 2 * H, kv.qkv_w, H, t.gX, H, Re, H, 2 * H, true));
+    (void)D;
+    return HFT_OK;
+  };
+  for (int l = (int)m->dec.size() - 1; l >= 0; --l) {
+    DecTape& D = t.dec[l + 1];
+    const DecLayerW& lw = m->dec[l];
+    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G));
+    ln_bwd(m, s, t.gT, D.s1, lw.ln, Rd, t.gT, G);
+    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
+    HFT_TRY(attn_bwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD));
+    HFT_TRY(gemm_dw(s, t.gDQ, H, D.t0, H, gof(m, G, lw.ca.q_w), H, gof(m, G, lw.ca.q_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, t.gDQ, H, m->w[lw.ca.q_w], H, t.gT, H, Rd, H, H, true));
+    HFT_TRY(cross_kv_bwd(D, lw, m->dec_ca_kv[l + 1]));
+    ln_bwd(m, s, t.gT, D.s0, lw.ln, Rd, t.gT, G);
+    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_s, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.sa.o_w], H, t.gCTX, H, Rd, H, H, false));
+    HFT_TRY(attn_bwd(m, s, D.qkv, 3 * H, (long long)NN * 3 * H, D.qkv + H, D.qkv + 2 * H, 3 * H, t.gCTX, D.ctx_s, D.lse_s, Se, NN, NN, t.gDQ, 3 * H, t.gDQ + H,
+                     t.gDQ + 2 * H, 3 * H, t.dD));
+    HFT_TRY(gemm_dw(s, t.gDQ, 3 * H, D.tin, H, gof(m, G, lw.sa.q_w), H, gof(m, G, lw.sa.q_b), Rd, H, H));
+    HFT_TRY(gemm_dw(s, t.gDQ + H, 3 * H, D.tin, H, gof(m, G, lw.sa.k_w), H, gof(m, G, lw.sa.k_b), Rd, H, H));
+    HFT_TRY(gemm_dw(s, t.gDQ + 2 * H, 3 * H, D.tin, H, gof(m, G, lw.sa.v_w), H, gof(m, G, lw.sa.v_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, t.gDQ, 3 * H, m->dec_sa_qkv[l].qkv_w, H, t.gT, H, Rd, H, 3 * H, true));
+  }
+  {                                                                                     // layer zero
+    DecTape& D = t.dec[0];
+    const DecLayerW& lw = m->dec0;
+    float* g_pos = gof(m, G, m->dec_pos_freq);
+    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G));
+    ln_bwd(m, s, t.gT, D.s1, lw.ln, Rd, t.gT, G);                                       // s1 = pos_embedding_freq + fc_o(ctx)
+    colsum(s, t.gT, Se, (long long)NN * H, g_pos);
+    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
+    HFT_TRY(attn_bwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD));
+    HFT_CHECK_CUDA(cudaMemsetAsync(t.gQ0, 0, (size_t)NN * H * sizeof(float), s));
+    colsum(s, t.gDQ, Se, (long long)NN * H, t.gQ0);                                     // the same projected queries serve every sequence
+    HFT_TRY(gemm_dw(s, t.gQ0, H, m->w[m->dec_pos_freq], H, gof(m, G, lw.ca.q_w), H, gof(m, G, lw.ca.q_b), NN, H, H));
+    HFT_TRY(gemm_nn(s, t.gQ0, H, m->w[lw.ca.q_w], H, g_pos, H, NN, H, H, true));
+    HFT_TRY(cross_kv_bwd(D, lw, m->dec_ca_kv[0]));
+  }
+  // ---- encoder ----
+  for (int l = (int)m->enc.size() - 1; l >= 0; --l)
+    HFT_TRY(enc_layer_bwd(t, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], t.gX, t.gBIG, t.gCTX, t.gHID, G));
+  colsum(s, t.gX, Se, (long long)NB * H, gof(m, G, m->pos_freq));                       // pos_embedding_freq (encoder)
+  // ---- front: conv + Linear through the collapsed 65-tap filter ----
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.g_front_w, 0, (size_t)H * m->nproc * sizeof(float), s));
+  HFT_CHECK_CUDA(cudaMemsetAsync(t.g_front_b, 0, (size_t)H * sizeof(float), s));
+  {
+    LaunchScope ls(HFT_KCLASS_FRONT, s);
+    if (H == 64) front_bwd_kernel<65, 4><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    else if (H == 128) front_bwd_kernel<65, 2><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    else front_bwd_kernel<65, 1><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    const int C = m->d.cnn_channel, kw = m->d.cnn_kernel, n_out = m->nproc - (kw - 1);
+    const int total = H * C * n_out + H + C * kw + C;
+    front_chain_bwd_kernel<<<(total + 127) / 128, 128, 0, s>>>(t.g_front_w, t.g_front_b, m->w[m->tok_w], m->w[m->conv_w], m->w[m->conv_b], H, C, kw, n_out, m->nproc,
+                                                                gof(m, G, m->tok_w), gof(m, G, m->tok_b), gof(m, G, m->conv_w), gof(m, G, m->conv_b));
+  }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
+int derive_weights_public(Model* m, cudaStream_t s);      // model.cu
+
+}  // namespace hft
+
+using namespace hft;
+
+extern "C" int hft_trainer_create(hft_trainer** out, hft_model* model, int32_t batch) {
+  HFT_REQUIRE(out && model && batch >= 1, HFT_ERR_ARG, "hft_trainer_create: bad argument");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_trainer_create: call hft_model_set_weights first");
+  HFT_REQUIRE(m->nvel == 128 && m->nproc == 65, HFT_ERR_UNSUPPORTED, "hft_trainer_create: built for 128 velocities and margin 32");
+  Trainer* t = new Trainer();
+  t->m = m;
+  t->B = batch;
+  int rc = alloc_tape(*t);
+  if (rc != HFT_OK) { cudaFree(t->arena); delete t; return rc; }
+  *out = reinterpret_cast<hft_trainer*>(t);
+  return HFT_OK;
+}
+
+extern "C" int hft_trainer_destroy(hft_trainer* trainer) {
+  if (!trainer) return HFT_OK;
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  cudaFree(t->arena);
+  delete t;
+  return HFT_OK;
+}
+
+extern "C" int64_t hft_model_param_floats(const hft_model* model) {
+  const Model* m = reinterpret_cast<const Model*>(model);
+  if (!m) return -1;
+  int64_t total = 0;
+  for (auto& w : m->spec) total += (w.numel + 3) & ~3ll;
+  return total;
+}
+extern "C" int64_t hft_model_param_offset(const hft_model* model, int index) {
+  const Model* m = reinterpret_cast<const Model*>(model);
+  if (!m || index < 0 || index >= (int)m->spec.size()) return -1;
+  int64_t off = 0;
+  for (int i = 0; i < index; ++i) off += (m->spec[i].numel + 3) & ~3ll;
+  return off;
+}
+extern "C" float* hft_model_params(hft_model* model) { return model ? reinterpret_cast<Model*>(model)->arena : nullptr; }
+
+extern "C" int hft_model_get_params(hft_model* model, float* params_out_dev, void* stream) {
+  HFT_REQUIRE(model && params_out_dev, HFT_ERR_ARG, "hft_model_get_params: NULL argument");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_model_get_params: no weights registered");
+  HFT_CHECK_CUDA(cudaMemcpyAsync(params_out_dev, m->arena, (size_t)hft_model_param_floats(model) * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HFT_OK;
+}
+
+extern "C" int hft_model_refresh(hft_model* model, void* stream) {
+  HFT_REQUIRE(model, HFT_ERR_ARG, "hft_model_refresh: NULL model");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_model_refresh: no weights registered");
+  HFT_TRY(derive_weights_public(m, (cudaStream_t)stream));
+  return tc_prepare_weights(m, (cudaStream_t)stream);
+}
+
+extern "C" int hft_train_forward_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                                          const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
+                                          const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream) {
+  HFT_REQUIRE(trainer && spec_dev && label_onset_dev && label_offset_dev && label_mpe_dev && label_velocity_dev && loss_dev && grads_dev, HFT_ERR_ARG,
+              "hft_train_forward_backward: NULL argument");
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_launch_count();
+  HFT_CHECK_CUDA(cudaMemsetAsync(grads_dev, 0, (size_t)hft_model_param_floats(reinterpret_cast<hft_model*>(t->m)) * sizeof(float), s));
+  HFT_TRY(train_forward(*t, spec_dev, stride_b, stride_bin, stride_t, s));
+  return train_backward(*t, spec_dev, stride_b, stride_bin, stride_t, label_onset_dev, label_offset_dev, label_mpe_dev,
+                        reinterpret_cast<const long long*>(label_velocity_dev), weight_A, weight_B, loss_dev, grads_dev, s);
+}
+
+extern "C" int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,
+                             float eps, int64_t step, float grad_scale, void* stream) {
+  HFT_REQUIRE(params_dev && grads_dev && exp_avg_dev && exp_avg_sq_dev && n >= 0 && step >= 1, HFT_ERR_ARG, "hft_adam_step: bad argument");
+  if (n == 0) return HFT_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  reset_launch_count();
+  {
+    LaunchScope ls(HFT_KCLASS_NORM, stream);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev, n, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+  }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}

@@ -1,0 +1,528 @@
+// fp32 CUDA-core kernels of the training step (reference hftt_code/training/train.py:89-160): the backward passes of the
+// hFT layers (Linear, LayerNorm, multi-head attention, ReLU, embeddings, the conv+Linear front), the 8-term loss
+// (BCELoss on the six sigmoid outputs + CrossEntropyLoss on the two velocity logit tensors) and Adam.
+#pragma once
+#include "f32_kernels.cuh"
+
+namespace hft {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// C[M,N] (+)= A[M,K] * B[K,N]   (dX = dY * W with W = [out,in] row-major as B).  Optional ReLU mask: C *= (mask > 0).
+// 128x128x16 tiles like sgemm_tn_kernel.  K % 16 == 0, N % 4 == 0, lda % 4 == 0, ldb % 4 == 0.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                                       float* __restrict__ C, int ldc, int M, int N, int K, bool accum,
+                                                       const float* __restrict__ mask, int ldm) {
+  __shared__ __align__(16) float As[GBK][GBM + GPAD];
+  __shared__ __align__(16) float Bs[GBK][GBN + GPAD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int lrow = tid >> 1, lk = (tid & 1) * 8;          // A tile: 128 rows x 16 k
+  const int brow = tid >> 4, bcol = (tid & 15) * 8;       // B tile: 16 k x 128 cols
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const bool a_ok = (m0 + lrow) < M;
+  const bool b_ok0 = (n0 + bcol) < N, b_ok1 = (n0 + bcol + 4) < N;
+  const float* ap = A + (long long)(m0 + lrow) * lda + lk;
+  const float* bp = Bm + (long long)brow * ldb + n0 + bcol;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a0 = a_ok ? *reinterpret_cast<const float4*>(ap) : z, a1 = a_ok ? *reinterpret_cast<const float4*>(ap + 4) : z;
+  float4 b0 = b_ok0 ? *reinterpret_cast<const float4*>(bp) : z, b1 = b_ok1 ? *reinterpret_cast<const float4*>(bp + 4) : z;
+  for (int k0 = 0; k0 < K; k0 += GBK) {
+    As[lk + 0][lrow] = a0.x; As[lk + 1][lrow] = a0.y; As[lk + 2][lrow] = a0.z; As[lk + 3][lrow] = a0.w;
+    As[lk + 4][lrow] = a1.x; As[lk + 5][lrow] = a1.y; As[lk + 6][lrow] = a1.z; As[lk + 7][lrow] = a1.w;
+    *reinterpret_cast<float4*>(&Bs[brow][bcol]) = b0;
+    *reinterpret_cast<float4*>(&Bs[brow][bcol + 4]) = b1;
+    __syncthreads();
+    if (k0 + GBK < K) {
+      a0 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK) : z;
+      a1 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK + 4) : z;
+      const float* bq = bp + (long long)(k0 + GBK) * ldb;
+      b0 = b_ok0 ? *reinterpret_cast<const float4*>(bq) : z;
+      b1 = b_ok1 ? *reinterpret_cast<const float4*>(bq + 4) : z;
+    }
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      float4 ra0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 ra1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      float4 rb0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float4 rb1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      float ra[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
+      float rb[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (col >= N) continue;
+      float v = acc[i][j];
+      if (mask && !(mask[(long long)row * ldm + col] > 0.f)) v = 0.f;
+      if (accum) v += C[(long long)row * ldc + col];
+      C[(long long)row * ldc + col] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dW[N,K] += dY[M,N]^T * X[M,K],  db[N] += colsum(dY)      (weight gradient of y = x W^T + b)
+// grid (ceil(N/64), ceil(K/64), splits): every CTA reduces its slice of the M rows into a 64 x 64 tile held in registers
+// (4 x 4 per thread) and adds it to dW with fp32 atomics.  N, K arbitrary (guards); ldy % 4 == 0 and ldx % 4 == 0.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DWT = 64, DWR = 16;
+__global__ void __launch_bounds__(256) dw_gemm_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW,
+                                                      int ldw, float* __restrict__ db, long long M, int N, int K, long long rows_per_split) {
+  __shared__ __align__(16) float Ys[DWR][DWT];
+  __shared__ __align__(16) float Xs[DWR][DWT];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * DWT, k0 = blockIdx.y * DWT;
+  const long long m_begin = (long long)blockIdx.z * rows_per_split;
+  const long long m_end = (m_begin + rows_per_split < M) ? m_begin + rows_per_split : M;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;           // loader: row 0..15, 4 columns
+  const int tn = tid >> 4, tk = tid & 15;                 // compute: n = tn*4.., k = tk*4..
+  float acc[4][4], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long m = m_begin; m < m_end; m += DWR) {
+    const long long row = m + lr;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
+    if (row < m_end) {
+      const float* yp = dY + row * ldy + n0 + lc;
+      const float* xp = X + row * ldx + k0 + lc;
+      if (n0 + lc + 3 < N) y = *reinterpret_cast<const float4*>(yp);
+      else { if (n0 + lc < N) y.x = yp[0]; if (n0 + lc + 1 < N) y.y = yp[1]; if (n0 + lc + 2 < N) y.z = yp[2]; }
+      if (k0 + lc + 3 < K) x = *reinterpret_cast<const float4*>(xp);
+      else { if (k0 + lc < K) x.x = xp[0]; if (k0 + lc + 1 < K) x.y = xp[1]; if (k0 + lc + 2 < K) x.z = xp[2]; }
+    }
+    *reinterpret_cast<float4*>(&Ys[lr][lc]) = y;
+    *reinterpret_cast<float4*>(&Xs[lr][lc]) = x;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < DWR; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&Ys[r][tn * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Xs[r][tk * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bsum[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tn * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (k < K) atomicAdd(dW + (long long)n * ldw + k, acc[i][j]);
+    }
+    if (db && blockIdx.y == 0 && tk == 0) atomicAdd(db + n, bsum[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm backward (y = (s - mean) * rstd * g + b, s = the saved pre-LayerNorm sum):
+//   ds = rstd * (dy g - mean(dy g) - xhat * mean(dy g xhat)),  dg += sum dy xhat,  db += sum dy.   One warp per row,
+// 8 rows per warp; the block's column partials go through shared memory and one atomicAdd per column.
+// dy and ds may alias.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ g, int H,
+                                                     long long rows, float* __restrict__ ds, float* __restrict__ dg, float* __restrict__ db) {
+  __shared__ float s_dg[8][256], s_db[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = H >> 5;
+  float pg[8], pb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
+  const long long row0 = ((long long)blockIdx.x * 8 + warp) * 8;
+  for (int rr = 0; rr < 8; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) break;
+    float v[8], d[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) { v[i] = s[row * H + lane + 32 * i]; d[i] = dy[row * H + lane + 32 * i]; sum += v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) { float t = v[i] - mean; q = fmaf(t, t, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)H + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) {
+        const float xh = (v[i] - mean) * rstd;
+        const float dxh = d[i] * g[lane + 32 * i];
+        pg[i] = fmaf(d[i], xh, pg[i]);
+        pb[i] += d[i];
+        v[i] = xh; d[i] = dxh;
+        m1 += dxh; m2 = fmaf(dxh, xh, m2);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+    m1 /= (float)H; m2 /= (float)H;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) ds[row * H + lane + 32 * i] = rstd * (d[i] - m1 - v[i] * m2);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per) { s_dg[warp][lane + 32 * i] = pg[i]; s_db[warp][lane + 32 * i] = pb[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += s_dg[w][c]; b += s_db[w][c]; }
+    atomicAdd(dg + c, a);
+    atomicAdd(db + c, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Attention backward for one (sequence, head), scores recomputed from Q, K and the saved row log-sum-exp:
+//   P = exp(Q K^T c - lse),  dP = dO V^T,  D_i = dO_i . O_i,  dS = P (dP - D) c,  dQ = dS K,  dK = dS^T Q,  dV = P^T dO.
+// Pass 1 (one thread per query row): dQ and D.  Pass 2 (one thread per key row): dK and / or dV, no atomics.
+// ------------------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
+                                                          const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, const float* __restrict__ O,
+                                                          int ldo, const float* __restrict__ lse, int Lq, int Lk, int heads, float c,
+                                                          float* __restrict__ dQ, int lddq, float* __restrict__ Dout) {
+  extern __shared__ __align__(16) float smem_bwd[];
+  float* sK = smem_bwd;
+  float* sV = smem_bwd + (size_t)Lk * DH;
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const float* kbase = Kp + (long long)seq * Lk * ldkv + head * DH;
+  const float* vbase = Vp + (long long)seq * Lk * ldkv + head * DH;
+  for (int i = threadIdx.x; i < Lk * (DH / 4); i += blockDim.x) {
+    int j = i / (DH / 4), cc = i % (DH / 4);
+    reinterpret_cast<float4*>(sK)[i] = *reinterpret_cast<const float4*>(kbase + (long long)j * ldkv + cc * 4);
+    reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(vbase + (long long)j * ldkv + cc * 4);
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r >= Lq) return;
+  float q[DH], go[DH], acc[DH];
+  const float* qp = Q + (long long)seq * q_seq_stride + (long long)r * ldq + head * DH;
+  const float* gp = dO + ((long long)seq * Lq + r) * ldo + head * DH;
+  const float* op = O + ((long long)seq * Lq + r) * ldo + head * DH;
+  float D = 0.f;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) { q[i] = qp[i]; go[i] = gp[i]; D = fmaf(go[i], op[i], D); acc[i] = 0.f; }
+  const float l = lse[((long long)seq * heads + head) * Lq + r];
+  for (int j = 0; j < Lk; ++j) {
+    const float* kr = sK + (size_t)j * DH;
+    const float* vr = sV + (size_t)j * DH;
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) { s = fmaf(q[i], kr[i], s); dp = fmaf(go[i], vr[i], dp); }
+    const float ds = expf(s * c - l) * (dp - D) * c;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) acc[i] = fmaf(ds, kr[i], acc[i]);
+  }
+  float* out = dQ + ((long long)seq * Lq + r) * lddq + head * DH;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) out[i] = acc[i];
+  Dout[((long long)seq * heads + head) * Lq + r] = D;
+}
+
+// MODE 0: dK and dV, 1: dK only, 2: dV only (head_dim 64 needs two passes to stay inside the register file)
+template <int DH, int MODE>
+__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
+                                                           const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, int ldo,
+                                                           const float* __restrict__ lse, const float* __restrict__ Din, int Lq, int Lk, int heads, float c,
+                                                           float* __restrict__ dK, float* __restrict__ dV, int lddkv) {
+  extern __shared__ __align__(16) float smem_bwd[];
+  float* sQ = smem_bwd;
+  float* sG = smem_bwd + (size_t)Lq * DH;
+  float* sL = sG + (size_t)Lq * DH;
+  float* sD = sL + Lq;
+  const int seq = blockIdx.x, head = blockIdx.y;
+  for (int i = threadIdx.x; i < Lq * (DH / 4); i += blockDim.x) {
+    int j = i / (DH / 4), cc = i % (DH / 4);
+    reinterpret_cast<float4*>(sQ)[i] = *reinterpret_cast<const float4*>(Q + (long long)seq * q_seq_stride + (long long)j * ldq + head * DH + cc * 4);
+    reinterpret_cast<float4*>(sG)[i] = *reinterpret_cast<const float4*>(dO + ((long long)seq * Lq + j) * ldo + head * DH + cc * 4);
+  }
+  for (int i = threadIdx.x; i < Lq; i += blockDim.x) {
+    sL[i] = lse[((long long)seq * heads + head) * Lq + i];
+    sD[i] = Din[((long long)seq * heads + head) * Lq + i];
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j >= Lk) return;
+  float k[DH], v[MODE == 2 ? 1 : DH], ak[MODE == 2 ? 1 : DH], av[MODE == 1 ? 1 : DH];
+  const float* kp = Kp + ((long long)seq * Lk + j) * ldkv + head * DH;
+  const float* vp = Vp + ((long long)seq * Lk + j) * ldkv + head * DH;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) {
+    k[i] = kp[i];
+    if (MODE != 2) { v[i] = vp[i]; ak[i] = 0.f; }
+    if (MODE != 1) av[i] = 0.f;
+  }
+  for (int r = 0; r < Lq; ++r) {
+    const float* qr = sQ + (size_t)r * DH;
+    const float* gr = sG + (size_t)r * DH;
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) {
+      s = fmaf(qr[i], k[i], s);
+      if (MODE != 2) dp = fmaf(gr[i], v[i], dp);
+    }
+    const float p = expf(s * c - sL[r]);
+    if (MODE != 1) {
+#pragma unroll
+      for (int i = 0; i < DH; ++i) av[i] = fmaf(p, gr[i], av[i]);
+    }
+    if (MODE != 2) {
+      const float ds = p * (dp - sD[r]) * c;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) ak[i] = fmaf(ds, qr[i], ak[i]);
+    }
+  }
+  if (MODE != 2) {
+    float* o = dK + ((long long)seq * Lk + j) * lddkv + head * DH;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = ak[i];
+  }
+  if (MODE != 1) {
+    float* o = dV + ((long long)seq * Lk + j) * lddkv + head * DH;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = av[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Loss of one head group (train.py:139-151) and its gradient with respect to the logits.
+//   logits [rows, ld]: columns 0..2 onset / offset / mpe (pre-sigmoid), 3..3+V-1 velocity; rows in (b,f,n) order, or
+//   (b,n,f) when time_major.  labels are [B,F,NN] in (b,f,n) order.  Every term is a mean over the rows positions:
+//   BCELoss (log clamped at -100 like torch) on sigmoid(logit), CrossEntropyLoss on the velocity logits.
+//   dlogits = weight * dLoss/dlogit;  loss[0] += weight * sum of the four terms.   One warp per row (V = 128).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, int ld, int V, int F, int NN, long long rows, bool time_major,
+                                                        const float* __restrict__ y_on, const float* __restrict__ y_off, const float* __restrict__ y_mpe,
+                                                        const long long* __restrict__ y_vel, float weight, float* __restrict__ dlogits,
+                                                        float* __restrict__ loss) {
+  __shared__ float s_loss[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  float part = 0.f;
+  if (row < rows) {
+    long long lrow = row;
+    if (time_major) {
+      int f = (int)(row % F);
+      long long bn = row / F;
+      int n = (int)(bn % NN);
+      lrow = ((bn / NN) * F + f) * NN + n;
+    }
+    const float inv_n = 1.f / (float)rows;
+    const float* lp = logits + row * ld;
+    float* gp = dlogits + row * ld;
+    // velocity: V = 128 -> 4 logits per lane
+    float v[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = lp[3 + lane + 32 * i]; mx = fmaxf(mx, v[i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) se += expf(v[i] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lsum = mx + logf(se);
+    const int lab = (int)y_vel[lrow];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = lane + 32 * i;
+      const float p = expf(v[i] - lsum);
+      gp[3 + col] = weight * inv_n * (p - (col == lab ? 1.f : 0.f));
+      if (col == lab) part += (lsum - v[i]) * inv_n;
+    }
+    if (lane < 3) {
+      const float* yy = lane == 0 ? y_on : (lane == 1 ? y_off : y_mpe);
+      const float y = yy[lrow];
+      const float z = lp[lane];
+      const float p = 1.f / (1.f + expf(-z));
+      const float l1 = fmaxf(logf(p), -100.f), l0 = fmaxf(logf(1.f - p), -100.f);
+      part += -(y * l1 + (1.f - y) * l0) * inv_n;
+      const float pq = p * (1.f - p);
+      gp[lane] = weight * inv_n * (p - y) * (pq / fmaxf(pq, 1e-12f));
+    }
+    for (int col = 3 + V + lane; col < ld; col += 32) gp[col] = 0.f;     // padding columns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  }
+  if (lane == 0) s_loss[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_loss[w];
+    atomicAdd(loss, weight * t);
+  }
+}
+
+// out[c] += sum_r in[r, c]   (embedding gradients: the same table row is added to many sequences).  grid (ceil(cols/256), splits)
+__global__ void colsum_kernel(const float* __restrict__ in, long long rows, long long cols, long long rows_per_split, float* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_split;
+  const long long r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
+  float a = 0.f;
+  for (long long r = r0; r < r1; ++r) a += in[r * cols + c];
+  atomicAdd(out + c, a);
+}
+
+// gT[((b*F+f)*NN+n), h] += gU[((b*NN+n)*F+f), h] * scale     (backward of the time re-layout, model_spec2midi.py:189-191)
+__global__ void time_relayout_bwd_kernel(const float* __restrict__ gU, float scale, int F, int NN, int H, long long total, float* __restrict__ gT) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int h = (int)(i % H);
+  long long r = i / H;
+  int f = (int)(r % F);
+  long long bn = r / F;
+  int n = (int)(bn % NN);
+  long long b = bn / NN;
+  gT[(((b * F + f) * NN + n)) * H + h] += gU[i] * scale;
+}
+
+// Front backward: dWc[h, j] += sum_{b,f} dE[(b,f,bin), h] * spec[b, bin, f + j],  dbc[h] += sum dE   (collapsed 65-tap filter).
+// grid (n_bin); threads = G tap groups x H (G * H = 256).  dE = dX * sqrt(H) (the embedding scale).
+template <int NPROC, int G>
+__global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st, const float* __restrict__ dX,
+                                                        float scale, int H, int F, int NB, int B, float* __restrict__ dWc, float* __restrict__ dbc) {
+  __shared__ float s_row[256];
+  const int bin = blockIdx.x;
+  const int W = F + NPROC - 1;
+  const int h = threadIdx.x % H, g = threadIdx.x / H;
+  constexpr int NA = (NPROC + G - 1) / G;
+  float acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  for (int b = 0; b < B; ++b) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < W; i += blockDim.x) s_row[i] = spec[b * sb + bin * sbin + i * st];
+    __syncthreads();
+    for (int f = 0; f < F; ++f) {
+      const float e = dX[(((long long)b * F + f) * NB + bin) * H + h] * scale;
+      if (g == 0) bsum += e;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int j = g + a * G;
+        if (j < NPROC) acc[a] = fmaf(e, s_row[f + j], acc[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const int j = g + a * G;
+    if (j < NPROC) atomicAdd(dWc + h * NPROC + j, acc[a]);
+  }
+  if (g == 0) atomicAdd(dbc + h, bsum);
+}
+
+// Chain rule through the collapse Wc[h,j] = sum_{c,i} tok_w[h, c*n_out + (j-i)] conv_w[c,i],  bc[h] = tok_b[h] + sum tok_w conv_b:
+//   d tok_w[h, c*n_out+k] = sum_i dWc[h,k+i] conv_w[c,i] + dbc[h] conv_b[c];   d conv_w[c,i] = sum_{h,k} dWc[h,k+i] tok_w[h,c*n_out+k];
+//   d conv_b[c] = sum_h dbc[h] sum_k tok_w[h,c*n_out+k];   d tok_b = dbc.
+__global__ void front_chain_bwd_kernel(const float* __restrict__ dWc, const float* __restrict__ dbc, const float* __restrict__ tok_w,
+                                       const float* __restrict__ conv_w, const float* __restrict__ conv_b, int H, int C, int kw, int n_out, int n_proc,
+                                       float* __restrict__ g_tok_w, float* __restrict__ g_tok_b, float* __restrict__ g_conv_w, float* __restrict__ g_conv_b) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_tok = H * C * n_out;
+  if (idx < n_tok) {
+    const int h = idx / (C * n_out), c = (idx / n_out) % C, k = idx % n_out;
+    float a = dbc[h] * conv_b[c];
+    for (int i = 0; i < kw; ++i) a = fmaf(dWc[h * n_proc + k + i], conv_w[c * kw + i], a);
+    g_tok_w[idx] += a;
+  } else if (idx < n_tok + H) {
+    g_tok_b[idx - n_tok] += dbc[idx - n_tok];
+  } else if (idx < n_tok + H + C * kw) {
+    const int e = idx - n_tok - H, c = e / kw, i = e % kw;
+    float a = 0.f;
+    for (int h = 0; h < H; ++h)
+      for (int k = 0; k < n_out; ++k) a = fmaf(dWc[h * n_proc + k + i], tok_w[(long long)h * C * n_out + c * n_out + k], a);
+    g_conv_w[e] += a;
+  } else if (idx < n_tok + H + C * kw + C) {
+    const int c = idx - n_tok - H - C * kw;
+    float a = 0.f;
+    for (int h = 0; h < H; ++h) {
+      float t = 0.f;
+      for (int k = 0; k < n_out; ++k) t += tok_w[(long long)h * C * n_out + c * n_out + k];
+      a = fmaf(dbc[h], t, a);
+    }
+    g_conv_b[c] += a;
+  }
+}
+
+// heads: fused [NP, H] weight / [NP] bias (rows 0..2 onset / offset / mpe, 3..3+V-1 velocity, rest zero padding)
+__global__ void pack_heads_f32_kernel(const float* __restrict__ w_on, const float* __restrict__ w_off, const float* __restrict__ w_mpe,
+                                      const float* __restrict__ w_vel, const float* __restrict__ b_on, const float* __restrict__ b_off,
+                                      const float* __restrict__ b_mpe, const float* __restrict__ b_vel, int V, int H, int NP, float* __restrict__ w,
+                                      float* __restrict__ bias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP * H) return;
+  int r = i / H, h = i % H;
+  float v = 0.f, b = 0.f;
+  if (r == 0) { v = w_on[h]; b = b_on[0]; }
+  else if (r == 1) { v = w_off[h]; b = b_off[0]; }
+  else if (r == 2) { v = w_mpe[h]; b = b_mpe[0]; }
+  else if (r < 3 + V) { v = w_vel[(r - 3) * H + h]; b = b_vel[r - 3]; }
+  w[i] = v;
+  if (h == 0) bias[r] = b;
+}
+__global__ void unpack_heads_grad_kernel(const float* __restrict__ gw, const float* __restrict__ gb, int V, int H, float* __restrict__ g_on,
+                                         float* __restrict__ g_off, float* __restrict__ g_mpe, float* __restrict__ g_vel, float* __restrict__ gb_on,
+                                         float* __restrict__ gb_off, float* __restrict__ gb_mpe, float* __restrict__ gb_vel) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (3 + V) * H) return;
+  int r = i / H, h = i % H;
+  float* dst = r == 0 ? g_on + h : (r == 1 ? g_off + h : (r == 2 ? g_mpe + h : g_vel + (long long)(r - 3) * H + h));
+  *dst += gw[i];
+  if (h == 0) {
+    float* bd = r == 0 ? gb_on : (r == 1 ? gb_off : (r == 2 ? gb_mpe : gb_vel + (r - 3)));
+    *bd += gb[r];
+  }
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad), m_training.py:146:  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+// p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).   g is multiplied by grad_scale first (1 / world size after the all-reduce).
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                            float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+}
+
+}  // namespace
+}  // namespace hft

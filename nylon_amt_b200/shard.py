@@ -38,3 +38,34 @@ def features_sharded(amt, wav_paths):
     rank, _, ws = world()
     lo, hi = partition(len(wav_paths), ws, rank)
     return {p: amt.wav2feature(p) for p in wav_paths[lo:hi]}
+
+
+# ---- data-parallel training (BASELINE config 5): the one exchange step of the whole path -------------------------------
+def block_range(n_items, rank, world_size):
+    """Alias of partition() with the (rank, world) argument order the training code reads naturally."""
+    return partition(n_items, world_size, rank)
+
+
+def flatten_bucket(tensors):
+    """Concatenate gradient tensors into ONE flat fp32 bucket (the CUDA trainer's gradients already are one)."""
+    import torch
+    return torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+
+
+def unflatten_bucket(flat, like):
+    """Views of `flat` shaped like the tensors of `like`."""
+    out, off = [], 0
+    for t in like:
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += t.numel()
+    return out
+
+
+def allreduce_bucket(flat, group=None):
+    """Sum the flat gradient bucket over the ranks in place (NCCL over NVLink on GPUs, gloo in the CPU tests); returns the
+    world size to divide by.  A single process is a no-op."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+    return 1
