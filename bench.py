@@ -98,6 +98,135 @@ def cpu_reference_arm(n_segments, threads=None):
             "logmel_s": t_mel, "forward_s": t_fwd}
 
 
+def _timed(fn, steps, dev, dist, stream):
+    import torch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_logmel(args, hft, _lib, L, dev, dist, rank, world):
+    """BASELINE configs[2]: fused log-mel sweep over 5-minute clips (4.8 M samples, 18 751 frames each), clips sharded by rank,
+    one ragged-batch launch per step; roofline = algorithmic bytes (1 KB in + 1 KB out per frame) / kernel time / HBM peak."""
+    import numpy as np
+    import torch
+    cfg = hft.default_config()
+    amt = hft.AMT(cfg, None, None)
+    plan = amt._logmel_plan()
+    clip = 4_800_000
+    n_clips = max(1, int(round(args.hours * 12)))
+    T = 1 + clip // 256
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    wav = 0.1 * torch.randn(n_clips * clip, device=dev, generator=gen)
+    out = torch.empty((n_clips * T, 256), device=dev)
+    starts = (ctypes.c_int64 * n_clips)(*[i * clip for i in range(n_clips)])
+    lens = (ctypes.c_int64 * n_clips)(*([clip] * n_clips))
+    stream = torch.cuda.current_stream(dev)
+    launches = [0]
+
+    def step():
+        _lib.check(L.hft_logmel_batch_f32(plan.ptr, ctypes.c_void_p(wav.data_ptr()), starts, lens, n_clips, ctypes.c_void_p(out.data_ptr()),
+                                          ctypes.c_void_p(stream.cuda_stream)), "hft_logmel_batch_f32")
+        launches[0] += L.hft_last_launch_count()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    launches[0] = 0
+    ms = _timed(step, args.steps, dev, dist, stream) / args.steps
+    n_launch = launches[0]
+    clocks = sampler.stop()
+    audio_s = n_clips * clip / 16000.0
+    pk = peaks()
+    gbs = n_clips * T * LOGMEL_BYTES_PER_FRAME / ms / 1e6
+    if rank == 0:
+        print(json.dumps({"metric": "audio-sec/sec log-mel feature extraction", "value": world * audio_s / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "configs[2]: fused log-mel sweep, %d x 5-minute clips (%.2f h) per GPU in one ragged-batch launch" % (n_clips, n_clips / 12.0),
+                                     "l2_policy": "%.1f GB in + %.1f GB out per step exceed the 126 MB L2" % (wav.numel() * 4 / 1e9, out.numel() * 4 / 1e9),
+                                     "sharding": "clips per rank, no collective"},
+                          "gpu_launches": int(n_launch), "clocks": clocks,
+                          "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                       "traffic": None, "peak_source": pk["src"], "algorithmic_bytes_per_frame": LOGMEL_BYTES_PER_FRAME,
+                                       "note": "compute-bound kernel: ~2.6 k warp instructions per frame (fp32 FFT), see DESIGN.md 5"},
+                          "cpu_baseline": None}))
+    return 0
+
+
+def run_train(args, hft, _lib, L, dev, dist, rank, world):
+    """BASELINE configs[4]: reduced hFT (hid 64, ff 128, 2+2 layers, 2 heads), batch 8 segments per GPU, Adam lr 1e-4, dropout 0;
+    forward + loss + backward, ONE flat-bucket NCCL all-reduce (1.12 MB), Adam.  Reports step time and the exposed all-reduce time."""
+    import torch
+    cfg = hft.default_config()
+    B = 8
+    model = hft.build_model(cfg, 64, 128, 2, 2, dropout=0.0, seed=1234, device=dev)
+    opt = hft.training.Adam(model, lr=1e-4, batch_size=B)
+    gen = torch.Generator(device=dev).manual_seed(2000 + rank)
+    spec = -9.0 + 3.0 * torch.randn((B, 256, 192), device=dev, generator=gen)
+    u = torch.rand((3, B, 128, 88), device=dev, generator=gen)
+    lab = [(u[i] > 0.9).float() for i in range(3)]
+    lab.append(torch.where(u[2] > 0.9, torch.randint(0, 128, (B, 128, 88), device=dev, generator=gen), torch.zeros((B, 128, 88), dtype=torch.int64, device=dev)))
+    stream = torch.cuda.current_stream(dev)
+    launches = [0]
+    t_ar = [0.0]
+
+    def step(measure_ar=False):
+        opt.forward_backward(spec, *lab)
+        launches[0] += L.hft_last_launch_count()
+        if measure_ar:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            w = opt.all_reduce()
+            a1.record(stream)
+            a1.synchronize()
+            t_ar[0] += a0.elapsed_time(a1)
+        else:
+            w = opt.all_reduce()
+        opt.step(w)
+        launches[0] += L.hft_last_launch_count()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    launches[0] = 0
+    ms = _timed(step, args.steps, dev, dist, stream) / args.steps
+    n_launch = launches[0]
+    clocks = sampler.stop()
+    for _ in range(3):
+        step(measure_ar=True)
+    loss = float(opt.loss.item())
+    seg_s = world * B / (ms / 1e3)
+    gflop = 3 * 16.57 * B                      # forward 16.57 GFLOP / segment (SURVEY.md 8), backward ~2x
+    if rank == 0:
+        print(json.dumps({"metric": "training segments/sec (reduced hFT fwd+loss+bwd+Adam)", "value": seg_s, "unit": "segments/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "configs[4]: reduced hFT (hid 64, ff 128, 2+2 layers, 2 heads) training step, batch 8 per GPU, Adam lr 1e-4, dropout 0",
+                                     "parallelism": "dp%d, one flat-bucket all-reduce of %d floats per step" % (world, opt.n)},
+                          "allreduce_ms": t_ar[0] / 3, "loss_after": loss, "gpu_launches": int(n_launch), "clocks": clocks,
+                          "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": 72.0, "unit": "TFLOP/s",
+                                       "frac": gflop / ms / 72.0, "traffic": None, "peak_source": "148 SMs x 128 FMA lanes x 1.9 GHz (nominal fp32)"},
+                          "cpu_baseline": None}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -110,6 +239,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=16, help="segments per forward call")
     ap.add_argument("--cpu-segments", type=int, default=8, help="bounded CPU-baseline sample (segments of 2.048 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "logmel", "train"],
+                    help="transcribe (default, the headline: configs[1]); logmel: configs[2] feature sweep (--hours per GPU as 5-minute clips); "
+                         "train: configs[4] reduced-hFT data-parallel training step (batch 8 per GPU, Adam, flat-bucket all-reduce)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,6 +283,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = hft.default_config()
+    if args.workload != "transcribe":
+        extra = run_logmel(args, hft, _lib, L, dev, dist, rank, world) if args.workload == "logmel" else run_train(args, hft, _lib, L, dev, dist, rank, world)
+        if dist is not None:
+            dist.destroy_process_group()
+        return extra
     amt = hft.AMT(cfg, None, batch_size=args.chunk)
     model = hft.build_model(cfg, 256, 512, 3, 4, seed=1234, device=dev)
     model.precision = args.precision
@@ -261,8 +398,18 @@ def main():
     dom = max(prof, key=lambda n: prof[n]["ms"])
     fwd_ms = total_prof - prof["logmel"]["ms"]
     achieved_tf = n_seg * GFLOP_PER_SEGMENT / max(fwd_ms, 1e-9)                 # GFLOP / ms = TFLOP/s
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")          # ncu-measured DRAM bytes per segment of the forward (dram__bytes_read + write, all kernels)
+    if os.path.isfile(tp):
+        tj = json.load(open(tp))
+        if args.precision in tj.get("dram_bytes_per_segment", {}):
+            traffic = tj["dram_bytes_per_segment"][args.precision] * n_seg
+            traffic_src = tj.get("source")
     roofline = {"bound": "tensor", "kernel": "hFT forward (all classes; dominant: %s, %.0f%% of step)" % (dom, 100 * prof[dom]["ms"] / total_prof),
-                "achieved": achieved_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops"], "traffic": None,
+                "achieved": achieved_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops"], "traffic": traffic,
+                "traffic_source": traffic_src,
+                "hbm": {"achieved": (traffic / max(fwd_ms, 1e-9) / 1e6) if traffic else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": (traffic / max(fwd_ms, 1e-9) / 1e6 / pk["hbm_gbs"]) if traffic else None},
                 "peak_source": pk["src"], "algorithmic_gflop_per_segment": GFLOP_PER_SEGMENT,
                 "classes_ms": {n: round(v["ms"], 3) for n, v in prof.items()},
                 "logmel": {"bound": "hbm", "achieved": T * LOGMEL_BYTES_PER_FRAME / max(prof["logmel"]["ms"], 1e-9) / 1e6,
