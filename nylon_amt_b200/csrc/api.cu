@@ -1,6 +1,7 @@
 // Error plumbing, version and device facts of the C ABI (include/hft_sm100.h).
 #include "common.cuh"
 #include "hft_internal.h"
+#include <stdlib.h>
 #include <vector>
 
 namespace hft {
@@ -31,7 +32,17 @@ LaunchScope::LaunchScope(int kc, void* st) : kclass(kc), stream(st), ev0(nullptr
     ev0 = e;
   }
 }
+// HFT_DEBUG_SYNC=1: synchronise after every launch and report the first failing one (ordinal within the call + kernel class)
+static bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 LaunchScope::~LaunchScope() {
+  if (debug_sync()) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fprintf(stderr, "[hft debug] launch #%lld (class %d) failed: %s\n", g_launches, kclass, cudaGetErrorString(e)); fflush(stderr); }
+  }
   if (ev0) {
     cudaEvent_t e;
     cudaEventCreate(&e);

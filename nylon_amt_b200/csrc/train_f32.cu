@@ -157,7 +157,7 @@ static int alloc_tape(Trainer& t) {
   fl += n_tim * layer_floats(Rd, St, m->nframe) + 2 * Rd * H;                             // time layers + u0 / u_out
   fl += n_dec * (Rd * (12 * H + P) + Re * 2 * H + 2 * Se * heads * m->nnote + 64 * 16) + Rd * H;   // decoder layers + t_out
   fl += 2 * Rd * t.NP + 2 * ((size_t)t.NP * H + t.NP) + (size_t)t.NP * H + t.NP + (size_t)H * m->nproc + H + 64 * 16;
-  fl += Re * (H + 3 * H + H + P) + Rd * (H + 3 * H + H) + Rd * t.NP + Re + (size_t)m->nnote * H + 64 * 12;              // gradient work buffers
+  fl += Re * (H + 3 * H + H + P) + Rd * (H + 3 * H + H) + Rd * t.NP + Re * heads + (size_t)m->nnote * H + 64 * 12;              // gradient work buffers
   t.arena_bytes = fl * sizeof(float);
   HFT_CHECK_CUDA(cudaMalloc(&t.arena, t.arena_bytes));
   float* p = t.arena;
@@ -184,7 +184,7 @@ static int alloc_tape(Trainer& t) {
   t.g_head_w = take((long long)t.NP * H); t.g_head_b = take(t.NP);
   t.g_front_w = take(H * m->nproc); t.g_front_b = take(H);
   t.gX = take(Re * H); t.gBIG = take(Re * 3 * H); t.gCTX = take(Re * H); t.gHID = take(Re * P);
-  t.gT = take(Rd * H); t.gDQ = take(Rd * 3 * H); t.gU = take(Rd * H); t.gLOG = take(Rd * t.NP); t.dD = take(Re); t.gQ0 = take((long long)m->nnote * H);
+  t.gT = take(Rd * H); t.gDQ = take(Rd * 3 * H); t.gU = take(Rd * H); t.gLOG = take(Rd * t.NP); t.dD = take(Re * heads); t.gQ0 = take((long long)m->nnote * H);
   HFT_REQUIRE((size_t)(p - t.arena) * sizeof(float) <= t.arena_bytes, HFT_ERR_STATE, "trainer tape overflow (%zu > %zu)", (size_t)(p - t.arena) * sizeof(float), t.arena_bytes);
   return HFT_OK;
 }
