@@ -19,7 +19,7 @@
 
 namespace hft {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;          // 16 warps / SM: the kernel is issue- and latency-bound, not bandwidth-bound
 constexpr int kFramesPerBlock = 16;
 constexpr int kSpan = (kFramesPerBlock - 1) * kHop + kNfft;   // floats staged per block
 
@@ -52,9 +52,8 @@ struct SmemLayout {
   static constexpr int melw = twr + 520 * 8;
   static constexpr int melinfo = melw + kMaxMelW * 4;
   static constexpr int warp0 = melinfo + kNmels * 4;
-  static constexpr int tile_bytes = 32 * kTStride * 8;                       // T / Z
-  static constexpr int p_bytes = 1040 * 4;                                   // P[0..1024]
-  static constexpr int per_warp = tile_bytes + p_bytes;
+  static constexpr int tile_bytes = 32 * kTStride * 8;                       // T / Z; P[0..1024] overlays it once Z is consumed
+  static constexpr int per_warp = tile_bytes;
   static constexpr int bars = warp0 + kWarps * per_warp;
   static constexpr int total = bars + 16;
 };
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const __grid_con
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float2* s_T = reinterpret_cast<float2*>(smem + SmemLayout::warp0 + warp * SmemLayout::per_warp);
-  float* s_P = reinterpret_cast<float*>(smem + SmemLayout::warp0 + warp * SmemLayout::per_warp + SmemLayout::tile_bytes);
+  float* s_P = reinterpret_cast<float*>(s_T);
 
   // constant tables -> shared memory, once per persistent CTA
   for (int i = tid; i < kNfft; i += kWarps * 32) s_win[i] = p.window[i];
@@ -158,7 +157,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const __grid_con
       __syncwarp();
       lm_cols_store(lane, u, s_T);
       __syncwarp();
-      lm_power(lane, s_T, s_twr, s_P);
+      {
+        float plo[16], phi[16], p0, p1024;
+        lm_power_regs(lane, s_T, s_twr, plo, phi, p0, p1024);
+        __syncwarp();                              // every lane has read its Z entries: P may overwrite them
+        lm_power_store(lane, plo, phi, p0, p1024, s_P);
+      }
       __syncwarp();
       lm_mel(lane, s_P, s_melw, s_melinfo, p.log_offset, b.clip.out + (b.t0 + f) * kNmels);
       __syncwarp();

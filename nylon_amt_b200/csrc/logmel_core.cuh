@@ -65,8 +65,9 @@ HFT_HD void lm_cols_store(int lane, const float2 (&u)[32], float2* Z) {
 }
 
 // Step 5: real-input untangle + power.  twr[k] = exp(-2 pi i k / 2048), k = 0..512.
-// P[k] = |X[k]|^2 for k = 0..1024.
-HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {
+// P[k] = |X[k]|^2 for k = 0..1024.  The lane's 32 (+1) powers are computed into registers first (lm_power_regs) and
+// stored afterwards (lm_power_store), so that P may overlay Z in shared memory (a __syncwarp() goes between the two).
+HFT_HD void lm_power_regs(int lane, const float2* Z, const float2* twr, float (&plo)[16], float (&phi)[16], float& p0, float& p1024) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     int k = 1 + lane + 32 * j;                       // 1..512
@@ -76,15 +77,30 @@ HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {
     float orr = bi, oi = -br;                        // O2 = B / i                    (= 2 O[k])
     float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;   // T2 = W^k O2
     float xr = ar + tr, xi = ai + ti, yr = ar - tr, yi = ai - ti;
-    P[k] = 0.25f * (xr * xr + xi * xi);
-    P[1024 - k] = 0.25f * (yr * yr + yi * yi);
+    plo[j] = 0.25f * (xr * xr + xi * xi);
+    phi[j] = 0.25f * (yr * yr + yi * yi);
   }
+  p0 = 0.f; p1024 = 0.f;
   if (lane == 0) {
     float2 z0 = Z[0];
     float s = z0.x + z0.y, d = z0.x - z0.y;
-    P[0] = s * s;
-    P[1024] = d * d;
+    p0 = s * s;
+    p1024 = d * d;
   }
+}
+HFT_HD void lm_power_store(int lane, const float (&plo)[16], const float (&phi)[16], float p0, float p1024, float* P) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    int k = 1 + lane + 32 * j;
+    P[k] = plo[j];
+    P[1024 - k] = phi[j];
+  }
+  if (lane == 0) { P[0] = p0; P[1024] = p1024; }
+}
+HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {      // P and Z must not overlap
+  float plo[16], phi[16], p0, p1024;
+  lm_power_regs(lane, Z, twr, plo, phi, p0, p1024);
+  lm_power_store(lane, plo, phi, p0, p1024, P);
 }
 
 // Step 6+7: banded mel sums and log.  Lane handles mel bins lane + 32 j.
