@@ -67,6 +67,21 @@ int hft_logmel_host_f32(hft_logmel_plan* plan, const float* wav_host, int64_t n_
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Channel mix-down + resampling in front of the log-mel kernel.
+ * Replaces: wave_mono = torch.mean(wave, dim=0); torchaudio.transforms.Resample(sr, 16000)(wave_mono)
+ *           -- reference hftt_code/model/amt.py:56-58 (same call in dataset_creation.py:21-24).
+ * kernel_host is the polyphase table [new_reduced][2*width + orig_reduced] fp32 that torchaudio builds
+ * (torchaudio.functional.functional._get_sinc_resample_kernel: sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99),
+ * with orig_reduced = sr / gcd, new_reduced = 16000 / gcd.  Output length = ceil(new * n_in / orig).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hft_resample_plan hft_resample_plan;
+int hft_resample_create(hft_resample_plan** plan, const float* kernel_host, int32_t orig_reduced, int32_t new_reduced, int32_t width);
+int hft_resample_destroy(hft_resample_plan* plan);
+int64_t hft_resample_num_samples(const hft_resample_plan* plan, int64_t n_in);
+/* wav_dev [channels][n_in] fp32 (channel-major, like torchaudio.load) -> out_dev [n_out] fp32 mono at the new rate. */
+int hft_resample_mono_f32(hft_resample_plan* plan, const float* wav_dev, int32_t channels, int64_t n_in, float* out_dev, int64_t n_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * hFT-Transformer forward.
  * Replaces: Model_SPEC2MIDI.forward(input_spec) -- reference hftt_code/model/model_spec2midi.py:15-35
  *           (Encoder_SPEC2MIDI.forward :60-106, Decoder_SPEC2MIDI.forward :145-216, EncoderLayer :230-245,

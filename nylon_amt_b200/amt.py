@@ -61,6 +61,22 @@ class _LogmelPlan:
             pass
 
 
+class _ResamplePlan:
+    def __init__(self, kernel, orig_reduced, new_reduced, width):
+        self.ptr = ctypes.c_void_p()
+        self.kernel = kernel
+        _lib.check(_lib.lib().hft_resample_create(ctypes.byref(self.ptr), ctypes.c_void_p(kernel.data_ptr()), orig_reduced, new_reduced, width),
+                   "hft_resample_create")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().hft_resample_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class AMT():
     def __init__(self, config, model_path, batch_size=1, verbose_flag=False):
         if verbose_flag is True:
@@ -151,13 +167,48 @@ class AMT():
             r += T
         return outs
 
+    def _resample_plan(self, sr):
+        """Plan of torchaudio.transforms.Resample(sr, 16000) (amt.py:57): the polyphase table comes from the same torchaudio
+        function the reference calls, so the coefficients are bit-identical."""
+        plans = self.__dict__.setdefault("_rs_plans", {})
+        if sr not in plans:
+            import math
+            from torchaudio.functional.functional import _get_sinc_resample_kernel
+            new = int(self.config['feature']['sr'])
+            g = math.gcd(int(sr), new)
+            kernel, width = _get_sinc_resample_kernel(int(sr), new, g)           # [new/g, 1, 2*width + sr/g] fp32
+            k = kernel.reshape(kernel.shape[0], -1).contiguous().float()
+            plans[sr] = _ResamplePlan(k, int(sr) // g, new // g, int(width))
+        return plans[sr]
+
+    def wave2mono16k(self, wave, sr):
+        """amt.py:56-58 on the device: CUDA tensor [C,N] at `sr` Hz -> CUDA tensor [N'] mono at config sr (channel mean + sinc resampling)."""
+        if not wave.is_cuda:
+            raise RuntimeError("wave2mono16k expects a CUDA tensor (no CPU fallback)")
+        w = wave.float().contiguous()
+        if w.dim() == 1:
+            w = w[None]
+        if sr == self.config['feature']['sr']:
+            return torch.mean(w, dim=0)                      # Resample.forward returns its input when the rates agree
+        plan = self._resample_plan(sr)
+        C, n = w.shape
+        n_out = int(_lib.lib().hft_resample_num_samples(plan.ptr, n))
+        out = torch.empty(n_out, device=w.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(w.device).cuda_stream
+        with torch.cuda.device(w.device):
+            _lib.check(_lib.lib().hft_resample_mono_f32(plan.ptr, ctypes.c_void_p(w.data_ptr()), C, n, ctypes.c_void_p(out.data_ptr()), n_out,
+                                                        ctypes.c_void_p(stream)), "hft_resample_mono_f32")
+        return out
+
     def wav2feature(self, f_wav):
         """amt.py:34-63: wav file -> CPU FloatTensor [T, mel_bins] = log(mel + log_offset).T"""
         wave, sr = _read_wav(f_wav)
-        wave_mono = torch.mean(wave, dim=0)
         if sr != self.config['feature']['sr']:
-            raise NotImplementedError("resampling %d -> %d Hz (amt.py:57-58) is not on the B200 hot path yet; "
-                                      "feed %d Hz audio" % (sr, self.config['feature']['sr'], self.config['feature']['sr']))
+            # amt.py:56-58: channel mean + torchaudio Resample, on the device, feeding the log-mel kernel without a host round trip
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the B200 path has no CPU fallback")
+            return self.wave2feature(self.wave2mono16k(wave.cuda(), sr)).cpu()
+        wave_mono = torch.mean(wave, dim=0)
         plan = self._logmel_plan()
         x = wave_mono.contiguous().float()
         n = x.numel()
