@@ -8,6 +8,7 @@
 #include "tc_attn.cuh"
 #include "tc_attn2.cuh"
 #include "tc_gemm.cuh"
+#include "tc_ffn.cuh"
 
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -158,6 +159,7 @@ struct W16 {            // one weight matrix [N, K] (x3: [N, 2K] = hi | lo) in 1
   int N = 0, K = 0, n_tile = 0;
   CUtensorMap map;                  // box 64 x n_tile
   CUtensorMap map2;                 // box 64 x n_tile/2: one CTA's half of the W rows in PAIR (cta_group::2) mode
+  CUtensorMap map64;                // box 64 x 64: fc_1 rows of one CTA for one 128-unit hidden block (fused FFN)
   const float* bias = nullptr;
 };
 
@@ -229,6 +231,8 @@ static int prepare_weights(Model* m, TcState& t, cudaStream_t s) {
     int r = make_map(&w.map, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile, bf);
     if (r != HFT_OK) rc = r;
     r = make_map(&w.map2, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, w.n_tile / 2, bf);
+    if (r != HFT_OK) rc = r;
+    r = make_map(&w.map64, w.ptr, N, (long long)K * cm, (long long)K * cm, kBlockK, 64, bf);
     if (r != HFT_OK) rc = r;
   };
   auto mk_enc = [&](TcLayer& L, const EncLayerW& lw, const FusedAttn& f) {
@@ -533,6 +537,49 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
   return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }
 
+// Fused FFN block (tc_ffn.cuh): x = LN(x + fc_2(relu(fc_1(x)))) in place.  1 (default) wherever it applies (hid 256, pf 512,
+// rows % 256 == 0); HFT_TC_FFN=0 keeps the two-GEMM path.
+static bool ffn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_FFN"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+static bool ffn_fusable(Model* m, long long R) { return ffn_fused_enabled() && m->H == kFfnH && m->P == kFfnP && R % (2 * kBlockM) == 0; }
+
+static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, long long R, const W16& w1, const W16& w2, const LnW& ln) {
+  FfnParams fp{};
+  fp.m_tiles = (int)(R / (2 * kBlockM));
+  fp.x3 = t.x3 ? 1 : 0;
+  fp.lo_off = m->H; fp.w1_lo_off = m->H; fp.w2_lo_off = m->P;
+  fp.b1 = w1.bias; fp.b2 = w2.bias; fp.gamma = m->w[ln.g]; fp.beta = m->w[ln.b];
+  static int sms = num_sms();
+  int units = sms / 2;
+  if (units > fp.m_tiles) units = fp.m_tiles;
+  const size_t smem = ffn_smem_bytes(fp.x3);
+  HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "fused ffn: %zu bytes of shared memory needed", smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * units));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  if (t.bf16) {
+    static bool set = false;
+    if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<true>, mx, w1.map64, w2.map2, sx, fp));
+  } else {
+    static bool set = false;
+    if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<false>, mx, w1.map64, w2.map2, sx, fp));
+  }
+  return HFT_OK;
+}
+
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
 static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, const CUtensorMap& sqkv, const CUtensorMap& mq,
                             const CUtensorMap& mkv, const CUtensorMap& mkv_unit, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
@@ -543,6 +590,7 @@ static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensor
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
   HFT_TRY(attention(m, t, s, LK, mq, mkv, mkv_unit, a, S, 3 * H));
   HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
+  if (ffn_fusable(m, R)) return ffn_fused(m, t, s, mx, sx, R, lw.w1, lw.w2, ln);   // x = LN(x + fc_2(relu(fc_1(x)))), hidden kept in TMEM
   HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P));
   HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
   return HFT_OK;
@@ -598,6 +646,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
+    if (ffn_fusable(m, Rd)) return ffn_fused(m, t, s, t.mT, t.sT, Rd, lw.w1, lw.w2, ln);
     HFT_TRY(linear(t, s, EPI_RELU, t.mT, lw.w1, Rd, t.sHID, 0, m->P));
     HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, Rd, t.sT, 0, H, &t.mT, &ln, m));
     return HFT_OK;

@@ -184,6 +184,17 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with A read from TMEM (each CTA's own 128 rows), e.g. an activation produced by an epilogue in place
+__device__ __forceinline__ void umma_f16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in both CTAs of the pair once all MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   const uint16_t mask = 3;
