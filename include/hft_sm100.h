@@ -176,6 +176,11 @@ int hft_profile_read(int kclass, double* ms, int64_t* launches);
  * :357, :372-375, :236, :242. */
 int hft_tc_linear(int bf16, int epi, const void* a16_dev, const void* w16_dev, const float* bias_dev, int64_t M, int32_t N, int32_t K,
                   void* out16_dev, const void* resid16_dev, const float* gamma_dev, const float* beta_dev, void* stream);
+/* out[M,256] = LayerNorm(x + fc_2(relu(fc_1(x)))) * gamma + beta for hid_dim 256 / pf_dim 512 (w1 [512,256], w2 [256,512], 16-bit),
+ * M % 256 == 0: the fused FFN kernel (CTA pairs, hidden activation kept in tensor memory).  Replaces
+ * PositionwiseFeedforwardLayer.forward + the residual LayerNorm, model_spec2midi.py:369-378, :242. */
+int hft_tc_ffn(int bf16, const void* x16_dev, const void* w1_16_dev, const float* b1_dev, const void* w2_16_dev, const float* b2_dev,
+               const float* gamma_dev, const float* beta_dev, int64_t M, void* out16_dev, void* stream);
 /* Self-attention over n_seq sequences of L tokens (L in {256, 128, 88}) stored as qkv[n_seq*L, 3*heads*dh]
  * (q | k | v): ctx[n_seq*L, heads*dh] = softmax(q k^T / sqrt(dh)) v, optional probs[n_seq, heads, L, L] fp32 (L = 256
  * only).  Replaces MultiHeadAttentionLayer.forward :335-355. */

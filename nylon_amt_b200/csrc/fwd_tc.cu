@@ -537,14 +537,17 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
   return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }
 
-// Fused FFN block (tc_ffn.cuh): x = LN(x + fc_2(relu(fc_1(x)))) in place.  1 (default) wherever it applies (hid 256, pf 512,
-// rows % 256 == 0); HFT_TC_FFN=0 keeps the two-GEMM path.
-static bool ffn_fused_enabled() {
+// Fused FFN block (tc_ffn.cuh): x = LN(x + fc_2(relu(fc_1(x)))) in place, where it applies (hid 256, pf 512, rows % 256 == 0).
+// Measured on B200 (r01, same box back to back): bf16 3 989 -> 4 181 x real-time, fp16x3 2 025 -> 2 138 x.  In split mode the
+// resident x tile (128 KB hi|lo) leaves room for only 4 W ring slots, so the kernel is bound by the latency of the W stream
+// (profiles/r01_prof_ffn_x3_*), not by HBM: it moves 3.5 x fewer bytes than the two GEMMs it replaces.  HFT_TC_FFN=0 disables it.
+static bool ffn_fused_enabled(bool x3) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HFT_TC_FFN"); v = (e && e[0] == '0') ? 0 : 1; }
+  (void)x3;
   return v == 1;
 }
-static bool ffn_fusable(Model* m, long long R) { return ffn_fused_enabled() && m->H == kFfnH && m->P == kFfnP && R % (2 * kBlockM) == 0; }
+static bool ffn_fusable(Model* m, const TcState& t, long long R) { return ffn_fused_enabled(t.x3) && m->H == kFfnH && m->P == kFfnP && R % (2 * kBlockM) == 0; }
 
 static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, long long R, const W16& w1, const W16& w2, const LnW& ln) {
   FfnParams fp{};
@@ -590,7 +593,7 @@ static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensor
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
   HFT_TRY(attention(m, t, s, LK, mq, mkv, mkv_unit, a, S, 3 * H));
   HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
-  if (ffn_fusable(m, R)) return ffn_fused(m, t, s, mx, sx, R, lw.w1, lw.w2, ln);   // x = LN(x + fc_2(relu(fc_1(x)))), hidden kept in TMEM
+  if (ffn_fusable(m, t, R)) return ffn_fused(m, t, s, mx, sx, R, lw.w1, lw.w2, ln);   // x = LN(x + fc_2(relu(fc_1(x)))), hidden kept in TMEM
   HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P));
   HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
   return HFT_OK;
@@ -646,7 +649,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
-    if (ffn_fusable(m, Rd)) return ffn_fused(m, t, s, t.mT, t.sT, Rd, lw.w1, lw.w2, ln);
+    if (ffn_fusable(m, t, Rd)) return ffn_fused(m, t, s, t.mT, t.sT, Rd, lw.w1, lw.w2, ln);
     HFT_TRY(linear(t, s, EPI_RELU, t.mT, lw.w1, Rd, t.sHID, 0, m->P));
     HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, Rd, t.sT, 0, H, &t.mT, &ln, m));
     return HFT_OK;
@@ -729,6 +732,43 @@ extern "C" int hft_tc_linear(int bf16, int epi, const void* a16, const void* w16
   g.gamma = gamma; g.beta = beta;
   reset_launch_count();
   return launch_gemm(bf16 != 0, epi, ma, w, M, g, &mo, epi == 2 ? &mr : nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int hft_tc_ffn(int bf16, const void* x16, const void* w1_16, const float* b1, const void* w2_16, const float* b2, const float* gamma, const float* beta,
+                          int64_t M, void* out16, void* stream) {
+  HFT_REQUIRE(x16 && w1_16 && b1 && w2_16 && b2 && gamma && beta && out16, HFT_ERR_ARG, "hft_tc_ffn: NULL buffer");
+  HFT_REQUIRE(M > 0 && M % (2 * kBlockM) == 0, HFT_ERR_UNSUPPORTED, "hft_tc_ffn: M=%lld must be a multiple of 256", (long long)M);
+  CUtensorMap mx, mw1, mw2, mo;
+  HFT_TRY(make_map(&mx, x16, M, kFfnH, kFfnH, kBlockK, kBlockM, bf16 != 0));
+  HFT_TRY(make_map(&mw1, w1_16, kFfnP, kFfnH, kFfnH, kBlockK, 64, bf16 != 0));
+  HFT_TRY(make_map(&mw2, w2_16, kFfnH, kFfnP, kFfnP, kBlockK, 128, bf16 != 0));
+  HFT_TRY(make_map(&mo, out16, M, kFfnH, kFfnH, 64, 32, bf16 != 0));
+  FfnParams fp{};
+  fp.m_tiles = (int)(M / (2 * kBlockM));
+  fp.x3 = 0; fp.lo_off = kFfnH; fp.w1_lo_off = kFfnH; fp.w2_lo_off = kFfnP;
+  fp.b1 = b1; fp.b2 = b2; fp.gamma = gamma; fp.beta = beta;
+  int units = num_sms() / 2;
+  if (units > fp.m_tiles) units = fp.m_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * units));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = ffn_smem_bytes(0);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  reset_launch_count();
+  LaunchScope ls(HFT_KCLASS_GEMM, stream);
+  if (bf16) {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<true>, mx, mw1, mw2, mo, fp));
+  } else {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<false>, mx, mw1, mw2, mo, fp));
+  }
+  return HFT_OK;
 }
 
 extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16, int64_t n_seq, int32_t L, void* ctx16, float* probs,

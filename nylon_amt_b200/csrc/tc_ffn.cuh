@@ -32,11 +32,11 @@ struct FfnParams {
 };
 
 constexpr int kFfnH = 256, kFfnP = 512, kFfnJB = 128, kFfnNJ = kFfnP / kFfnJB, kFfnKC = kFfnH / 64;
-constexpr int kFfnSlots = 4;
 constexpr int kFfnSlot = 16384;
+__host__ __device__ constexpr int ffn_slots(int x3) { return x3 ? 4 : 8; }   // split mode: the 128 KB x tile leaves room for 4
 
 __host__ __device__ constexpr size_t ffn_smem_bytes(int x3) {
-  return 1024 + (size_t)kFfnKC * (x3 ? 2 : 1) * kChunkA /*x tile*/ + (size_t)kFfnSlots * kFfnSlot /*W ring*/ + 4096 /*I64 half*/ +
+  return 1024 + (size_t)kFfnKC * (x3 ? 2 : 1) * kChunkA /*x tile*/ + (size_t)ffn_slots(x3) * kFfnSlot /*W ring*/ + 4096 /*I64 half*/ +
          4 * kWarpStage /*store staging*/ + (kFfnP + 3 * kFfnH) * 4 /*b1 b2 gamma beta*/ + 512;
 }
 
@@ -47,6 +47,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int parts = p.x3 ? 2 : 1;
+  const int kFfnSlots = ffn_slots(p.x3);
   uint8_t* s_x = smem;                                                   // [parts][KC] chunks of 128 x 64
   uint8_t* s_ring = s_x + (size_t)parts * kFfnKC * kChunkA;              // [slots] x 16 KB
   uint8_t* s_i64 = s_ring + (size_t)kFfnSlots * kFfnSlot;                // 32 x 64 half identity
@@ -56,15 +57,15 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
   float* s_g = s_b2 + kFfnH;
   float* s_be = s_g + kFfnH;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_be + kFfnH);
-  uint64_t* rfull = bars;                // [4]
-  uint64_t* rempty = bars + 4;           // [4]
-  uint64_t* x_full = bars + 8;
-  uint64_t* x_empty = bars + 9;
-  uint64_t* s_ready = bars + 10;         // [2]
-  uint64_t* p_ready = bars + 12;         // [2]  (leader: 8 arrivals = 4 warps x 2 CTAs)
-  uint64_t* y_ready = bars + 14;
-  uint64_t* y_free = bars + 15;          // (leader: 8 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* rfull = bars;                // [8]
+  uint64_t* rempty = bars + 8;           // [8]
+  uint64_t* x_full = bars + 16;
+  uint64_t* x_empty = bars + 17;
+  uint64_t* s_ready = bars + 18;         // [2]
+  uint64_t* p_ready = bars + 20;         // [2]  (leader: 8 arrivals = 4 warps x 2 CTAs)
+  uint64_t* y_ready = bars + 22;
+  uint64_t* y_free = bars + 23;          // (leader: 8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -200,15 +201,17 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
       for (int mt = unit; mt < p.m_tiles; mt += units, ++it) {
         mbar_wait(x_full, xph); xph ^= 1;
         fence_after_sync();
-        mbar_wait(y_free, yph ^ 1);                                       // the previous tile's LayerNorm epilogue has drained Y
-        yph ^= 1;
-        fence_after_sync();
-        // Y = x (residual) through the identity: column block cb of Y <- x chunk cb (hi, then lo)
-        for (int cb = 0; cb < kFfnKC; ++cb) {
-          uint32_t acc = 0;
-          for (int part = 0; part < parts; ++part)
-            ss4(tmem_base + kYCol + cb * 64, smem_u32(s_x + (size_t)(part * kFfnKC + cb) * kChunkA), i64_addr, id64, acc);
-        }
+        auto residual = [&]() {
+          mbar_wait(y_free, yph ^ 1);                                     // the previous tile's LayerNorm epilogue has drained Y
+          yph ^= 1;
+          fence_after_sync();
+          // Y = x (residual) through the identity: column block cb of Y <- x chunk cb (hi, then lo)
+          for (int cb = 0; cb < kFfnKC; ++cb) {
+            uint32_t acc = 0;
+            for (int part = 0; part < parts; ++part)
+              ss4(tmem_base + kYCol + cb * 64, smem_u32(s_x + (size_t)(part * kFfnKC + cb) * kChunkA), i64_addr, id64, acc);
+          }
+        };
         for (int j = 0; j < kFfnNJ; ++j) {
           const uint32_t d = tmem_base + kSCol + (j & 1) * 128;
           uint32_t acc = 0;
@@ -230,6 +233,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
           }
           umma_commit_2cta(&s_ready[j & 1]);
           if (j == kFfnNJ - 1) umma_commit_2cta(x_empty);                 // x is dead once GEMM1 of the last block has completed
+          if (j == 1) residual();                                         // after two GEMM1 blocks: the previous tile's epilogue overlaps them
           if (j >= 1) gemm2(j - 1);
         }
         gemm2(kFfnNJ - 1);

@@ -63,6 +63,29 @@ def test_linear_residual_layernorm(kind, M, N, K):
 
 
 @pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("M", [256, 512, 256 * 75, 256 * 149])
+def test_fused_ffn(kind, M):
+    """hft_tc_ffn: LayerNorm(x + fc_2(relu(fc_1(x)))) on CTA pairs with the hidden activation kept in TMEM."""
+    H, P = 256, 512
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = (torch.randn((M, H), device="cuda", generator=g)).to(DT[kind])
+    w1 = (torch.randn((P, H), device="cuda", generator=g) / 16).to(DT[kind])
+    w2 = (torch.randn((H, P), device="cuda", generator=g) / 22).to(DT[kind])
+    b1 = 0.1 * torch.randn(P, device="cuda", generator=g)
+    b2 = 0.1 * torch.randn(H, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    out = torch.zeros((M, H), device="cuda", dtype=DT[kind])
+    rc = _lib.lib().hft_tc_ffn(1 if kind == "bf16" else 0, _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(beta), M, _ptr(out), None)
+    _lib.check(rc, "hft_tc_ffn")
+    torch.cuda.synchronize()
+    hid = torch.relu(x.float() @ w1.float().t() + b1).to(DT[kind]).float()          # the kernel rounds the hidden activation to 16 bits
+    ref = torch.nn.functional.layer_norm(x.float() + hid @ w2.float().t() + b2, (H,), gamma, beta, 1e-5)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 * EPS[kind] * ref.abs().max().item() + 1e-3, (kind, M, err)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
 @pytest.mark.parametrize("dh,heads,L,n_seq,probs", [(64, 4, 256, 3, True), (64, 4, 256, 2, False), (64, 4, 128, 5, False), (64, 4, 88, 7, False),
                                                     (64, 4, 256, 80, False), (64, 4, 128, 100, False), (64, 1, 88, 301, False), (64, 2, 256, 1, False),
                                                     (32, 2, 256, 3, True), (32, 2, 128, 3, False), (32, 2, 88, 5, False)])
