@@ -464,9 +464,9 @@ static int launch_attn(int heads, int dh, bool bf16, bool x3, int LK, const CUte
 }
 
 // ---- pipelined attention (tc_attn2.cuh): dh = 64, no probabilities -------------------------------------------------------
-template <bool BF16, int NKEY, int NH, bool X3>
+template <bool BF16, int NKEY, int NH, bool X3, bool PROBS = false>
 static int launch_attn2_t(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const Attn2Params& ap, cudaStream_t s) {
-  auto kern = attn2_kernel<BF16, 64, NKEY, NH, X3>;
+  auto kern = attn2_kernel<BF16, 64, NKEY, NH, X3, PROBS>;
   static bool attr_set = false;
   if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem<64, X3>::total)); attr_set = true; }
   static int sms = num_sms();
@@ -477,6 +477,7 @@ static int launch_attn2_t(const CUtensorMap& mq, const CUtensorMap& mkv, const C
 
 template <bool BF16, bool X3>
 static int launch_attn2_k(int LK, const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const Attn2Params& ap, cudaStream_t s) {
+  if (LK == 256 && ap.probs) return launch_attn2_t<BF16, 128, 2, X3, true>(mq, mkv, mo, ap, s);
   if (LK == 256) return launch_attn2_t<BF16, 128, 2, X3>(mq, mkv, mo, ap, s);
   if (LK == 128) return launch_attn2_t<BF16, 128, 1, X3>(mq, mkv, mo, ap, s);
   if (LK == 96) return launch_attn2_t<BF16, 96, 1, X3>(mq, mkv, mo, ap, s);
@@ -498,6 +499,8 @@ static int launch_attn2(int heads, bool bf16, bool x3, int LK, const CUtensorMap
   ap.n_items = (int)items;
   ap.n_rounds = (int)((items + 1) / 2);
   ap.shared_kv = ap.q_tiles == 2 ? 1 : 0;
+  ap.probs = a.probs;
+  HFT_REQUIRE(!ap.probs || LK == 256, HFT_ERR_UNSUPPORTED, "tc attention: probabilities are returned for 256-key sequences only");
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   if (x3) {
     HFT_REQUIRE(!bf16, HFT_ERR_UNSUPPORTED, "x3 attention is built for fp16 parts");
@@ -510,6 +513,15 @@ static int launch_attn2(int heads, bool bf16, bool x3, int LK, const CUtensorMap
 static bool attn2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HFT_TC_ATTN2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+// The probabilities-returning cross-attention: the pipelined kernel has a PROBS variant (un-normalised rows written during the
+// softmax pass, rescaled in place by the same thread), but its row-per-lane global accesses make it slower than the
+// one-tile-per-CTA kernel (measured r01: attention 433 -> 447 ms per hour), so it is opt-in: HFT_TC_ATTN2_PROBS=1.
+static bool attn2_probs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_ATTN2_PROBS"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 
@@ -533,7 +545,7 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
   a.q_lo_off = q_width;            // hi-block width of the Q tensor (3H for fused QKV buffers, H for the pitch-query table)
   a.kv_lo_off = 3 * m->H;
   a.ctx = t.CTX; a.ld_ctx = m->H * t.cm(); a.ctx_lo_off = m->H;
-  if (m->dh == 64 && a.probs == nullptr && attn2_enabled()) return launch_attn2(m->heads, t.bf16, t.x3, LK, mq, mkv_unit, t.sCTX, a, n_seq, s);
+  if (m->dh == 64 && attn2_enabled() && (a.probs == nullptr || attn2_probs_enabled())) return launch_attn2(m->heads, t.bf16, t.x3, LK, mq, mkv_unit, t.sCTX, a, n_seq, s);
   return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }
 
@@ -786,7 +798,7 @@ extern "C" int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void*
   const bool use_tma = dh == 64 && L % 128 == 0;
   if (use_tma) HFT_TRY(make_map(&mo, ctx16, n_seq * L, H, H, 64, 128, bf16 != 0));
   reset_launch_count();
-  if (dh == 64 && !probs && attn2_enabled()) {          // pipelined kernel (tc_attn2.cuh)
+  if (dh == 64 && attn2_enabled() && (!probs || attn2_probs_enabled())) {   // pipelined kernel (tc_attn2.cuh)
     CUtensorMap mku, so;
     HFT_TRY(make_map(&mku, qkv16, n_seq * L, 3 * H, 3 * H, dh, LK == 96 ? 96 : 128, bf16 != 0));
     HFT_TRY(make_map(&so, ctx16, n_seq * L, H, H, 64, 32, bf16 != 0));

@@ -16,7 +16,9 @@
 // L2 -> shared-memory traffic; otherwise they work on different (sequence, head) items.
 // x3 mode (split operands): S = Qh Kh + Ql Kh + Qh Kl;  P = Ph + Pl (both in TMEM, [hi 16 cols | lo 16 cols] per 32 keys);
 // O = Ph Vh + Pl Vh + Ph Vl;  ctx stored hi | lo.
-// The probabilities-returning variant (last decoder layer) stays on tc_attn.cuh.
+// PROBS variant (last decoder cross-attention, model_spec2midi.py:360): every unit's un-normalised exp2 values are written to the
+// fp32 probability tensor during its softmax pass; once both units' maxima and sums are known the same thread rescales its own row
+// in place (the row is still in L2), so no extra TMEM state is needed.
 #pragma once
 #include "tc_attn.cuh"
 
@@ -38,6 +40,7 @@ struct Attn2Params {
   int n_items;            // n_seq * heads * q_tiles
   int n_rounds;           // ceil(n_items / 2)
   int shared_kv;          // 1: q_tiles == 2, both warpgroups use the same K / V half-tiles
+  float* probs;           // PROBS: fp32 [n_seq, heads, lq, lk]
 };
 
 template <int DH, bool X3>
@@ -54,7 +57,7 @@ struct Attn2Smem {
 constexpr int kAttn2Threads = 64 + 256;
 
 // NKEY: keys per unit (128, or 96 for the 88-key decoder self-attention); NH: units per tile (Lk = NH * NKEY)
-template <bool BF16, int DH, int NKEY, int NH, bool X3>
+template <bool BF16, int DH, int NKEY, int NH, bool X3, bool PROBS = false>
 __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                                                                 const __grid_constant__ CUtensorMap map_o, const __grid_constant__ Attn2Params p) {
   using L = Attn2Smem<DH, X3>;
@@ -249,6 +252,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
       if (tile >= p.n_items) continue;
       int seq, head, qt;
       decode(tile, seq, head, qt);
+      const int qrow_p = qt * 128 + r;
+      float* prow = PROBS ? p.probs + (((long long)seq * p.heads + head) * p.lq + (qrow_p < p.lq ? qrow_p : 0)) * p.lk : nullptr;
       float mx[NH], sum[NH];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
@@ -288,6 +293,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
               if (c * 32 + 2 * j + 1 >= kvalid) e1 = 0.f;
             }
             s += e0 + e1;
+            if (PROBS) { v[2 * j] = __float_as_uint(e0); v[2 * j + 1] = __float_as_uint(e1); }
             if (X3) split_pack<BF16>(e0, e1, pw[j], pw[16 + j]);
             else pw[j] = Op16<BF16>::pack(e0, e1);
           }
@@ -298,6 +304,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 16; ++j) ph16[j] = pw[j];
             tmem_st16(t_row + c * 16, ph16);
+          }
+          if (PROBS && qrow_p < p.lq) {                     // un-normalised for now; rescaled below once max / sum of the whole row are known
+            float4* dst = reinterpret_cast<float4*>(prow + h * NKEY + c * 32);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4)
+              dst[q4] = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]));
           }
         }
         mx[h] = ms;
@@ -316,6 +328,18 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
       }
       const float inv = 1.f / (NH == 2 ? sum[0] * f0 + sum[NH - 1] * f1 : sum[0]);
       f0 *= inv; f1 *= inv;
+      if (PROBS && qrow_p < p.lq) {                         // softmax probabilities: this thread's own row, written above
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float f = h == 0 ? f0 : f1;
+          float4* row4 = reinterpret_cast<float4*>(prow + h * NKEY);
+#pragma unroll 4
+          for (int q4 = 0; q4 < NKEY / 4; ++q4) {
+            float4 t = row4[q4];
+            row4[q4] = make_float4(t.x * f, t.y * f, t.z * f, t.w * f);
+          }
+        }
+      }
       mbar_wait(&o_ready[w], oph); oph ^= 1;
       fence_after_sync();
       const int qrow = qt * 128 + r;
