@@ -123,3 +123,35 @@ def test_c_abi_argument_errors(amt):
     out = torch.zeros((10, 256), device="cuda")
     rc = _lib.lib().hft_logmel_f32(plan.ptr, ctypes.c_void_p(x.data_ptr()), 1000, ctypes.c_void_p(out.data_ptr()), 10, None)
     assert rc == 10001 and b"n_frames" in _lib.lib().hft_last_error()
+
+
+def test_conv_wav2fe_driver(amt, golden_dir, tmp_path):
+    """The reference's corpus driver (conv_wav2fe.py:13-50) with the same command line: lists -> pickled CPU feature tensors."""
+    import json
+    import pickle
+    import wave as _wave
+    from nylon_amt_b200 import conv_wav2fe
+    g = np.load(os.path.join(golden_dir, "logmel.npz"))
+    names = [k[4:] for k in g.files if k.startswith("pcm_")][:3]
+    d_list, d_wav, d_out = tmp_path / "list", tmp_path / "wav", tmp_path / "feature"
+    for d in (d_list, d_wav, d_out):
+        d.mkdir()
+    for n in names:
+        pcm = g["pcm_" + n]
+        with _wave.open(str(d_wav / (n + ".wav")), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+            f.writeframes(np.ascontiguousarray(pcm).astype("<i2").tobytes())
+    (d_list / "train.list").write_text("\n".join(names[:2]) + "\n")
+    (d_list / "test.list").write_text(names[2] + "\n")
+    (d_list / "valid.list").write_text("")
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(hft.default_config()))
+    n = conv_wav2fe.main(["-d_list", str(d_list), "-d_wav", str(d_wav), "-d_feature", str(d_out), "-config", str(cfg)])
+    assert n == 3
+    for name in names:
+        with open(d_out / (name + ".pkl"), "rb") as f:
+            feat = pickle.load(f)
+        ref = g["feat_" + name]
+        assert isinstance(feat, torch.Tensor) and not feat.is_cuda and tuple(feat.shape) == ref.shape
+        ok, worst = lo.close_logmel(feat.numpy(), ref, 1e-4, fft_noise=256.0)
+        assert ok, (name, worst)
