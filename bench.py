@@ -175,8 +175,8 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world):
     import torch
     cfg = hft.default_config()
     B = 8
-    model = hft.build_model(cfg, 64, 128, 2, 2, dropout=0.0, seed=1234, device=dev)
-    opt = hft.training.Adam(model, lr=1e-4, batch_size=B)
+    model = hft.build_model(cfg, 64, 128, 2, 2, dropout=args.dropout, seed=1234, device=dev)
+    opt = hft.training.Adam(model, lr=1e-4, batch_size=B, seed=rank)
     gen = torch.Generator(device=dev).manual_seed(2000 + rank)
     spec = -9.0 + 3.0 * torch.randn((B, 256, 192), device=dev, generator=gen)
     u = torch.rand((3, B, 128, 88), device=dev, generator=gen)
@@ -212,15 +212,24 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world):
     for _ in range(3):
         step(measure_ar=True)
     loss = float(opt.loss.item())
+    L.hft_profile_enable(1)                     # per-class device time of one extra step (events around every launch)
+    step()
+    torch.cuda.synchronize(dev)
+    L.hft_profile_enable(0)
+    classes = {}
+    for k, n in enumerate(["logmel", "front", "gemm", "attention", "norm", "heads"]):
+        t, c = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(L.hft_profile_read(k, ctypes.byref(t), ctypes.byref(c)), "hft_profile_read")
+        classes[n] = {"ms": round(t.value, 3), "launches": c.value}
     seg_s = world * B / (ms / 1e3)
     gflop = 3 * 16.57 * B                      # forward 16.57 GFLOP / segment, backward ~2x
     if rank == 0:
         print(json.dumps({"metric": "training segments/sec (reduced hFT fwd+loss+bwd+Adam)", "value": seg_s, "unit": "segments/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "configs[4]: reduced hFT (hid 64, ff 128, 2+2 layers, 2 heads) training step, batch 8 per GPU, Adam lr 1e-4, dropout 0",
+                          "config": {"workload": "configs[4]: reduced hFT (hid 64, ff 128, 2+2 layers, 2 heads) training step, batch 8 per GPU, Adam lr 1e-4, dropout %g" % args.dropout,
                                      "parallelism": "dp%d, one flat-bucket all-reduce of %d floats per step" % (world, opt.n)},
-                          "allreduce_ms": t_ar[0] / 3, "loss_after": loss, "gpu_launches": int(n_launch), "clocks": clocks,
+                          "allreduce_ms": t_ar[0] / 3, "loss_after": loss, "classes": classes, "gpu_launches": int(n_launch), "clocks": clocks,
                           "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": 72.0, "unit": "TFLOP/s",
                                        "frac": gflop / ms / 72.0, "traffic": None, "peak_source": "148 SMs x 128 FMA lanes x 1.9 GHz (nominal fp32)"},
                           "cpu_baseline": None}))
@@ -242,6 +251,7 @@ def main():
     ap.add_argument("--workload", default="transcribe", choices=["transcribe", "logmel", "train"],
                     help="transcribe (default, the headline: configs[1]); logmel: configs[2] feature sweep (--hours per GPU as 5-minute clips); "
                          "train: configs[4] reduced-hFT data-parallel training step (batch 8 per GPU, Adam, flat-bucket all-reduce)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="train workload: dropout probability (reference trains with 0.1; 0 = the parity configuration)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

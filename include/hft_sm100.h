@@ -192,7 +192,7 @@ int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16_dev,
  * Replaces: the body of train() -- reference hftt_code/training/train.py:89-160 (model(input) in train mode, BCELoss on
  *           the six sigmoid outputs + CrossEntropyLoss on the two velocity logit tensors, loss = weight_A * loss_A +
  *           weight_B * loss_B, loss.backward(), optimizer.step()) with torch.optim.Adam(lr) of
- *           hftt_code/training/m_training.py:146.  fp32 CUDA-core kernels; dropout p = 0 only (the parity configuration).
+ *           hftt_code/training/m_training.py:146.  fp32 CUDA-core kernels; dropout through hft_trainer_set_dropout.
  * Parameters and gradients are ONE flat fp32 vector each: the tensors of the state_dict in schema order, every tensor
  * padded to a multiple of 4 floats (hft_model_param_offset).  The flat gradient is the single bucket the data-parallel
  * configuration all-reduces over NCCL between hft_train_forward_backward and hft_adam_step.
@@ -222,6 +222,21 @@ int hft_trainer_destroy(hft_trainer* trainer);
 int hft_train_forward_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
                                const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
                                const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream);
+
+/* Dropout of the training forward (nn.Dropout(p) of the reference modules; the reference trains with p = 0.1, m_training.py).
+ * Masks are counter based: element idx of site `site` is kept iff hash(seed, site, idx) >= p * 2^32 and scaled by 1 / (1 - p);
+ * the backward regenerates them.  Call before every step with a fresh seed; p = 0 (default) disables every mask.
+ * Site numbering (Le encoder layers, Ld decoder layers incl. layer zero):
+ *   0                      encoder embedding dropout (model_spec2midi.py:95), idx = row * hid + col of [B*F*n_bin, hid]
+ *   1 + 4 l + {0,1,2,3}    encoder layer l: attention probabilities (idx = ((seq * heads + head) * Lq + i) * Lk + j), attention sub-layer
+ *                          output [rows, hid], FFN hidden [rows, pf], FFN sub-layer output [rows, hid]
+ *   D0 = 1 + 4 Le, + {0,1,2,3}           decoder layer zero: cross probabilities, cross output, FFN hidden, FFN output
+ *   D0 + 4 + 6 (l - 1) + {0..5}, l >= 1  decoder layer l: self probabilities, self output, cross probabilities, cross output, FFN hidden, FFN output
+ *   T0 = D0 + 4 + 6 (Ld - 1)             time embedding dropout (:191), rows in (b, note, frame) order
+ *   T0 + 1 + 4 l + {0,1,2,3}             time layer l (same four sites as an encoder layer) */
+int hft_trainer_set_dropout(hft_trainer* trainer, float p, uint32_t seed);
+/* mask_out_dev[i] = kept ? 1 / (1 - p) : 0 for i < n of one site: the multiplier the kernels apply (test / restatement aid). */
+int hft_dropout_mask(float p, uint32_t seed, int32_t site, int64_t n, float* mask_out_dev, void* stream);
 
 /* torch.optim.Adam (no weight decay, no amsgrad) on flat vectors: grads are multiplied by grad_scale first (1 / world size
  * after a sum all-reduce); step counts from 1. */

@@ -60,6 +60,8 @@ SYMBOLS = {
     "hft_model_get_params": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "hft_trainer_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int32]),
     "hft_trainer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "hft_trainer_set_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32]),
+    "hft_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "hft_train_forward_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]),

@@ -8,6 +8,39 @@
 namespace hft {
 namespace {
 
+// ---- dropout (training step only) ---------------------------------------------------------------------------------------
+// Counter-based: element `idx` of dropout site `site` is kept iff hash(seed, site, idx) >= thresh (thresh = p * 2^32), and kept
+// values are scaled by 1 / (1 - p) (nn.Dropout semantics).  The backward pass regenerates the same decisions, nothing is stored.
+struct Drop {
+  uint32_t thresh;     // 0: no dropout
+  uint32_t seed;
+  uint32_t site;
+  float scale;
+};
+__host__ __device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  uint32_t h = (uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x85EBCA77u ^ d.seed ^ (d.site * 0xC2B2AE3Du);
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  return h >= d.thresh;
+}
+// x[i] = keep ? x[i] * scale : 0   (forward in place; also the backward of an element-wise dropout)
+__global__ void dropout_kernel(float* __restrict__ x, long long n, Drop d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = drop_keep(d, (unsigned long long)i) ? x[i] * d.scale : 0.f;
+}
+// m[i] = keep ? scale : 0   (the multiplier itself; lets a restatement check its own mask arithmetic against the kernels')
+__global__ void dropout_mask_kernel(float* __restrict__ m, long long n, Drop d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  m[i] = drop_keep(d, (unsigned long long)i) ? d.scale : 0.f;
+}
+// y[i] = keep ? x[i] * scale : 0   (out of place: the sub-layer branch of a gradient that also feeds the residual path)
+__global__ void dropout_copy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, Drop d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = drop_keep(d, (unsigned long long)i) ? x[i] * d.scale : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // front: unfold(65) -> conv(1,C,(1,kw)) -> Linear -> *sqrt(H) + pos  (model_spec2midi.py:65-95), collapsed to one
 // 65-tap filter per hidden unit.  grid (n_bin, B); X[((b*F+f)*NB+bin)*H + h].
@@ -127,7 +160,7 @@ template <int DH>
 __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride,
                                                        const float* __restrict__ Kp, const float* __restrict__ Vp, int ldkv, int Lq, int Lk,
                                                        int heads, float inv_scale, float* __restrict__ ctx, int ldc, float* __restrict__ probs,
-                                                       float* __restrict__ lse = nullptr) {
+                                                       float* __restrict__ lse = nullptr, Drop drop = Drop{0, 0, 0, 1.f}) {
   extern __shared__ __align__(16) float smem_attn[];
   float* sK = smem_attn;
   float* sV = smem_attn + (size_t)Lk * DH;
@@ -176,8 +209,10 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__
       float4 t = kr[c];
       s = fmaf(q[c * 4], t.x, s); s = fmaf(q[c * 4 + 1], t.y, s); s = fmaf(q[c * 4 + 2], t.z, s); s = fmaf(q[c * 4 + 3], t.w, s);
     }
-    const float p = expf(s * inv_scale - mx) * inv_sum;
+    float p = expf(s * inv_scale - mx) * inv_sum;
     if (prow) prow[j] = p;
+    if (drop.thresh)                                   // dropout on the probabilities (model_spec2midi.py:348), training only
+      p = drop_keep(drop, (unsigned long long)((((long long)seq * heads + head) * Lq + r) * Lk + j)) ? p * drop.scale : 0.f;
     const float4* vr = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
 #pragma unroll
     for (int c = 0; c < DH / 4; ++c) {
@@ -197,7 +232,8 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ r, long long r_rows,
                                                          const float* __restrict__ g, const float* __restrict__ b, int H, long long rows,
-                                                         float* __restrict__ y, float* __restrict__ sum_out = nullptr) {
+                                                         float* __restrict__ y, float* __restrict__ sum_out = nullptr, Drop drop = Drop{0, 0, 0, 1.f},
+                                                         bool drop_x = false) {
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -209,7 +245,12 @@ __global__ void __launch_bounds__(256) add_ln_f32_kernel(const float* __restrict
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i < per) {
-      v[i] = xp[lane + 32 * i] + rp[lane + 32 * i];
+      float xv = xp[lane + 32 * i], rv = rp[lane + 32 * i];
+      if (drop.thresh) {                               // sub-layer dropout before the residual add (model_spec2midi.py:236), training only
+        const bool keep = drop_keep(drop, (unsigned long long)(row * H + lane + 32 * i));
+        if (drop_x) xv = keep ? xv * drop.scale : 0.f; else rv = keep ? rv * drop.scale : 0.f;
+      }
+      v[i] = xv + rv;
       s += v[i];
       if (sum_out) sum_out[row * H + lane + 32 * i] = v[i];      // pre-LayerNorm sum, kept for the backward pass
     }

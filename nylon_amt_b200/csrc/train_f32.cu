@@ -5,8 +5,9 @@
 // probabilities from Q, K and the log-sum-exp instead of storing [S, heads, Lq, Lk].
 // Gradients land in one flat fp32 vector laid out like the model's parameter arena (state_dict order, every tensor
 // padded to 4 floats) so that the data-parallel configuration all-reduces ONE bucket over NCCL.
-// Dropout: the reference trains with p = 0.1; this step implements p = 0 (the parity configuration of SURVEY.md 8d
-// config 5) and the host mirror refuses any other value.
+// Dropout (the reference trains with p = 0.1): counter-based masks, hash(seed, site, element) -- see Drop in f32_kernels.cuh;
+// the backward regenerates them.  Sites are numbered in forward order (hft_sm100.h documents the numbering) so that a
+// restatement can reproduce the masks; p = 0 (the parity configuration of SURVEY.md 8d config 5) skips every mask.
 #include "common.cuh"
 #include "model.h"
 #include "train_kernels.cuh"
@@ -43,7 +44,21 @@ struct Trainer {
   float *g_front_w = nullptr, *g_front_b = nullptr;
   // gradient work buffers
   float *gX = nullptr, *gBIG = nullptr, *gCTX = nullptr, *gHID = nullptr, *gT = nullptr, *gDQ = nullptr, *gU = nullptr, *gLOG = nullptr, *dD = nullptr, *gQ0 = nullptr;
+  float* gM = nullptr;           // masked copy of a gradient (sub-layer branch under dropout)
   int NP = 144;                  // padded head width (3 + V = 131 -> multiple of 16)
+  float p_drop = 0.f;
+  uint32_t seed = 0;
+  Drop drop(int site) const {
+    Drop d{0u, seed, (uint32_t)site, 1.f};
+    if (p_drop > 0.f) { d.thresh = (uint32_t)((double)p_drop * 4294967296.0); d.scale = 1.f / (1.f - p_drop); }
+    return d;
+  }
+  // site numbering (forward order)
+  int site_enc(int l) const { return 1 + 4 * l; }
+  int site_dec0() const { return 1 + 4 * (int)m->enc.size(); }
+  int site_dec(int l) const { return site_dec0() + 4 + 6 * l; }           // l = 0 is the first DecoderLayer after layer zero
+  int site_time_emb() const { return site_dec0() + 4 + 6 * (int)m->dec.size(); }
+  int site_time(int l) const { return site_time_emb() + 1 + 4 * l; }
 };
 
 // ---- launch helpers -------------------------------------------------------------------------------------------------
@@ -58,11 +73,11 @@ static int gemm_tn(cudaStream_t s, const float* A, int lda, const float* Wt, int
 }
 // C[M,N] (+)= A[M,K] * W[K,N]
 static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int ldb, float* C, int ldc, long long M, int N, int K, bool accum,
-                   const float* mask = nullptr, int ldm = 0) {
+                   const float* mask = nullptr, int ldm = 0, float mask_scale = 1.f) {
   HFT_REQUIRE(K % GBK == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_nn: N=%d K=%d lda=%d ldb=%d", N, K, lda, ldb);
   dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  sgemm_nn_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm);
+  sgemm_nn_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm, mask_scale);
   return HFT_OK;
 }
 // dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)
@@ -78,9 +93,23 @@ static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int
   dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), 256, 0, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
   return HFT_OK;
 }
-static void ln_fwd(Model* m, cudaStream_t s, const float* x, const float* r, long long r_rows, const LnW& ln, long long rows, float* y, float* sum_out) {
+static void ln_fwd(Model* m, cudaStream_t s, const float* x, const float* r, long long r_rows, const LnW& ln, long long rows, float* y, float* sum_out,
+                   Drop drop = Drop{0, 0, 0, 1.f}, bool drop_x = false) {
   LaunchScope ls(HFT_KCLASS_NORM, s);
-  add_ln_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, r, r_rows, m->w[ln.g], m->w[ln.b], m->H, rows, y, sum_out);
+  add_ln_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, r, r_rows, m->w[ln.g], m->w[ln.b], m->H, rows, y, sum_out, drop, drop_x);
+}
+// element-wise dropout in place (forward of an embedding / hidden dropout, or the backward of one)
+static void dropout_inplace(cudaStream_t s, float* x, long long n, const Drop& d) {
+  if (!d.thresh) return;
+  LaunchScope ls(HFT_KCLASS_NORM, s);
+  dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, d);
+}
+// gradient of the sub-layer branch under dropout: g itself when p = 0, else a masked copy in `scratch`
+static const float* branch_grad(cudaStream_t s, const float* g, float* scratch, long long n, const Drop& d) {
+  if (!d.thresh) return g;
+  LaunchScope ls(HFT_KCLASS_NORM, s);
+  dropout_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, scratch, n, d);
+  return scratch;
 }
 static void ln_bwd(Model* m, cudaStream_t s, const float* dy, const float* sum, const LnW& ln, long long rows, float* ds, float* G) {
   LaunchScope ls(HFT_KCLASS_NORM, s);
@@ -94,7 +123,7 @@ static void colsum(cudaStream_t s, const float* in, long long rows, long long co
 }
 
 static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
-                    int Lq, int Lk, float* ctx, float* lse) {
+                    int Lq, int Lk, float* ctx, float* lse, Drop drop = Drop{0, 0, 0, 1.f}) {
   const int dh = m->dh;
   size_t smem = (size_t)2 * Lk * dh * sizeof(float);
   int threads = (Lq + 31) / 32 * 32;
@@ -104,17 +133,18 @@ static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   if (dh == 64) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse);
+    attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse);
+    attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
   }
   return HFT_OK;
 }
 
 template <int DH>
 static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO,
-                      const float* O, const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf) {
+                      const float* O, const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf,
+                      Drop drop) {
   const float c = 1.f / sqrtf((float)DH);
   dim3 grid((unsigned)S, m->heads);
   const size_t smem1 = (size_t)2 * Lk * DH * sizeof(float);
@@ -123,22 +153,22 @@ static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long lo
   HFT_REQUIRE(t1 <= 256 && t2 <= 256 && smem1 <= 200 * 1024 && smem2 <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention backward: Lq=%d Lk=%d", Lq, Lk);
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf);
+  attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
   if (DH <= 32) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
+    attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dkv_kernel<DH, 1><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
-    attn_bwd_dkv_kernel<DH, 2><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv);
+    attn_bwd_dkv_kernel<DH, 1><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
+    attn_bwd_dkv_kernel<DH, 2><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
   }
   return HFT_OK;
 }
 static int attn_bwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO, const float* O,
-                    const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf) {
-  if (m->dh == 64) return attn_bwd_t<64>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf);
-  return attn_bwd_t<32>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf);
+                    const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf, Drop drop) {
+  if (m->dh == 64) return attn_bwd_t<64>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
+  return attn_bwd_t<32>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
 }
 
 // gradient slot of a registered parameter inside the flat gradient vector
@@ -157,7 +187,7 @@ static int alloc_tape(Trainer& t) {
   fl += n_tim * layer_floats(Rd, St, m->nframe) + 2 * Rd * H;                             // time layers + u0 / u_out
   fl += n_dec * (Rd * (12 * H + P) + Re * 2 * H + 2 * Se * heads * m->nnote + 64 * 16) + Rd * H;   // decoder layers + t_out
   fl += 2 * Rd * t.NP + 2 * ((size_t)t.NP * H + t.NP) + (size_t)t.NP * H + t.NP + (size_t)H * m->nproc + H + 64 * 16;
-  fl += Re * (H + 3 * H + H + P) + Rd * (H + 3 * H + H) + Rd * t.NP + Re * heads + (size_t)m->nnote * H + 64 * 12;              // gradient work buffers
+  fl += Re * (2 * H + 3 * H + H + P) + Rd * (H + 3 * H + H) + Rd * t.NP + Re * heads + (size_t)m->nnote * H + 64 * 12;              // gradient work buffers
   t.arena_bytes = fl * sizeof(float);
   HFT_CHECK_CUDA(cudaMalloc(&t.arena, t.arena_bytes));
   float* p = t.arena;
@@ -185,41 +215,47 @@ static int alloc_tape(Trainer& t) {
   t.g_front_w = take(H * m->nproc); t.g_front_b = take(H);
   t.gX = take(Re * H); t.gBIG = take(Re * 3 * H); t.gCTX = take(Re * H); t.gHID = take(Re * P);
   t.gT = take(Rd * H); t.gDQ = take(Rd * 3 * H); t.gU = take(Rd * H); t.gLOG = take(Rd * t.NP); t.dD = take(Re * heads); t.gQ0 = take((long long)m->nnote * H);
+  t.gM = take(Re * H);
   HFT_REQUIRE((size_t)(p - t.arena) * sizeof(float) <= t.arena_bytes, HFT_ERR_STATE, "trainer tape overflow (%zu > %zu)", (size_t)(p - t.arena) * sizeof(float), t.arena_bytes);
   return HFT_OK;
 }
 
 // ---- forward with tape ----------------------------------------------------------------------------------------------
 // EncoderLayer (model_spec2midi.py:230-245): x = L.xin -> out
-static int enc_layer_fwd(Model* m, cudaStream_t s, LayerTape& L, long long S, int Lq, const EncLayerW& lw, const FusedAttn& qkv, float* out, float* tmp) {
+// dropout sites of the layer: base + 0 attention probabilities, + 1 attention sub-layer output, + 2 FFN hidden, + 3 FFN sub-layer output
+static int enc_layer_fwd(Trainer& t, cudaStream_t s, LayerTape& L, long long S, int Lq, const EncLayerW& lw, const FusedAttn& qkv, float* out, float* tmp, int base) {
+  Model* m = t.m;
   const int H = m->H, P = m->P;
   const long long R = S * Lq;
   HFT_TRY(gemm_tn(s, L.xin, H, qkv.qkv_w, H, qkv.qkv_b, L.qkv, 3 * H, R, 3 * H, H, false));
-  HFT_TRY(attn_fwd(m, s, L.qkv, 3 * H, (long long)Lq * 3 * H, L.qkv + H, L.qkv + 2 * H, 3 * H, S, Lq, Lq, L.ctx, L.lse));
+  HFT_TRY(attn_fwd(m, s, L.qkv, 3 * H, (long long)Lq * 3 * H, L.qkv + H, L.qkv + 2 * H, 3 * H, S, Lq, Lq, L.ctx, L.lse, t.drop(base)));
   HFT_TRY(gemm_tn(s, L.ctx, H, m->w[lw.sa.o_w], H, m->w[lw.sa.o_b], tmp, H, R, H, H, false));
-  ln_fwd(m, s, L.xin, tmp, R, lw.ln, R, L.x1, L.s1);
+  ln_fwd(m, s, L.xin, tmp, R, lw.ln, R, L.x1, L.s1, t.drop(base + 1));
   HFT_TRY(gemm_tn(s, L.x1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], L.hid, P, R, P, H, true));
+  dropout_inplace(s, L.hid, R * P, t.drop(base + 2));
   HFT_TRY(gemm_tn(s, L.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, R, H, P, false));
-  ln_fwd(m, s, L.x1, tmp, R, lw.ln, R, out, L.s2);
+  ln_fwd(m, s, L.x1, tmp, R, lw.ln, R, out, L.s2, t.drop(base + 3));
   return HFT_OK;
 }
 
 // EncoderLayer backward: g = dL/d(out) on entry, dL/d(xin) on exit (in place)
 static int enc_layer_bwd(Trainer& t, cudaStream_t s, LayerTape& L, long long S, int Lq, const EncLayerW& lw, const FusedAttn& qkv, float* g, float* gqkv, float* gctx,
-                         float* ghid, float* G) {
+                         float* ghid, float* G, int base) {
   Model* m = t.m;
   const int H = m->H, P = m->P;
   const long long R = S * Lq;
   ln_bwd(m, s, g, L.s2, lw.ln, R, g, G);
-  HFT_TRY(gemm_dw(s, g, H, L.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), R, H, P));
-  HFT_TRY(gemm_nn(s, g, H, m->w[lw.ff.w2], P, ghid, P, R, P, H, false, L.hid, P));          // through fc_2 and the ReLU
+  const float* gb = branch_grad(s, g, t.gM, R * H, t.drop(base + 3));                       // gradient of the FFN branch (sub-layer dropout)
+  HFT_TRY(gemm_dw(s, gb, H, L.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), R, H, P));
+  HFT_TRY(gemm_nn(s, gb, H, m->w[lw.ff.w2], P, ghid, P, R, P, H, false, L.hid, P, t.drop(base + 2).scale));   // through fc_2, the hidden dropout and the ReLU
   HFT_TRY(gemm_dw(s, ghid, P, L.x1, H, gof(m, G, lw.ff.w1), H, gof(m, G, lw.ff.b1), R, P, H));
   HFT_TRY(gemm_nn(s, ghid, P, m->w[lw.ff.w1], H, g, H, R, H, P, true));                     // + residual path already in g
   ln_bwd(m, s, g, L.s1, lw.ln, R, g, G);
-  HFT_TRY(gemm_dw(s, g, H, L.ctx, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), R, H, H));
-  HFT_TRY(gemm_nn(s, g, H, m->w[lw.sa.o_w], H, gctx, H, R, H, H, false));
+  gb = branch_grad(s, g, t.gM, R * H, t.drop(base + 1));                                    // gradient of the attention branch
+  HFT_TRY(gemm_dw(s, gb, H, L.ctx, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), R, H, H));
+  HFT_TRY(gemm_nn(s, gb, H, m->w[lw.sa.o_w], H, gctx, H, R, H, H, false));
   HFT_TRY(attn_bwd(m, s, L.qkv, 3 * H, (long long)Lq * 3 * H, L.qkv + H, L.qkv + 2 * H, 3 * H, gctx, L.ctx, L.lse, S, Lq, Lq, gqkv, 3 * H, gqkv + H, gqkv + 2 * H,
-                   3 * H, t.dD));
+                   3 * H, t.dD, t.drop(base)));
   HFT_TRY(gemm_dw(s, gqkv, 3 * H, L.xin, H, gof(m, G, lw.sa.q_w), H, gof(m, G, lw.sa.q_b), R, H, H));
   HFT_TRY(gemm_dw(s, gqkv + H, 3 * H, L.xin, H, gof(m, G, lw.sa.k_w), H, gof(m, G, lw.sa.k_b), R, H, H));
   HFT_TRY(gemm_dw(s, gqkv + 2 * H, 3 * H, L.xin, H, gof(m, G, lw.sa.v_w), H, gof(m, G, lw.sa.v_b), R, H, H));
@@ -247,36 +283,41 @@ static int train_forward(Trainer& t, const float* spec, long long sb, long long 
     LaunchScope ls(HFT_KCLASS_FRONT, s);
     front_f32_kernel<65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.enc[0].xin);
   }
+  dropout_inplace(s, t.enc[0].xin, Re * H, t.drop(0));                                   // embedding dropout, model_spec2midi.py:95
   for (size_t l = 0; l < m->enc.size(); ++l)
-    HFT_TRY(enc_layer_fwd(m, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], l + 1 < m->enc.size() ? t.enc[l + 1].xin : t.x_enc, tmp));
+    HFT_TRY(enc_layer_fwd(t, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], l + 1 < m->enc.size() ? t.enc[l + 1].xin : t.x_enc, tmp, t.site_enc((int)l)));
   // decoder layer zero (model_spec2midi.py:255-272)
   {
     DecTape& D = t.dec[0];
     const DecLayerW& lw = m->dec0;
     HFT_TRY(gemm_tn(s, t.x_enc, H, m->dec_ca_kv[0].qkv_w, H, m->dec_ca_kv[0].qkv_b, D.kv, 2 * H, Re, 2 * H, H, false));
-    HFT_TRY(attn_fwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c));
+    const int b0 = t.site_dec0();                            // + 0 cross probabilities, + 1 cross output, + 2 hidden, + 3 FFN output
+    HFT_TRY(attn_fwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c, t.drop(b0)));
     HFT_TRY(gemm_tn(s, D.ctx_c, H, m->w[lw.ca.o_w], H, m->w[lw.ca.o_b], tmp, H, Rd, H, H, false));
-    ln_fwd(m, s, tmp, m->w[m->dec_pos_freq], NN, lw.ln, Rd, D.t1, D.s1);
+    ln_fwd(m, s, tmp, m->w[m->dec_pos_freq], NN, lw.ln, Rd, D.t1, D.s1, t.drop(b0 + 1), true);   // the sub-layer output is the first operand here
     HFT_TRY(gemm_tn(s, D.t1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], D.hid, P, Rd, P, H, true));
+    dropout_inplace(s, D.hid, Rd * P, t.drop(b0 + 2));
     HFT_TRY(gemm_tn(s, D.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, Rd, H, P, false));
-    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, m->dec.empty() ? t.t_out : t.dec[1].tin, D.s2);
+    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, m->dec.empty() ? t.t_out : t.dec[1].tin, D.s2, t.drop(b0 + 3));
   }
   for (size_t l = 0; l < m->dec.size(); ++l) {               // model_spec2midi.py:283-306
     DecTape& D = t.dec[l + 1];
     const DecLayerW& lw = m->dec[l];
     float* out = l + 1 < m->dec.size() ? t.dec[l + 2].tin : t.t_out;
     HFT_TRY(gemm_tn(s, D.tin, H, m->dec_sa_qkv[l].qkv_w, H, m->dec_sa_qkv[l].qkv_b, D.qkv, 3 * H, Rd, 3 * H, H, false));
-    HFT_TRY(attn_fwd(m, s, D.qkv, 3 * H, (long long)NN * 3 * H, D.qkv + H, D.qkv + 2 * H, 3 * H, Se, NN, NN, D.ctx_s, D.lse_s));
+    const int bl = t.site_dec((int)l);                       // + 0 self probabilities, + 1 self output, + 2 cross probabilities, + 3 cross output, + 4 hidden, + 5 FFN output
+    HFT_TRY(attn_fwd(m, s, D.qkv, 3 * H, (long long)NN * 3 * H, D.qkv + H, D.qkv + 2 * H, 3 * H, Se, NN, NN, D.ctx_s, D.lse_s, t.drop(bl)));
     HFT_TRY(gemm_tn(s, D.ctx_s, H, m->w[lw.sa.o_w], H, m->w[lw.sa.o_b], tmp, H, Rd, H, H, false));
-    ln_fwd(m, s, D.tin, tmp, Rd, lw.ln, Rd, D.t0, D.s0);
+    ln_fwd(m, s, D.tin, tmp, Rd, lw.ln, Rd, D.t0, D.s0, t.drop(bl + 1));
     HFT_TRY(gemm_tn(s, D.t0, H, m->w[lw.ca.q_w], H, m->w[lw.ca.q_b], D.qc, H, Rd, H, H, false));
     HFT_TRY(gemm_tn(s, t.x_enc, H, m->dec_ca_kv[l + 1].qkv_w, H, m->dec_ca_kv[l + 1].qkv_b, D.kv, 2 * H, Re, 2 * H, H, false));
-    HFT_TRY(attn_fwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c));
+    HFT_TRY(attn_fwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, Se, NN, NB, D.ctx_c, D.lse_c, t.drop(bl + 2)));
     HFT_TRY(gemm_tn(s, D.ctx_c, H, m->w[lw.ca.o_w], H, m->w[lw.ca.o_b], tmp, H, Rd, H, H, false));
-    ln_fwd(m, s, D.t0, tmp, Rd, lw.ln, Rd, D.t1, D.s1);
+    ln_fwd(m, s, D.t0, tmp, Rd, lw.ln, Rd, D.t1, D.s1, t.drop(bl + 3));
     HFT_TRY(gemm_tn(s, D.t1, H, m->w[lw.ff.w1], H, m->w[lw.ff.b1], D.hid, P, Rd, P, H, true));
+    dropout_inplace(s, D.hid, Rd * P, t.drop(bl + 4));
     HFT_TRY(gemm_tn(s, D.hid, P, m->w[lw.ff.w2], P, m->w[lw.ff.b2], tmp, H, Rd, H, P, false));
-    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, out, D.s2);
+    ln_fwd(m, s, D.t1, tmp, Rd, lw.ln, Rd, out, D.s2, t.drop(bl + 5));
   }
   HFT_TRY(pack_heads(t, s));
   HFT_TRY(gemm_tn(s, t.t_out, H, t.head_w[0], H, t.head_b[0], t.logits_a, t.NP, Rd, t.NP, H, false));
@@ -284,8 +325,9 @@ static int train_forward(Trainer& t, const float* spec, long long sb, long long 
     LaunchScope ls(HFT_KCLASS_NORM, s);
     time_relayout_f32_kernel<<<(unsigned)((Rd * H + 255) / 256), 256, 0, s>>>(t.t_out, m->w[m->pos_time], sqrtH, F, NN, H, Rd * H, t.tim.empty() ? t.u_out : t.tim[0].xin);
   }
+  dropout_inplace(s, t.tim.empty() ? t.u_out : t.tim[0].xin, Rd * H, t.drop(t.site_time_emb()));   // model_spec2midi.py:191
   for (size_t l = 0; l < m->tim.size(); ++l)
-    HFT_TRY(enc_layer_fwd(m, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], l + 1 < m->tim.size() ? t.tim[l + 1].xin : t.u_out, tmp));
+    HFT_TRY(enc_layer_fwd(t, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], l + 1 < m->tim.size() ? t.tim[l + 1].xin : t.u_out, tmp, t.site_time((int)l)));
   HFT_TRY(gemm_tn(s, t.u_out, H, t.head_w[1], H, t.head_b[1], t.logits_b, t.NP, Rd, t.NP, H, false));
   return HFT_OK;
 }
@@ -306,12 +348,13 @@ static int heads_bwd(Trainer& t, cudaStream_t s, int which, const float* x, floa
 }
 
 // FFN + LayerNorm block of a decoder layer: g = dL/d(out) -> dL/d(t1)
-static int dec_ffn_bwd(Trainer& t, cudaStream_t s, DecTape& D, const DecLayerW& lw, long long Rd, float* g, float* G) {
+static int dec_ffn_bwd(Trainer& t, cudaStream_t s, DecTape& D, const DecLayerW& lw, long long Rd, float* g, float* G, int site_hid, int site_out) {
   Model* m = t.m;
   const int H = m->H, P = m->P;
   ln_bwd(m, s, g, D.s2, lw.ln, Rd, g, G);
-  HFT_TRY(gemm_dw(s, g, H, D.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), Rd, H, P));
-  HFT_TRY(gemm_nn(s, g, H, m->w[lw.ff.w2], P, t.gHID, P, Rd, P, H, false, D.hid, P));
+  const float* gb = branch_grad(s, g, t.gM, Rd * H, t.drop(site_out));
+  HFT_TRY(gemm_dw(s, gb, H, D.hid, P, gof(m, G, lw.ff.w2), P, gof(m, G, lw.ff.b2), Rd, H, P));
+  HFT_TRY(gemm_nn(s, gb, H, m->w[lw.ff.w2], P, t.gHID, P, Rd, P, H, false, D.hid, P, t.drop(site_hid).scale));
   HFT_TRY(gemm_dw(s, t.gHID, P, D.t1, H, gof(m, G, lw.ff.w1), H, gof(m, G, lw.ff.b1), Rd, P, H));
   HFT_TRY(gemm_nn(s, t.gHID, P, m->w[lw.ff.w1], H, g, H, Rd, H, P, true));
   return HFT_OK;
@@ -331,7 +374,8 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
   }
   HFT_TRY(heads_bwd(t, s, 1, t.u_out, t.gU, false, G));
   for (int l = (int)m->tim.size() - 1; l >= 0; --l)
-    HFT_TRY(enc_layer_bwd(t, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], t.gU, t.gDQ, t.gCTX, t.gHID, G));
+    HFT_TRY(enc_layer_bwd(t, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], t.gU, t.gDQ, t.gCTX, t.gHID, G, t.site_time(l)));
+  dropout_inplace(s, t.gU, Rd * H, t.drop(t.site_time_emb()));                           // back through the time-embedding dropout
   colsum(s, t.gU, (long long)B * NN, (long long)F * H, gof(m, G, m->pos_time));          // pos_embedding_time
   // ---- heads A + re-layout ----
   {
@@ -356,19 +400,22 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
   for (int l = (int)m->dec.size() - 1; l >= 0; --l) {
     DecTape& D = t.dec[l + 1];
     const DecLayerW& lw = m->dec[l];
-    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G));
+    const int bl = t.site_dec(l);
+    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G, bl + 4, bl + 5));
     ln_bwd(m, s, t.gT, D.s1, lw.ln, Rd, t.gT, G);
-    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
-    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
-    HFT_TRY(attn_bwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD));
+    const float* gb = branch_grad(s, t.gT, t.gM, Rd * H, t.drop(bl + 3));
+    HFT_TRY(gemm_dw(s, gb, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, gb, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
+    HFT_TRY(attn_bwd(m, s, D.qc, H, (long long)NN * H, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD, t.drop(bl + 2)));
     HFT_TRY(gemm_dw(s, t.gDQ, H, D.t0, H, gof(m, G, lw.ca.q_w), H, gof(m, G, lw.ca.q_b), Rd, H, H));
     HFT_TRY(gemm_nn(s, t.gDQ, H, m->w[lw.ca.q_w], H, t.gT, H, Rd, H, H, true));
     HFT_TRY(cross_kv_bwd(D, lw, m->dec_ca_kv[l + 1]));
     ln_bwd(m, s, t.gT, D.s0, lw.ln, Rd, t.gT, G);
-    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_s, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), Rd, H, H));
-    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.sa.o_w], H, t.gCTX, H, Rd, H, H, false));
+    gb = branch_grad(s, t.gT, t.gM, Rd * H, t.drop(bl + 1));
+    HFT_TRY(gemm_dw(s, gb, H, D.ctx_s, H, gof(m, G, lw.sa.o_w), H, gof(m, G, lw.sa.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, gb, H, m->w[lw.sa.o_w], H, t.gCTX, H, Rd, H, H, false));
     HFT_TRY(attn_bwd(m, s, D.qkv, 3 * H, (long long)NN * 3 * H, D.qkv + H, D.qkv + 2 * H, 3 * H, t.gCTX, D.ctx_s, D.lse_s, Se, NN, NN, t.gDQ, 3 * H, t.gDQ + H,
-                     t.gDQ + 2 * H, 3 * H, t.dD));
+                     t.gDQ + 2 * H, 3 * H, t.dD, t.drop(bl)));
     HFT_TRY(gemm_dw(s, t.gDQ, 3 * H, D.tin, H, gof(m, G, lw.sa.q_w), H, gof(m, G, lw.sa.q_b), Rd, H, H));
     HFT_TRY(gemm_dw(s, t.gDQ + H, 3 * H, D.tin, H, gof(m, G, lw.sa.k_w), H, gof(m, G, lw.sa.k_b), Rd, H, H));
     HFT_TRY(gemm_dw(s, t.gDQ + 2 * H, 3 * H, D.tin, H, gof(m, G, lw.sa.v_w), H, gof(m, G, lw.sa.v_b), Rd, H, H));
@@ -378,12 +425,14 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
     DecTape& D = t.dec[0];
     const DecLayerW& lw = m->dec0;
     float* g_pos = gof(m, G, m->dec_pos_freq);
-    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G));
-    ln_bwd(m, s, t.gT, D.s1, lw.ln, Rd, t.gT, G);                                       // s1 = pos_embedding_freq + fc_o(ctx)
+    const int b0 = t.site_dec0();
+    HFT_TRY(dec_ffn_bwd(t, s, D, lw, Rd, t.gT, G, b0 + 2, b0 + 3));
+    ln_bwd(m, s, t.gT, D.s1, lw.ln, Rd, t.gT, G);                                       // s1 = pos_embedding_freq + dropout(fc_o(ctx))
     colsum(s, t.gT, Se, (long long)NN * H, g_pos);
-    HFT_TRY(gemm_dw(s, t.gT, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
-    HFT_TRY(gemm_nn(s, t.gT, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
-    HFT_TRY(attn_bwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD));
+    const float* gb = branch_grad(s, t.gT, t.gM, Rd * H, t.drop(b0 + 1));
+    HFT_TRY(gemm_dw(s, gb, H, D.ctx_c, H, gof(m, G, lw.ca.o_w), H, gof(m, G, lw.ca.o_b), Rd, H, H));
+    HFT_TRY(gemm_nn(s, gb, H, m->w[lw.ca.o_w], H, t.gCTX, H, Rd, H, H, false));
+    HFT_TRY(attn_bwd(m, s, m->q0, H, 0, D.kv, D.kv + H, 2 * H, t.gCTX, D.ctx_c, D.lse_c, Se, NN, NB, t.gDQ, H, gkv, gkv + H, 2 * H, t.dD, t.drop(b0)));
     HFT_CHECK_CUDA(cudaMemsetAsync(t.gQ0, 0, (size_t)NN * H * sizeof(float), s));
     colsum(s, t.gDQ, Se, (long long)NN * H, t.gQ0);                                     // the same projected queries serve every sequence
     HFT_TRY(gemm_dw(s, t.gQ0, H, m->w[m->dec_pos_freq], H, gof(m, G, lw.ca.q_w), H, gof(m, G, lw.ca.q_b), NN, H, H));
@@ -392,7 +441,8 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
   }
   // ---- encoder ----
   for (int l = (int)m->enc.size() - 1; l >= 0; --l)
-    HFT_TRY(enc_layer_bwd(t, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], t.gX, t.gBIG, t.gCTX, t.gHID, G));
+    HFT_TRY(enc_layer_bwd(t, s, t.enc[l], Se, NB, m->enc[l], m->enc_qkv[l], t.gX, t.gBIG, t.gCTX, t.gHID, G, t.site_enc(l)));
+  dropout_inplace(s, t.gX, Re * H, t.drop(0));                                           // back through the embedding dropout
   colsum(s, t.gX, Se, (long long)NB * H, gof(m, G, m->pos_freq));                       // pos_embedding_freq (encoder)
   // ---- front: conv + Linear through the collapsed 65-tap filter ----
   HFT_CHECK_CUDA(cudaMemsetAsync(t.g_front_w, 0, (size_t)H * m->nproc * sizeof(float), s));
@@ -436,6 +486,24 @@ extern "C" int hft_trainer_destroy(hft_trainer* trainer) {
   Trainer* t = reinterpret_cast<Trainer*>(trainer);
   cudaFree(t->arena);
   delete t;
+  return HFT_OK;
+}
+
+extern "C" int hft_trainer_set_dropout(hft_trainer* trainer, float p, uint32_t seed) {
+  HFT_REQUIRE(trainer && p >= 0.f && p < 1.f, HFT_ERR_ARG, "hft_trainer_set_dropout: p must be in [0, 1)");
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  t->p_drop = p;
+  t->seed = seed;
+  return HFT_OK;
+}
+
+extern "C" int hft_dropout_mask(float p, uint32_t seed, int32_t site, int64_t n, float* mask_out_dev, void* stream) {
+  HFT_REQUIRE(mask_out_dev && n >= 0 && p >= 0.f && p < 1.f, HFT_ERR_ARG, "hft_dropout_mask: bad argument");
+  if (n == 0) return HFT_OK;
+  Drop d{0u, seed, (uint32_t)site, 1.f};
+  if (p > 0.f) { d.thresh = (uint32_t)((double)p * 4294967296.0); d.scale = 1.f / (1.f - p); }
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask_out_dev, n, d);
+  HFT_CHECK_CUDA(cudaGetLastError());
   return HFT_OK;
 }
 

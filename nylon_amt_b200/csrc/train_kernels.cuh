@@ -13,7 +13,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                                        float* __restrict__ C, int ldc, int M, int N, int K, bool accum,
-                                                       const float* __restrict__ mask, int ldm) {
+                                                       const float* __restrict__ mask, int ldm, float mask_scale) {
   __shared__ __align__(16) float As[GBK][GBM + GPAD];
   __shared__ __align__(16) float Bs[GBK][GBN + GPAD];
   const int tid = threadIdx.x;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
       int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
       if (col >= N) continue;
       float v = acc[i][j];
-      if (mask && !(mask[(long long)row * ldm + col] > 0.f)) v = 0.f;
+      if (mask) v = (mask[(long long)row * ldm + col] > 0.f) ? v * mask_scale : 0.f;
       if (accum) v += C[(long long)row * ldc + col];
       C[(long long)row * ldc + col] = v;
     }
@@ -212,7 +212,7 @@ template <int DH>
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
                                                           const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, const float* __restrict__ O,
                                                           int ldo, const float* __restrict__ lse, int Lq, int Lk, int heads, float c,
-                                                          float* __restrict__ dQ, int lddq, float* __restrict__ Dout) {
+                                                          float* __restrict__ dQ, int lddq, float* __restrict__ Dout, Drop drop) {
   extern __shared__ __align__(16) float smem_bwd[];
   float* sK = smem_bwd;
   float* sV = smem_bwd + (size_t)Lk * DH;
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restric
     float s = 0.f, dp = 0.f;
 #pragma unroll
     for (int i = 0; i < DH; ++i) { s = fmaf(q[i], kr[i], s); dp = fmaf(go[i], vr[i], dp); }
+    if (drop.thresh) dp = drop_keep(drop, (unsigned long long)((((long long)seq * heads + head) * Lq + r) * Lk + j)) ? dp * drop.scale : 0.f;
     const float ds = expf(s * c - l) * (dp - D) * c;
 #pragma unroll
     for (int i = 0; i < DH; ++i) acc[i] = fmaf(ds, kr[i], acc[i]);
@@ -256,7 +257,7 @@ template <int DH, int MODE>
 __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
                                                            const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, int ldo,
                                                            const float* __restrict__ lse, const float* __restrict__ Din, int Lq, int Lk, int heads, float c,
-                                                           float* __restrict__ dK, float* __restrict__ dV, int lddkv) {
+                                                           float* __restrict__ dK, float* __restrict__ dV, int lddkv, Drop drop) {
   extern __shared__ __align__(16) float smem_bwd[];
   float* sQ = smem_bwd;
   float* sG = smem_bwd + (size_t)Lq * DH;
@@ -294,11 +295,15 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restri
       if (MODE != 2) dp = fmaf(gr[i], v[i], dp);
     }
     const float p = expf(s * c - sL[r]);
+    float keep_scale = 1.f;                              // dropout on the probabilities: O = (P . mask * scale) V
+    if (drop.thresh) keep_scale = drop_keep(drop, (unsigned long long)((((long long)seq * heads + head) * Lq + r) * Lk + j)) ? drop.scale : 0.f;
     if (MODE != 1) {
+      const float pd = p * keep_scale;
 #pragma unroll
-      for (int i = 0; i < DH; ++i) av[i] = fmaf(p, gr[i], av[i]);
+      for (int i = 0; i < DH; ++i) av[i] = fmaf(pd, gr[i], av[i]);
     }
     if (MODE != 2) {
+      dp *= keep_scale;
       const float ds = p * (dp - sD[r]) * c;
 #pragma unroll
       for (int i = 0; i < DH; ++i) ak[i] = fmaf(ds, qr[i], ak[i]);

@@ -6,8 +6,9 @@ reference builds in hftt_code/training/m_training.py:146 (`optim.Adam(model.para
 
 Forward, the 8-term loss, backward and Adam run in libhft_sm100.so (hft_train_forward_backward / hft_adam_step,
 include/hft_sm100.h); PyTorch owns the flat gradient / moment tensors, and in the data-parallel configuration it
-all-reduces the ONE flat gradient bucket over NCCL between backward and the Adam step.  Dropout must be 0
-(the parity configuration): the library has no dropout masks and refuses to pretend otherwise.
+all-reduces the ONE flat gradient bucket over NCCL between backward and the Adam step.  Dropout: the p of the
+model's nn.Dropout modules (the reference builds them with 0.1) is applied with the library's counter-based masks
+(hft_trainer_set_dropout, fresh seed every step); p = 0 gives the deterministic parity configuration.
 """
 import ctypes
 
@@ -20,9 +21,12 @@ from . import _lib
 class Adam:
     """torch.optim.Adam(params, lr, betas, eps) semantics (no weight decay / amsgrad) on the library's flat parameter vector."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=8, process_group=None):
-        if any(isinstance(m, nn.Dropout) and m.p > 0 for m in model.modules()):
-            raise NotImplementedError("the B200 training step implements dropout p = 0 only (build the model with dropout=0.0)")
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=8, process_group=None, seed=0):
+        ps = sorted({float(m.p) for m in model.modules() if isinstance(m, nn.Dropout)})
+        if len(ps) > 1:
+            raise NotImplementedError("the B200 training step applies ONE dropout probability to every site (the reference does too); got %r" % (ps,))
+        self.p_drop = ps[0] if ps else 0.0
+        self.seed = int(seed)
         self.model, self.lr, self.betas, self.eps = model, float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.batch_size, self.group, self.step_count = int(batch_size), process_group, 0
         h = model.sync_weights()
@@ -74,6 +78,11 @@ class Adam:
                 raise RuntimeError("label tensors must be [B, n_frame, n_note]")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
+            if self.p_drop > 0.0:              # fresh masks every iteration: (seed, iteration) -> 32-bit seed of the counter-based generator
+                self._fb_calls = getattr(self, "_fb_calls", 0) + 1
+                step_seed = (self.seed * 2654435761 + self._fb_calls * 40503) & 0xFFFFFFFF
+                _lib.check(_lib.lib().hft_trainer_set_dropout(self.trainer, self.p_drop, step_seed), "hft_trainer_set_dropout")
+                self.last_dropout_seed = step_seed
             _lib.check(_lib.lib().hft_train_forward_backward(
                 self.trainer, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), ctypes.c_void_p(lab[0].data_ptr()),
                 ctypes.c_void_p(lab[1].data_ptr()), ctypes.c_void_p(lab[2].data_ptr()), ctypes.c_void_p(vel.data_ptr()), float(weight_A), float(weight_B),

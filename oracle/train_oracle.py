@@ -73,3 +73,98 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, beta1=0.9, beta
         exp_avg_sq[k].mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
         denom = (exp_avg_sq[k].sqrt() / math.sqrt(bc2)).add_(eps)
         params[k].addcdiv_(exp_avg[k], denom, value=-lr / bc1)
+
+
+# ---- dropout ------------------------------------------------------------------------------------------------------------
+def dropout_multiplier(p, seed, site, n):
+    """Restatement of the library's counter-based dropout (csrc/f32_kernels.cuh `drop_keep`): float32 [n] holding 1/(1-p) where
+    element idx is kept and 0 where it is dropped; kept iff lowbias32(idx_lo * 0x9E3779B1 ^ idx_hi * 0x85EBCA77 ^ seed ^ site * 0xC2B2AE3D) >= p * 2^32."""
+    import numpy as np
+    if p <= 0.0:
+        return torch.ones(n)
+    idx = np.arange(n, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    lo, hi = idx & m32, idx >> np.uint64(32)
+    h = ((lo * np.uint64(0x9E3779B1)) & m32) ^ ((hi * np.uint64(0x85EBCA77)) & m32) ^ np.uint64(seed & 0xFFFFFFFF) ^ np.uint64((site * 0xC2B2AE3D) & 0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x7feb352d)) & m32
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x846ca68b)) & m32
+    h ^= h >> np.uint64(16)
+    thresh = np.uint64(int(float(np.float32(p)) * 4294967296.0))
+    keep = h >= thresh
+    return torch.from_numpy(np.where(keep, np.float32(1.0) / (np.float32(1.0) - np.float32(p)), np.float32(0.0)).astype(np.float32))
+
+
+class DropOracle(GradOracle):
+    """Training-mode forward of the reference (nn.Dropout active at every site of model_spec2midi.py) with the masks of the
+    library's site numbering (include/hft_sm100.h, hft_trainer_set_dropout)."""
+
+    def __init__(self, state_dict, n_heads, p, seed, dtype=torch.float32):
+        super().__init__(state_dict, n_heads, dtype=dtype)
+        self.p, self.seed = float(p), int(seed)
+
+    def drop(self, x, site):
+        m = dropout_multiplier(self.p, self.seed, site, x.numel()).to(x.dtype).view(x.shape)
+        return x * m
+
+    def mha_d(self, q_in, kv_in, prefix, site):
+        S, Lq, H = q_in.shape
+        d = H // self.h
+        Q = self.linear(q_in, prefix + ".fc_q").view(S, Lq, self.h, d).permute(0, 2, 1, 3)
+        K = self.linear(kv_in, prefix + ".fc_k").view(S, -1, self.h, d).permute(0, 2, 1, 3)
+        V = self.linear(kv_in, prefix + ".fc_v").view(S, -1, self.h, d).permute(0, 2, 1, 3)
+        attn = torch.softmax((Q @ K.transpose(-1, -2)) / math.sqrt(d), dim=-1).contiguous()
+        x = (self.drop(attn, site) @ V).permute(0, 2, 1, 3).reshape(S, Lq, H)
+        return self.linear(x, prefix + ".fc_o")
+
+    def ffn_d(self, x, prefix, site):
+        return self.linear(self.drop(torch.relu(self.linear(x, prefix + ".fc_1")), site), prefix + ".fc_2")
+
+    def enc_layer_d(self, x, prefix, base):
+        x = self.ln(x + self.drop(self.mha_d(x, x, prefix + ".self_attention", base), base + 1), prefix + ".layer_norm")
+        return self.ln(x + self.drop(self.ffn_d(x, prefix + ".positionwise_feedforward", base + 2), base + 3), prefix + ".layer_norm")
+
+    def forward_grad(self, spec):
+        spec = torch.as_tensor(spec, dtype=self.dtype)
+        B = spec.shape[0]
+        x = self.drop(self.front(spec).contiguous(), 0)
+        for i in range(self.n_enc):
+            x = self.enc_layer_d(x, "encoder_spec2midi.layers_freq.%d" % i, 1 + 4 * i)
+        enc = x
+        p = "decoder_spec2midi"
+        S = enc.shape[0]
+        q0 = self.sd[p + ".pos_embedding_freq.weight"][None].expand(S, -1, -1)
+        d0 = 1 + 4 * self.n_enc
+        t = self.ln(q0 + self.drop(self.mha_d(q0, enc, p + ".layer_zero_freq.encoder_attention", d0), d0 + 1), p + ".layer_zero_freq.layer_norm")
+        t = self.ln(t + self.drop(self.ffn_d(t, p + ".layer_zero_freq.positionwise_feedforward", d0 + 2), d0 + 3), p + ".layer_zero_freq.layer_norm")
+        for i in range(self.n_dec - 1):
+            lp, b = p + ".layers_freq.%d" % i, d0 + 4 + 6 * i
+            t = self.ln(t + self.drop(self.mha_d(t, t, lp + ".self_attention", b), b + 1), lp + ".layer_norm")
+            t = self.ln(t + self.drop(self.mha_d(t, enc, lp + ".encoder_attention", b + 2), b + 3), lp + ".layer_norm")
+            t = self.ln(t + self.drop(self.ffn_d(t, lp + ".positionwise_feedforward", b + 4), b + 5), lp + ".layer_norm")
+        shp = (B, self.n_frame, self.n_note)
+        on_a = torch.sigmoid(self.linear(t, p + ".fc_onset_freq").reshape(shp))
+        off_a = torch.sigmoid(self.linear(t, p + ".fc_offset_freq").reshape(shp))
+        mpe_a = torch.sigmoid(self.linear(t, p + ".fc_mpe_freq").reshape(shp))
+        vel_a = self.linear(t, p + ".fc_velocity_freq").reshape(shp + (self.n_velocity,))
+        t0 = d0 + 4 + 6 * (self.n_dec - 1)
+        u = t.reshape(B, self.n_frame, self.n_note, self.hid).permute(0, 2, 1, 3).reshape(B * self.n_note, self.n_frame, self.hid)
+        u = self.drop((u * math.sqrt(self.hid) + self.sd[p + ".pos_embedding_time.weight"][None]).contiguous(), t0)
+        for i in range(self.n_dec):
+            u = self.enc_layer_d(u, p + ".layers_time.%d" % i, t0 + 1 + 4 * i)
+        shp_t = (B, self.n_note, self.n_frame)
+        on_b = torch.sigmoid(self.linear(u, p + ".fc_onset_time").reshape(shp_t).permute(0, 2, 1)).contiguous()
+        off_b = torch.sigmoid(self.linear(u, p + ".fc_offset_time").reshape(shp_t).permute(0, 2, 1)).contiguous()
+        mpe_b = torch.sigmoid(self.linear(u, p + ".fc_mpe_time").reshape(shp_t).permute(0, 2, 1)).contiguous()
+        vel_b = self.linear(u, p + ".fc_velocity_time").reshape(shp_t + (self.n_velocity,)).permute(0, 2, 1, 3).contiguous()
+        return on_a, off_a, mpe_a, vel_a, None, on_b, off_b, mpe_b, vel_b
+
+
+def loss_and_grads_dropout(state_dict, n_heads, spec, label_onset, label_offset, label_mpe, label_velocity, p, seed, weight_A=1.0, weight_B=1.0,
+                           dtype=torch.float32):
+    o = DropOracle(state_dict, n_heads, p, seed, dtype=dtype)
+    outs = o.forward_grad(spec)
+    loss = loss_from_outputs(outs, label_onset.to(dtype), label_offset.to(dtype), label_mpe.to(dtype), label_velocity, weight_A, weight_B)
+    loss.backward()
+    return float(loss.detach()), {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in o.sd.items()}
