@@ -84,22 +84,24 @@ __global__ void __launch_bounds__(256) front_f32_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBN = 128, GBK = 16, GPAD = 4;
 
-template <bool RELU>
+// BN: tile width (128, or 64 for the narrow projections of the reduced model so that no half-empty tile is computed)
+template <bool RELU, int BN = 128>
 __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int ldw,
                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K,
                                                        bool accum = false) {
+  constexpr int NJ = BN / 16;                      // columns per thread: 8 (two groups of 4, 64 apart) or 4
   __shared__ __align__(16) float As[GBK][GBM + GPAD];
-  __shared__ __align__(16) float Ws[GBK][GBN + GPAD];
+  __shared__ __align__(16) float Ws[GBK][BN + GPAD];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * BN;
   const int lrow = tid >> 1, lk = (tid & 1) * 8;
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[8][NJ];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const bool a_ok = (m0 + lrow) < M, w_ok = (n0 + lrow) < N;
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+  const bool a_ok = (m0 + lrow) < M, w_ld = lrow < BN, w_ok = w_ld && (n0 + lrow) < N;
   const float* ap = A + (long long)(m0 + lrow) * lda + lk;
   const float* wp = Wt + (long long)(n0 + lrow) * ldw + lk;
   float4 a0, a1, w0, w1;
@@ -111,8 +113,10 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
   for (int k0 = 0; k0 < K; k0 += GBK) {
     As[lk + 0][lrow] = a0.x; As[lk + 1][lrow] = a0.y; As[lk + 2][lrow] = a0.z; As[lk + 3][lrow] = a0.w;
     As[lk + 4][lrow] = a1.x; As[lk + 5][lrow] = a1.y; As[lk + 6][lrow] = a1.z; As[lk + 7][lrow] = a1.w;
-    Ws[lk + 0][lrow] = w0.x; Ws[lk + 1][lrow] = w0.y; Ws[lk + 2][lrow] = w0.z; Ws[lk + 3][lrow] = w0.w;
-    Ws[lk + 4][lrow] = w1.x; Ws[lk + 5][lrow] = w1.y; Ws[lk + 6][lrow] = w1.z; Ws[lk + 7][lrow] = w1.w;
+    if (w_ld) {
+      Ws[lk + 0][lrow] = w0.x; Ws[lk + 1][lrow] = w0.y; Ws[lk + 2][lrow] = w0.z; Ws[lk + 3][lrow] = w0.w;
+      Ws[lk + 4][lrow] = w1.x; Ws[lk + 5][lrow] = w1.y; Ws[lk + 6][lrow] = w1.z; Ws[lk + 7][lrow] = w1.w;
+    }
     __syncthreads();
     if (k0 + GBK < K) {                            // register prefetch of the next K slab
       a0 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK) : z;
@@ -125,13 +129,13 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
       float4 ra0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
       float4 ra1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
       float4 rb0 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-      float4 rb1 = *reinterpret_cast<const float4*>(&Ws[k][64 + tx * 4]);
+      float4 rb1 = BN == 128 ? *reinterpret_cast<const float4*>(&Ws[k][(BN == 128 ? 64 : 0) + tx * 4]) : z;
       float ra[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
       float rb[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+        for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
     int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
       if (col >= N) continue;
       float v = acc[i][j] + (bias ? bias[col] : 0.f);
@@ -150,6 +154,9 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
     }
   }
 }
+
+// tile width with the fewest padded columns (ties -> 128)
+inline int sgemm_tile_n(int N) { return ((N + 63) / 64 * 64 < (N + 127) / 128 * 128) ? 64 : 128; }
 
 // ------------------------------------------------------------------------------------------------------------
 // attention for one (sequence, head): softmax(Q K^T / sqrt(dh)) V  (model_spec2midi.py:342-348), two passes over

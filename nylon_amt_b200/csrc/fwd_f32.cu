@@ -16,10 +16,16 @@ namespace hft {
 static int gemm(cudaStream_t s, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc, long long M, int N, int K,
                 bool relu) {
   HFT_REQUIRE(K % GBK == 0 && lda % 4 == 0 && ldw % 4 == 0, HFT_ERR_UNSUPPORTED, "sgemm: K=%d lda=%d ldw=%d not supported", K, lda, ldw);
-  dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+  const int bn = sgemm_tile_n(N);
+  dim3 grid((N + bn - 1) / bn, (unsigned)((M + GBM - 1) / GBM));
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  if (relu) sgemm_tn_kernel<true><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
-  else sgemm_tn_kernel<false><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
+  if (bn == 64) {
+    if (relu) sgemm_tn_kernel<true, 64><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
+    else sgemm_tn_kernel<false, 64><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
+  } else {
+    if (relu) sgemm_tn_kernel<true, 128><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
+    else sgemm_tn_kernel<false, 128><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K);
+  }
   return HFT_OK;
 }
 

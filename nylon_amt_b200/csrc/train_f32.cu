@@ -65,19 +65,27 @@ struct Trainer {
 static int gemm_tn(cudaStream_t s, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc, long long M, int N, int K,
                    bool relu, bool accum = false) {
   HFT_REQUIRE(K % GBK == 0 && lda % 4 == 0 && ldw % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_tn: K=%d lda=%d ldw=%d", K, lda, ldw);
-  dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+  const int bn = sgemm_tile_n(N);
+  dim3 grid((N + bn - 1) / bn, (unsigned)((M + GBM - 1) / GBM));
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  if (relu) sgemm_tn_kernel<true><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
-  else sgemm_tn_kernel<false><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+  if (bn == 64) {
+    if (relu) sgemm_tn_kernel<true, 64><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+    else sgemm_tn_kernel<false, 64><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+  } else {
+    if (relu) sgemm_tn_kernel<true, 128><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+    else sgemm_tn_kernel<false, 128><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, bias, C, ldc, (int)M, N, K, accum);
+  }
   return HFT_OK;
 }
 // C[M,N] (+)= A[M,K] * W[K,N]
 static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int ldb, float* C, int ldc, long long M, int N, int K, bool accum,
                    const float* mask = nullptr, int ldm = 0, float mask_scale = 1.f) {
   HFT_REQUIRE(K % GBK == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_nn: N=%d K=%d lda=%d ldb=%d", N, K, lda, ldb);
-  dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+  const int bn = sgemm_tile_n(N);
+  dim3 grid((N + bn - 1) / bn, (unsigned)((M + GBM - 1) / GBM));
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  sgemm_nn_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm, mask_scale);
+  if (bn == 64) sgemm_nn_kernel<64><<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm, mask_scale);
+  else sgemm_nn_kernel<128><<<grid, 256, 0, s>>>(A, lda, W, ldb, C, ldc, (int)M, N, K, accum, mask, ldm, mask_scale);
   return HFT_OK;
 }
 // dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)

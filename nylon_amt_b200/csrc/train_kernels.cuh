@@ -11,23 +11,26 @@ namespace {
 // C[M,N] (+)= A[M,K] * B[K,N]   (dX = dY * W with W = [out,in] row-major as B).  Optional ReLU mask: C *= (mask > 0).
 // 128x128x16 tiles like sgemm_tn_kernel.  K % 16 == 0, N % 4 == 0, lda % 4 == 0, ldb % 4 == 0.
 // ------------------------------------------------------------------------------------------------------------
+template <int BN = 128>
 __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                                        float* __restrict__ C, int ldc, int M, int N, int K, bool accum,
                                                        const float* __restrict__ mask, int ldm, float mask_scale) {
+  constexpr int NJ = BN / 16;
+  constexpr int BV = BN / 16;                             // floats loaded per thread for the B tile: 8 (two float4) or 4 (one)
   __shared__ __align__(16) float As[GBK][GBM + GPAD];
-  __shared__ __align__(16) float Bs[GBK][GBN + GPAD];
+  __shared__ __align__(16) float Bs[GBK][BN + GPAD];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * BN;
   const int lrow = tid >> 1, lk = (tid & 1) * 8;          // A tile: 128 rows x 16 k
-  const int brow = tid >> 4, bcol = (tid & 15) * 8;       // B tile: 16 k x 128 cols
+  const int brow = tid >> 4, bcol = (tid & 15) * BV;      // B tile: 16 k x BN cols
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[8][NJ];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
   const bool a_ok = (m0 + lrow) < M;
-  const bool b_ok0 = (n0 + bcol) < N, b_ok1 = (n0 + bcol + 4) < N;
+  const bool b_ok0 = (n0 + bcol) < N, b_ok1 = BN == 128 && (n0 + bcol + 4) < N;
   const float* ap = A + (long long)(m0 + lrow) * lda + lk;
   const float* bp = Bm + (long long)brow * ldb + n0 + bcol;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
     As[lk + 0][lrow] = a0.x; As[lk + 1][lrow] = a0.y; As[lk + 2][lrow] = a0.z; As[lk + 3][lrow] = a0.w;
     As[lk + 4][lrow] = a1.x; As[lk + 5][lrow] = a1.y; As[lk + 6][lrow] = a1.z; As[lk + 7][lrow] = a1.w;
     *reinterpret_cast<float4*>(&Bs[brow][bcol]) = b0;
-    *reinterpret_cast<float4*>(&Bs[brow][bcol + 4]) = b1;
+    if (BN == 128) *reinterpret_cast<float4*>(&Bs[brow][bcol + 4]) = b1;
     __syncthreads();
     if (k0 + GBK < K) {
       a0 = a_ok ? *reinterpret_cast<const float4*>(ap + k0 + GBK) : z;
@@ -51,13 +54,13 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
       float4 ra0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
       float4 ra1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
       float4 rb0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      float4 rb1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      float4 rb1 = BN == 128 ? *reinterpret_cast<const float4*>(&Bs[k][(BN == 128 ? 64 : 0) + tx * 4]) : z;
       float ra[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
       float rb[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+        for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
     int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
       if (col >= N) continue;
       float v = acc[i][j];
