@@ -139,3 +139,55 @@ def test_transcript_matches_reference_golden(golden_dir):
     key = lambda n: (n["pitch"], round(n["onset"] / 0.016))
     mine, ref = {key(n) for n in notes}, {key(n) for n in ref_notes}
     assert len(mine ^ ref) <= max(2, len(ref) // 500), (len(mine), len(ref), len(mine ^ ref))
+
+
+def test_full_hour_paper_size_properties():
+    """BASELINE configs[1] at full size (1 h of 16 kHz audio -> 225 001 frames -> 1 758 segments, paper-size model, fp16x3): the oracle
+    cannot run this in seconds, so the checks are size-independent properties -- ranges, determinism, independence of a segment's
+    result from the batch it is computed in, and agreement of sampled segments with the fp32 CUDA-core path inside the 2e-3 budget."""
+    cfg = hft.default_config()
+    dev = torch.device("cuda")
+    amt = hft.AMT(cfg, None, batch_size=16)
+    model = hft.build_model(cfg, 256, 512, 3, 4, seed=1234, device=dev)
+    model.max_batch = 16
+    n = 3600 * 16000
+    wav = 0.1 * torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1000))
+    feat = amt.wave2feature(wav)
+    T = feat.shape[0]
+    assert T == 225001
+    n_seg = (T + 127) // 128
+    assert n_seg == 1758
+    a_input = torch.full((32 + n_seg * 128 + 32, 256), cfg["input"]["min_value"], device=dev)
+    a_input[32:32 + T] = feat
+    spec_all = torch.as_strided(a_input, (n_seg, 256, 192), (128 * 256, 1, 256))
+
+    def run(precision, lo, hi):
+        model.precision = precision
+        outs = [[] for _ in range(8)]
+        for s0 in range(lo, hi, 16):
+            o = model(spec_all[s0:min(s0 + 16, hi)])
+            for k, i in enumerate((0, 1, 2, 3, 5, 6, 7, 8)):
+                outs[k].append(o[i] if i not in (3, 8) else o[i].argmax(3).to(torch.int16))     # keep the velocity class, not 46 MB / segment
+        return [torch.cat(x) for x in outs]
+
+    full = run("fp16x3", 0, n_seg)
+    for k in (0, 1, 2, 4, 5, 6):
+        assert torch.isfinite(full[k]).all() and float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0
+        assert tuple(full[k].shape) == (n_seg, 128, 88)
+    # determinism
+    again = run("fp16x3", 0, 64)
+    for a, b in zip(again, full):
+        assert torch.equal(a, b[:64])
+    # a segment's result does not depend on its batch: segments 1000..1015 alone, and 1003..1007 as an odd-sized batch
+    part = run("fp16x3", 1000, 1016)
+    for a, b in zip(part, full):
+        assert torch.equal(a, b[1000:1016])
+    model.precision = "fp16x3"
+    odd = model(spec_all[1003:1008])
+    assert float((odd[5] - full[4][1003:1008]).abs().max()) <= 1e-5          # 5 segments take the single-CTA tiles (rows % 256 != 0 in the decoder)
+    # sampled segments against the fp32 CUDA-core path
+    for s0 in (0, 777, 1742):
+        ref = run("fp32", s0, s0 + 16 if s0 + 16 <= n_seg else n_seg)
+        for k in (0, 1, 2, 4, 5, 6):
+            err = float((ref[k] - full[k][s0:s0 + ref[k].shape[0]]).abs().max())
+            assert err <= TOL_FP32, (s0, k, err)
