@@ -421,6 +421,10 @@ def main():
                 "hbm": {"achieved": (traffic / max(fwd_ms, 1e-9) / 1e6) if traffic else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": (traffic / max(fwd_ms, 1e-9) / 1e6 / pk["hbm_gbs"]) if traffic else None},
                 "peak_source": pk["src"], "algorithmic_gflop_per_segment": GFLOP_PER_SEGMENT,
+                # executed tensor-core work: the collapsed front filter (4.17 GF, CUDA cores) and the constant layer-zero query projection
+                # (1.5 GF) are not executed as MMAs; split mode executes 3 products per algorithmic product (shortcuts reported)
+                "executed_mma": (lambda ex: {"tflops": ex, "frac": ex / pk["tflops"], "products": 3 if args.precision == "fp16x3" else 1})(
+                    (3 if args.precision == "fp16x3" else 1) * n_seg * (GFLOP_PER_SEGMENT - 4.17 - 1.5) / max(fwd_ms, 1e-9)) if args.precision != "fp32" else None,
                 "classes_ms": {n: round(v["ms"], 3) for n, v in prof.items()},
                 "logmel": {"bound": "hbm", "achieved": T * LOGMEL_BYTES_PER_FRAME / max(prof["logmel"]["ms"], 1e-9) / 1e6,
                            "peak": pk["hbm_gbs"], "unit": "GB/s",
