@@ -135,10 +135,19 @@ def test_transcript_matches_reference_golden(golden_dir):
     out = amt.transcript(t["feature"])
     notes = amt.mpe2note(a_onset=out[4], a_offset=out[5], a_mpe=out[6], a_velocity=out[7])
     ref_notes = json.loads(str(t["notes_B"]))
-    # note lists: same notes up to entries whose probability sits within the fp32 tolerance of a threshold
+    # note lists (north_star: identical thresholded note lists on the synthetic set): the decisive fixture keeps every probability
+    # clear of the thresholds, so the lists must agree note for note at frame resolution, in both fp32-class modes
     key = lambda n: (n["pitch"], round(n["onset"] / 0.016))
-    mine, ref = {key(n) for n in notes}, {key(n) for n in ref_notes}
-    assert len(mine ^ ref) <= max(2, len(ref) // 500), (len(mine), len(ref), len(mine ^ ref))
+    ref = {key(n): n for n in ref_notes}
+    for precision in ("fp16x3", "fp32"):
+        amt.model.precision = precision
+        out = amt.transcript(t["feature"])
+        notes = amt.mpe2note(a_onset=out[4], a_offset=out[5], a_mpe=out[6], a_velocity=out[7])
+        mine = {key(n): n for n in notes}
+        assert len(notes) == len(ref_notes) and set(mine) == set(ref), (precision, len(notes), len(ref_notes), len(set(mine) ^ set(ref)))
+        worst_on = max(abs(mine[k]["onset"] - ref[k]["onset"]) for k in ref)
+        same_vel = sum(mine[k]["velocity"] == ref[k]["velocity"] for k in ref) / len(ref)
+        assert worst_on <= 1e-3 and same_vel >= 0.999, (precision, worst_on, same_vel)     # sub-frame onset interpolation within 1 ms
 
 
 def test_full_hour_paper_size_properties():
