@@ -1,64 +1,65 @@
-#! python
-"""Driver of the feature path -- same command line as the reference's hftt_code/corpus/conv_wav2fe.py:13-50:
+"""Corpus feature driver on the B200 path.
+
+Command line compatible with the reference tool (hftt_code/corpus/conv_wav2fe.py:13-50; flags -d_list, -d_wav, -d_feature, -config):
 
     python -m nylon_amt_b200.conv_wav2fe -d_list LISTS -d_wav WAVS -d_feature OUT -config config.json
 
-For every name in {train,test,valid}.list it writes OUT/<name>.pkl holding the CPU FloatTensor [T, 256] that
-AMT.wav2feature returns (pickle protocol 4, conv_wav2fe.py:46-48).  Under torchrun the files of every list are split into
-contiguous blocks per rank (one process per GPU, no collective: SURVEY.md 8e); a single process converts everything.
+Every name found in LISTS/{train,test,valid}.list becomes OUT/<name>.pkl, a pickle (protocol 4) of the CPU FloatTensor [T, 256]
+returned by AMT.wav2feature -- the on-disk feature format the rest of the reference pipeline reads.  Launched under torchrun, each
+rank takes a contiguous block of every list (one process per GPU, no collective: SURVEY.md 8e).
 """
 import argparse
 import json
-import os
+import pathlib
 import pickle
 
-from . import amt, shard
+from . import shard
+from .amt import AMT
+
+SPLITS = ("train", "test", "valid")
+
+
+def _names(list_dir, split):
+    path = pathlib.Path(list_dir) / (split + ".list")
+    if not path.is_file():
+        return []
+    return [line.strip() for line in path.read_text(encoding="utf-8").splitlines() if line.strip()]
+
+
+def convert(list_dir, wav_dir, feature_dir, config, rank=0, world=1, log=print):
+    """Returns the number of files this rank converted."""
+    extractor = AMT(config, None, None)
+    wav_dir, feature_dir = pathlib.Path(wav_dir), pathlib.Path(feature_dir)
+    done = 0
+    for split in SPLITS:
+        names = _names(list_dir, split)
+        lo, hi = shard.partition(len(names), world, rank)
+        if rank == 0:
+            log("[%s] %d files, rank 0 takes %d" % (split, len(names), hi - lo))
+        for name in names[lo:hi]:
+            feature = extractor.wav2feature(str(wav_dir / (name + ".wav")))
+            with open(feature_dir / (name + ".pkl"), "wb") as fh:
+                pickle.dump(feature, fh, protocol=4)
+            done += 1
+    return done
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument('-d_list', help='corpus list directory')
-    parser.add_argument('-d_wav', help='wav file directory (input)')
-    parser.add_argument('-d_feature', help='feature file directory (output)')
-    parser.add_argument('-config', help='config file')
-    args = parser.parse_args(argv)
-
+    ap = argparse.ArgumentParser(description="wav -> log-mel feature pickles (B200)")
+    for flag, text in (("-d_list", "corpus list directory"), ("-d_wav", "wav file directory (input)"),
+                       ("-d_feature", "feature file directory (output)"), ("-config", "config file")):
+        ap.add_argument(flag, help=text, required=True)
+    ns = ap.parse_args(argv)
     rank, local_rank, world = shard.world()
-    if rank == 0:
-        print('** conv_wav2fe: convert wav to feature **')
-        print(' directory')
-        print('  wav     (input) : ' + str(args.d_wav))
-        print('  feature (output): ' + str(args.d_feature))
-        print('  corpus list     : ' + str(args.d_list))
-        print(' config file      : ' + str(args.config))
-
-    with open(args.config, 'r', encoding='utf-8') as f:
-        config = json.load(f)
     if world > 1:
         import torch
         torch.cuda.set_device(local_rank)
-
-    AMT = amt.AMT(config, None, None)
-    n_done = 0
-    for attribute in ['train', 'test', 'valid']:
-        path = args.d_list.rstrip('/') + '/' + str(attribute) + '.list'
-        if not os.path.isfile(path):
-            continue
-        if rank == 0:
-            print('-' + attribute + '-')
-        with open(path, 'r', encoding='utf-8') as f:
-            names = [l.rstrip('\n') for l in f.readlines() if l.strip()]
-        lo, hi = shard.partition(len(names), world, rank)
-        for fname in names[lo:hi]:
-            print(fname)
-            a_feature = AMT.wav2feature(args.d_wav.rstrip('/') + '/' + fname + '.wav')
-            with open(args.d_feature.rstrip('/') + '/' + fname + '.pkl', 'wb') as f:
-                pickle.dump(a_feature, f, protocol=4)
-            n_done += 1
+    config = json.loads(pathlib.Path(ns.config).read_text(encoding="utf-8"))
+    n = convert(ns.d_list, ns.d_wav, ns.d_feature, config, rank, world)
     if rank == 0:
-        print('** done **')
-    return n_done
+        print("conv_wav2fe: done (%d files on rank 0 of %d)" % (n, world))
+    return n
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     main()
