@@ -394,6 +394,7 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   gp.k_chunks = w.K / kBlockK;
   gp.bias = w.bias;
   gp.has_resid = (epi == EPI_LN && mr != nullptr) ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("HFT_TC_DEBUG"); dbg = e ? atoi(e) : 0; } gp.debug_flags = dbg; }
   if (epi == EPI_LN) HFT_REQUIRE(gp.n_tiles == 1, HFT_ERR_UNSUPPORTED, "tc gemm: LayerNorm epilogue needs the full row in one tile (N=%d)", w.N);
   // W stays resident when this CTA's slice fits beside a >= 3-deep A ring, the identity block and the store staging
   // (measured r01, bf16 K = 256: resident W + 3 A slots 573 ms/h vs streamed W 665 ms/h); otherwise W chunks stream

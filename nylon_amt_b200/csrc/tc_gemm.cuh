@@ -64,6 +64,7 @@ struct GemmParams {
   int n_vel;
   int time_major;         // rows are (b, note, frame): permute back to [B, frame, note]
   int n_frame, n_note;
+  int debug_flags;        // experiments only (HFT_TC_DEBUG): 1 = skip the TMA stores, 2 = skip the epilogue arithmetic
 };
 
 // n_rows_w: W rows staged per CTA (n_tile, or n_tile / 2 in PAIR mode)
@@ -287,7 +288,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(p.debug_flags & 1)) {
         tma_store_2d(&map_o, my_stage, col, row0);
         if (x3) tma_store_2d(&map_o, my_stage + kWarpStage, col + p.out_lo_off, row0);
         tma_store_commit();
