@@ -188,6 +188,22 @@ int hft_tc_attention(int bf16, int32_t dh, int32_t heads, const void* qkv16_dev,
                      float* probs_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Note decoding: the O(T x n_note) scans of AMT.mpe2note -- reference hftt_code/model/amt.py:179-344 (pure Python there).
+ * Activation maps are [T][n_note] fp32 row-major device arrays (what AMT.transcript returns, uploaded).  The host mirror
+ * (nylon_amt_b200/notes.py, mpe2note_device) compacts the flags and assembles the note dictionaries.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* flags_dev [n_note][T] (uint8): 1 where frame t is a peak of column p: a[t][p] >= thr and the first differing value on each side
+ * is lower (amt.py:196-212; all points of a plateau count). */
+int hft_note_peaks(const float* a_dev, int64_t T, int32_t n_note, float thr, uint8_t* flags_dev, void* stream);
+/* For n peaks idx_dev[n][2] = (pitch, frame): kind[i] = 1 and t32[i] = sub-frame peak time (amt.py:213-222, float32 arithmetic of
+ * numpy >= 2) when the two direct neighbours differ, else kind[i] = 0 (the time is frame * hop_sec). */
+int hft_note_peak_times(const float* a_dev, int64_t T, int32_t n_note, const int64_t* idx_dev, int64_t n, double hop_sec, uint8_t* kind_dev,
+                        float* t32_dev, void* stream);
+/* out[i] = first frame f in (frame_i, limit_i) with mpe[f][pitch_i] < thr, or -1 (amt.py:262-271). */
+int hft_note_first_below(const float* mpe_dev, int64_t T, int32_t n_note, const int64_t* idx_dev, const int64_t* limit_dev, int64_t n, float thr,
+                         int64_t* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Training step (BASELINE config 5: reduced hFT, batch 8 per GPU, Adam lr 1e-4, data parallel).
  * Replaces: the body of train() -- reference hftt_code/training/train.py:89-160 (model(input) in train mode, BCELoss on
  *           the six sigmoid outputs + CrossEntropyLoss on the two velocity logit tensors, loss = weight_A * loss_A +

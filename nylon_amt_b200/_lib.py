@@ -37,6 +37,11 @@ SYMBOLS = {
     "hft_resample_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "hft_resample_num_samples": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64]),
     "hft_resample_mono_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "hft_note_peaks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_note_peak_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_note_first_below": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "hft_model_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(hft_dims)]),
     "hft_model_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "hft_model_num_weights": (ctypes.c_int, [ctypes.c_void_p]),

@@ -297,9 +297,13 @@ class AMT():
     # ---- note decoding (host, amt.py:179-344) ---------------------------------------------------------------
     def mpe2note(self, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, thred_onset=0.5, thred_offset=0.5, thred_mpe=0.5,
                  mode_velocity='ignore_zero', mode_offset='shorter'):
-        from .notes import mpe2note as _mpe2note
-        return _mpe2note(self.config, a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe, mode_velocity,
-                         mode_offset)
+        from . import notes
+        # long transcripts: the O(T x 88) scans run on the device (hft_note_*), the result is identical to the host restructuring
+        n_cells = int(np.asarray(a_onset).shape[0]) * int(np.asarray(a_onset).shape[1]) if a_onset is not None else 0
+        if n_cells >= (1 << 20) and torch.cuda.is_available():
+            return notes.mpe2note_device(self.config, a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe, mode_velocity, mode_offset)
+        return notes.mpe2note(self.config, a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe, mode_velocity,
+                              mode_offset)
 
     def note2midi(self, a_note, f_midi):
         """amt.py:347-355 (file output; needs pretty_midi like the reference)."""

@@ -113,3 +113,92 @@ def mpe2note(config, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, t
                 a_note[-2]['offset'] = a_note[-1]['onset']
     a_note = sorted(sorted(a_note, key=lambda x: x['pitch']), key=lambda x: x['onset'])
     return a_note
+
+
+# ---- device-assisted variant ---------------------------------------------------------------------------------------------
+def _peaks_device(a_dev, thr, hop_sec):
+    """Peaks of every pitch column of a device map [T, N]: (pitch int64[n], loc int64[n], time float64[n]) sorted by (pitch, loc)."""
+    import ctypes
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    T, N = a_dev.shape
+    flags = torch.empty((N, T), dtype=torch.uint8, device=a_dev.device)
+    stream = torch.cuda.current_stream(a_dev.device).cuda_stream
+    _lib.check(L.hft_note_peaks(ctypes.c_void_p(a_dev.data_ptr()), T, N, float(thr), ctypes.c_void_p(flags.data_ptr()), ctypes.c_void_p(stream)), "hft_note_peaks")
+    idx = torch.nonzero(flags).contiguous()                    # [n, 2] int64, row-major order = sorted by (pitch, frame)
+    n = idx.shape[0]
+    kind = torch.empty(n, dtype=torch.uint8, device=a_dev.device)
+    t32 = torch.empty(n, dtype=torch.float32, device=a_dev.device)
+    _lib.check(L.hft_note_peak_times(ctypes.c_void_p(a_dev.data_ptr()), T, N, ctypes.c_void_p(idx.data_ptr()), n, float(hop_sec),
+                                     ctypes.c_void_p(kind.data_ptr()), ctypes.c_void_p(t32.data_ptr()), ctypes.c_void_p(stream)), "hft_note_peak_times")
+    idx_h = idx.cpu().numpy()
+    pitch, loc = idx_h[:, 0], idx_h[:, 1]
+    time = np.where(kind.cpu().numpy() == 1, t32.cpu().numpy().astype(np.float64), loc * hop_sec)
+    return idx, pitch, loc, time
+
+
+def mpe2note_device(config, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, thred_onset=0.5, thred_offset=0.5, thred_mpe=0.5,
+                    mode_velocity='ignore_zero', mode_offset='shorter', device='cuda'):
+    """Same result as mpe2note (and as the reference, amt.py:179-344), with the scans over the [T, n_note] maps done by
+    libhft_sm100 (hft_note_peaks / hft_note_peak_times / hft_note_first_below) and the note assembly vectorised over the detected onsets."""
+    import ctypes
+    import torch
+    from . import _lib
+    hop_sec = float(config['feature']['hop_sample'] / config['feature']['sr'])
+    note_min = config['midi']['note_min']
+    dev = torch.device(device)
+    on = torch.as_tensor(np.ascontiguousarray(a_onset, dtype=np.float32)).to(dev)
+    off = torch.as_tensor(np.ascontiguousarray(a_offset, dtype=np.float32)).to(dev)
+    mpe = torch.as_tensor(np.ascontiguousarray(a_mpe, dtype=np.float32)).to(dev)
+    a_velocity = np.asarray(a_velocity)
+    T, N = on.shape
+    n_frames_mpe = mpe.shape[0]
+    with torch.cuda.device(dev):
+        idx_on, p_on, l_on, t_on = _peaks_device(on, thred_onset, hop_sec)
+        _, p_off, l_off, t_off = _peaks_device(off, thred_offset, hop_sec)
+        m = p_on.shape[0]
+        if m == 0:
+            return []
+        # next onset of the same pitch (amt.py:262-268)
+        has_next = np.zeros(m, bool)
+        has_next[:-1] = p_on[1:] == p_on[:-1]
+        loc_next = np.where(has_next, np.roll(l_on, -1), n_frames_mpe)
+        time_next = np.where(has_next, np.roll(t_on, -1), (n_frames_mpe - 1) * hop_sec)
+        limit = torch.from_numpy(np.ascontiguousarray(loc_next.astype(np.int64))).to(dev)
+        below = torch.empty(m, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().hft_note_first_below(ctypes.c_void_p(mpe.data_ptr()), n_frames_mpe, N, ctypes.c_void_p(idx_on.data_ptr()), ctypes.c_void_p(limit.data_ptr()),
+                                                   m, float(thred_mpe), ctypes.c_void_p(below.data_ptr()), ctypes.c_void_p(stream)), "hft_note_first_below")
+        below = below.cpu().numpy()
+    # first offset peak strictly after the onset, same pitch (amt.py:274-283): search on the combined (pitch, frame) key
+    stride = max(T, n_frames_mpe) + 2
+    key_off = p_off * stride + l_off
+    k = np.searchsorted(key_off, p_on * stride + l_on, side='right')
+    kc = np.minimum(k, max(key_off.shape[0] - 1, 0))
+    flag_offset = (k < key_off.shape[0]) & ((p_off[kc] if key_off.shape[0] else np.zeros(m, np.int64)) == p_on) if key_off.shape[0] else np.zeros(m, bool)
+    loc_offset = np.where(flag_offset, l_off[kc] if key_off.shape[0] else 0, l_on + 1)
+    time_offset = np.where(flag_offset, t_off[kc] if key_off.shape[0] else 0.0, 0.0)
+    clip = loc_offset > loc_next
+    loc_offset = np.where(clip, loc_next, loc_offset)
+    time_offset = np.where(clip, time_next, time_offset)
+    flag_mpe = below >= 0
+    loc_mpe = np.where(flag_mpe, below, l_on + 1)
+    time_mpe = np.where(flag_mpe, loc_mpe * hop_sec, 0.0)
+    if mode_offset == 'offset':
+        both = time_offset
+    elif mode_offset == 'longer':
+        both = np.where(loc_offset >= loc_mpe, time_offset, time_mpe)
+    else:
+        both = np.where(loc_offset <= loc_mpe, time_offset, time_mpe)
+    offset_value = np.where(~flag_offset & ~flag_mpe, time_next, np.where(flag_offset & ~flag_mpe, time_offset, np.where(~flag_offset & flag_mpe, time_mpe, both)))
+    velocity = a_velocity[l_on, p_on].astype(np.int64)
+    keep = np.ones(m, bool) if mode_velocity != 'ignore_zero' else velocity > 0
+    p_k, on_k, off_k, v_k = p_on[keep], t_on[keep].astype(np.float64), offset_value[keep].astype(np.float64), velocity[keep]
+    # overlapping notes of the same pitch are cut at the next (kept) onset (amt.py:336-339)
+    if p_k.shape[0] > 1:
+        same = p_k[1:] == p_k[:-1]
+        cut = same & (on_k[1:] < off_k[:-1])
+        off_k[:-1] = np.where(cut, on_k[1:], off_k[:-1])
+    order = np.argsort(on_k, kind='stable')                     # sorted by pitch already; stable sort by onset = the reference's double sort
+    return [{'pitch': int(p_k[i] + note_min), 'onset': float(on_k[i]), 'offset': float(off_k[i]), 'velocity': int(v_k[i])} for i in order]
