@@ -154,6 +154,25 @@ def run_logmel(args, hft, _lib, L, dev, dist, rank, world):
     audio_s = n_clips * clip / 16000.0
     pk = peaks()
     gbs = n_clips * T * LOGMEL_BYTES_PER_FRAME / ms / 1e6
+    # what a user of the reference gets on this GPU today: the reference's own torchaudio MelSpectrogram + log (cuFFT + dense mel matmul),
+    # same clips, eager PyTorch on the device.  A library path, timed outside our timed region, reported beside it.
+    lib_ms = None
+    try:
+        import torchaudio
+        f = cfg["feature"]
+        tr = torchaudio.transforms.MelSpectrogram(sample_rate=f["sr"], n_fft=f["fft_bins"], win_length=f["window_length"], hop_length=f["hop_sample"],
+                                                  pad_mode=f["pad_mode"], n_mels=f["mel_bins"], norm="slaney").to(dev)
+        n_lib = min(n_clips, 24)                      # 2 h of audio per pass is plenty for a stable time
+        w2 = wav[: n_lib * clip].view(n_lib, clip)
+
+        def lib_step():
+            return torch.log(tr(w2) + f["log_offset"]).transpose(1, 2)
+
+        for _ in range(2):
+            lib_step()
+        lib_ms = _timed(lib_step, 3, dev, None, stream) / 3 * (n_clips / n_lib)
+    except Exception as e:                            # torchaudio missing on the box: report nothing rather than guess
+        lib_ms = None
     if rank == 0:
         print(json.dumps({"metric": "audio-sec/sec log-mel feature extraction", "value": world * audio_s / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -165,6 +184,8 @@ def run_logmel(args, hft, _lib, L, dev, dist, rank, world):
                           "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                                        "traffic": None, "peak_source": pk["src"], "algorithmic_bytes_per_frame": LOGMEL_BYTES_PER_FRAME,
                                        "note": "compute-bound kernel: ~2.6 k warp instructions per frame (fp32 FFT), see DESIGN.md 5"},
+                          "torchaudio_gpu": None if lib_ms is None else {"ms_per_step_equiv": lib_ms, "value": world * audio_s / (lib_ms / 1e3), "unit": "audio-s/s",
+                                                                         "what": "reference's torchaudio MelSpectrogram + log in eager PyTorch on the same GPU (cuFFT + dense mel matmul), scaled from a 2 h sample"},
                           "cpu_baseline": None}))
     return 0
 
