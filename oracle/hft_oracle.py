@@ -41,8 +41,10 @@ def dims_from_state_dict(sd):
 
 class Oracle:
     def __init__(self, state_dict, n_heads, n_margin=32, n_frame=128, n_bin=256, n_note=88, n_velocity=128,
-                 gemm_in=None, store=None, dtype=torch.float32):
-        self.sd = {k: v.detach().to("cpu", dtype) for k, v in state_dict.items()}
+                 gemm_in=None, store=None, dtype=torch.float32, device="cpu"):
+        # device: "cpu" (the oracle proper) or a CUDA device for bench.py's "eager PyTorch on the same GPU" baseline leg
+        self.device = torch.device(device)
+        self.sd = {k: v.detach().to(self.device, dtype) for k, v in state_dict.items()}
         self.h = n_heads
         self.n_margin, self.n_frame, self.n_bin = n_margin, n_frame, n_bin
         self.n_note, self.n_velocity = n_note, n_velocity
@@ -144,7 +146,7 @@ class Oracle:
     @torch.no_grad()
     def forward(self, spec):
         """spec [B, n_bin, margin+n_frame+margin] -> the reference's 9-tuple (model_spec2midi.py:35)."""
-        spec = torch.as_tensor(spec, dtype=self.dtype)
+        spec = torch.as_tensor(spec, dtype=self.dtype).to(self.device)
         return self.decoder(self.encoder(spec), spec.shape[0])
 
     __call__ = forward
