@@ -71,3 +71,39 @@ def test_full_hour_speed_and_identity():
     assert got == ref and len(ref) > 15000
     print("mpe2note 1 h: device-assisted %.2f s, host %.2f s" % (t_dev, t_host))
     assert t_dev < t_host
+
+
+def test_m_inference_driver_end_to_end(golden_dir, tmp_path):
+    """The evaluation driver (reference hftt_code/evaluation/m_inference.py, same flags and files): pickled model -> wav -> feature ->
+    activation maps -> note json, all through the B200 path; the notes equal AMT.mpe2note on the maps it wrote."""
+    import pickle
+    import wave as _wave
+    import torch
+    from nylon_amt_b200 import m_inference
+    g = np.load(os.path.join(golden_dir, "hft_reduced.npz"))
+    t = np.load(os.path.join(golden_dir, "transcript_reduced.npz"))
+    model = hft.build_model(CFG, 64, 128, 2, 2, device="cpu")
+    model.load_state_dict({k[2:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("w:")})
+    dirs = {k: tmp_path / k for k in ("cp", "wav", "fe", "mpe", "note")}
+    for d in dirs.values():
+        d.mkdir()
+    with open(dirs["cp"] / "best_model.pkl", "wb") as f:
+        pickle.dump(model, f)
+    pcm = t["pcm"].astype("<i2")
+    with _wave.open(str(dirs["wav"] / "clip.wav"), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+    (tmp_path / "test.list").write_text("clip\n")
+    (tmp_path / "config.json").write_text(json.dumps(CFG))
+    n = m_inference.main(["-f_config", str(tmp_path / "config.json"), "-f_list", str(tmp_path / "test.list"), "-d_cp", str(dirs["cp"]), "-d_wav", str(dirs["wav"]),
+                          "-d_fe", str(dirs["fe"]), "-d_mpe", str(dirs["mpe"]), "-d_note", str(dirs["note"]), "-calc_feature", "-calc_transcript"])
+    assert n == 1
+    with open(dirs["mpe"] / "clip_2nd.onset", "rb") as f:
+        on = pickle.load(f)
+    assert on.dtype == np.float32 and on.shape[1] == 88
+    maps = []
+    for head in ("onset", "offset", "mpe", "velocity"):
+        with open(dirs["mpe"] / ("clip_2nd." + head), "rb") as f:
+            maps.append(pickle.load(f))
+    written = json.loads((dirs["note"] / "clip_2nd.json").read_text())
+    assert written == notes.mpe2note(CFG, *maps)
+    assert (dirs["note"] / "clip_1st.json").is_file() and (dirs["fe"] / "clip.pkl").is_file()
