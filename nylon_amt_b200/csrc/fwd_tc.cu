@@ -517,6 +517,39 @@ static bool attn2_enabled() {
   return v == 1;
 }
 
+// Probabilities-returning attention (tc_attn2.cuh, attn_probs_kernel): persistent single-warpgroup kernel for Lq <= 128, Lk = 256, dh = 64
+template <bool BF16, bool X3>
+static int launch_attn_probs_t(const CUtensorMap& mq, const CUtensorMap& mkv, const Attn2Params& ap, cudaStream_t s) {
+  auto kern = attn_probs_kernel<BF16, X3>;
+  static bool attr_set = false;
+  if (!attr_set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnProbsSmem<X3>::total)); attr_set = true; }
+  static int sms = num_sms();
+  const int grid = ap.n_items < sms ? ap.n_items : sms;
+  kern<<<grid, kAttnProbsThreads, AttnProbsSmem<X3>::total, s>>>(mq, mkv, ap);
+  return HFT_OK;
+}
+// mkv256: K/V tensor map with box dh x 256
+static int launch_attn_probs(int heads, bool bf16, bool x3, const CUtensorMap& mq, const CUtensorMap& mkv256, const AttnParams& a, long long n_seq, cudaStream_t s) {
+  Attn2Params ap{};
+  ap.lq = a.lq; ap.lk = a.lk; ap.q_seq_rows = a.q_seq_rows; ap.q_tiles = 1; ap.heads = heads;
+  ap.q_col0 = a.q_col0; ap.k_col0 = a.k_col0; ap.v_col0 = a.v_col0;
+  ap.scale_log2e = 1.4426950408889634f / sqrtf(64.f);
+  ap.ctx = a.ctx; ap.ld_ctx = a.ld_ctx; ap.q_lo_off = a.q_lo_off; ap.kv_lo_off = a.kv_lo_off; ap.ctx_lo_off = a.ctx_lo_off;
+  ap.probs = a.probs;
+  const long long items = n_seq * heads;
+  HFT_REQUIRE(items < (1ll << 30) && a.lq <= 128 && a.lk == 256, HFT_ERR_UNSUPPORTED, "tc attention (probabilities): lq=%d lk=%d unsupported", a.lq, a.lk);
+  ap.n_items = (int)items;
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  if (x3) return launch_attn_probs_t<false, true>(mq, mkv256, ap, s);
+  return bf16 ? launch_attn_probs_t<true, false>(mq, mkv256, ap, s) : launch_attn_probs_t<false, false>(mq, mkv256, ap, s);
+}
+// HFT_TC_ATTN_PROBS=0 keeps the one-tile-per-CTA kernel for the probabilities-returning attention
+static bool attn_probs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_ATTN_PROBS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // The probabilities-returning cross-attention: the pipelined kernel has a PROBS variant (un-normalised rows written during the
 // softmax pass, rescaled in place by the same thread), but its row-per-lane global accesses make it slower than the
 // one-tile-per-CTA kernel (measured r01: attention 433 -> 447 ms per hour), so it is opt-in: HFT_TC_ATTN2_PROBS=1.
@@ -546,6 +579,8 @@ static int attention(Model* m, TcState& t, cudaStream_t s, int LK, const CUtenso
   a.q_lo_off = q_width;            // hi-block width of the Q tensor (3H for fused QKV buffers, H for the pitch-query table)
   a.kv_lo_off = 3 * m->H;
   a.ctx = t.CTX; a.ld_ctx = m->H * t.cm(); a.ctx_lo_off = m->H;
+  if (m->dh == 64 && a.probs != nullptr && a.lq <= 128 && a.lk == 256 && LK == 256 && attn_probs_enabled() && !attn2_probs_enabled())
+    return launch_attn_probs(m->heads, t.bf16, t.x3, mq, mkv, a, n_seq, s);
   if (m->dh == 64 && attn2_enabled() && (a.probs == nullptr || attn2_probs_enabled())) return launch_attn2(m->heads, t.bf16, t.x3, LK, mq, mkv_unit, t.sCTX, a, n_seq, s);
   return launch_attn(m->heads, m->dh, t.bf16, t.x3, LK, mq, mkv, &t.mCTX, a, n_seq, s);
 }

@@ -392,5 +392,243 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Probabilities-returning attention (last decoder cross-attention, model_spec2midi.py:164-165, :360): Lq <= 128 queries against 256 keys.
+// The returned softmax needs the row maximum / sum over ALL keys before anything is written, so this variant keeps the whole 256-column
+// score row of a tile in TMEM (S/P 256 columns + O 64) and runs ONE softmax warpgroup; it is still persistent and pipelined (Q and the
+// K / V tiles of the next item are loaded behind the current item's softmax; the PV MMA overlaps the probability write-out, which
+// re-reads P = hi + lo from TMEM once the row sum is known).  Warps: 0 producer, 1 MMA, 2..5 softmax / epilogue (thread = query row).
+// ---------------------------------------------------------------------------------------------------------------------------------
+template <bool X3>
+struct AttnProbsSmem {
+  static constexpr int parts = X3 ? 2 : 1;
+  static constexpr int q_bytes = 128 * 64 * 2 * parts;
+  static constexpr int kv_part = 256 * 64 * 2;                    // one 256-key x 64 operand part
+  static constexpr int slot_bytes = kv_part * parts;
+  static constexpr int total = 1024 + q_bytes + 2 * slot_bytes + 256;
+};
+constexpr int kAttnProbsThreads = 64 + 128;
+
+template <bool BF16, bool X3>
+__global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                                                                         const __grid_constant__ Attn2Params p) {
+  using L = AttnProbsSmem<X3>;
+  constexpr int kParts = X3 ? 2 : 1;
+  constexpr int DH = 64, LK = 256;
+  constexpr uint32_t kAtom = 1024, kRowBytes = 128, kOCol = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_q = smem;
+  uint8_t* s_ring = s_q + L::q_bytes;                                   // [2][parts][256 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + 2 * L::slot_bytes);
+  uint64_t* ring_full = bars;          // [2]
+  uint64_t* ring_empty = bars + 2;     // [2]
+  uint64_t* q_full = bars + 4;
+  uint64_t* q_empty = bars + 5;
+  uint64_t* s_ready = bars + 6;
+  uint64_t* p_ready = bars + 7;        // 4 warp arrivals
+  uint64_t* p_done = bars + 8;         // 4 warp arrivals: the probability write-out has finished reading P
+  uint64_t* o_ready = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(s_ready, 1); mbar_init(p_ready, 4); mbar_init(p_done, 4); mbar_init(o_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0, qph = 0;
+      for (int tile = blockIdx.x; tile < p.n_items; tile += gridDim.x) {
+        const int head = tile % p.heads, seq = tile / p.heads;
+        mbar_wait(q_empty, qph ^ 1);
+        mbar_expect_tx(q_full, (uint32_t)L::q_bytes);
+#pragma unroll
+        for (int part = 0; part < kParts; ++part)
+          tma_load_2d(s_q + part * (128 * 64 * 2), &map_q, part * p.q_lo_off + p.q_col0 + head * DH, seq * p.q_seq_rows, q_full);
+        qph ^= 1;
+        for (int kv = 0; kv < 2; ++kv) {                                  // K, then V
+          mbar_wait(&ring_empty[slot], ph ^ 1);
+          mbar_expect_tx(&ring_full[slot], (uint32_t)L::slot_bytes);
+#pragma unroll
+          for (int part = 0; part < kParts; ++part)
+            tma_load_2d(s_ring + (size_t)slot * L::slot_bytes + part * L::kv_part, &map_kv, part * p.kv_lo_off + (kv ? p.v_col0 : p.k_col0) + head * DH, seq * p.lk,
+                        &ring_full[slot]);
+          if (++slot == 2) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, LK, BF16, false, false);
+      const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);
+      int slot = 0;
+      uint32_t ph = 0, qph = 0, pph = 0, dph = 0;
+      auto take = [&]() -> int {
+        mbar_wait(&ring_full[slot], ph);
+        fence_after_sync();
+        const int s = slot;
+        if (++slot == 2) { slot = 0; ph ^= 1; }
+        return s;
+      };
+      for (int tile = blockIdx.x; tile < p.n_items; tile += gridDim.x) {
+        const int ks = take();
+        mbar_wait(q_full, qph); qph ^= 1;
+        mbar_wait(p_done, dph ^ 1); dph ^= 1;                             // the previous item's probabilities have been read out of P
+        fence_after_sync();
+        const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_ring + (size_t)ks * L::slot_bytes);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int part = 0; part < (X3 ? 3 : 1); ++part) {                 // S = Qh Kh + Ql Kh + Qh Kl
+          const uint32_t qp = qa + (part == 1 ? 128 * 64 * 2 : 0), kp = ka + (part == 2 ? L::kv_part : 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) {
+            umma_f16(tmem_base, make_sdesc(qp + k * 32, 16, kAtom, kSwz128), make_sdesc(kp + k * 32, 16, kAtom, kSwz128), idesc_s, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(s_ready);
+        umma_commit(q_empty);
+        umma_commit(&ring_empty[ks]);
+        const int vs = take();
+        mbar_wait(p_ready, pph); pph ^= 1;
+        fence_after_sync();
+        const uint32_t va = smem_u32(s_ring + (size_t)vs * L::slot_bytes);
+        acc = 0;
+#pragma unroll
+        for (int part = 0; part < (X3 ? 3 : 1); ++part) {                 // O = Ph Vh + Pl Vh + Ph Vl, A = P from TMEM
+          const uint32_t vp = va + (part == 2 ? L::kv_part : 0);
+#pragma unroll
+          for (int k = 0; k < LK / 16; ++k) {
+            const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
+            umma_f16_ts(tmem_base + kOCol, tmem_base + pcol, make_sdesc(vp + k * 16 * kRowBytes, kAtom, kAtom, kSwz128), idesc_o, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(o_ready);
+        umma_commit(&ring_empty[vs]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t sph = 0, oph = 0;
+    for (int tile = blockIdx.x; tile < p.n_items; tile += gridDim.x) {
+      const int head = tile % p.heads, seq = tile / p.heads;
+      const bool live = r < p.lq;
+      mbar_wait(s_ready, sph); sph ^= 1;
+      fence_after_sync();
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < LK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      const float ms = m * p.scale_log2e;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < LK / 32; ++c) {
+        uint32_t v[32], pw[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -ms));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -ms));
+          sum += e0 + e1;
+          if (X3) split_pack<BF16>(e0, e1, pw[j], pw[16 + j]);
+          else pw[j] = Op16<BF16>::pack(e0, e1);
+        }
+        if (X3) {
+          tmem_st32(t_row + c * 32, pw);
+        } else {
+          uint32_t ph16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ph16[j] = pw[j];
+          tmem_st16(t_row + c * 16, ph16);
+        }
+      }
+      tmem_st_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // probabilities: P = hi (+ lo) read back from TMEM, normalised, fp32 [n_seq, heads, lq, lk]
+      const float inv = 1.f / sum;
+      float* prow = p.probs + (((long long)seq * p.heads + head) * p.lq + (live ? r : 0)) * p.lk;
+#pragma unroll 1
+      for (int c = 0; c < LK / 32; ++c) {
+        float e[32];
+        if (X3) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            e[2 * j] = Op16<BF16>::lo(v[j]) + Op16<BF16>::lo(v[16 + j]);
+            e[2 * j + 1] = Op16<BF16>::hi(v[j]) + Op16<BF16>::hi(v[16 + j]);
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(t_row + (c >> 1) * 32, v);                           // 16 packed columns per 32 keys: chunk c sits in half (c & 1) of this load
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t w = (c & 1) ? v[16 + j] : v[j];
+            e[2 * j] = Op16<BF16>::lo(w);
+            e[2 * j + 1] = Op16<BF16>::hi(w);
+          }
+        }
+        if (live) {
+          float4* dst = reinterpret_cast<float4*>(prow + c * 32);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) dst[q4] = make_float4(e[4 * q4] * inv, e[4 * q4 + 1] * inv, e[4 * q4 + 2] * inv, e[4 * q4 + 3] * inv);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_done);
+      // context
+      mbar_wait(o_ready, oph); oph ^= 1;
+      fence_after_sync();
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(t_row + kOCol + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = __uint_as_float(o[2 * j]) * inv, b = __uint_as_float(o[2 * j + 1]) * inv;
+          if (X3) split_pack<BF16>(a, b, hi[c * 16 + j], lo[c * 16 + j]);
+          else hi[c * 16 + j] = Op16<BF16>::pack(a, b);
+        }
+      }
+      if (live) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.ctx) + ((long long)seq * p.lq + r) * p.ld_ctx + head * DH);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (X3) *reinterpret_cast<uint4*>(dst + p.ctx_lo_off / 2 + q * 4) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace tc
 }  // namespace hft
