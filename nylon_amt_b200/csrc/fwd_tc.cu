@@ -401,9 +401,13 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   // through a ring of their own.
   const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (gp.x3 ? 2 : 1);
   const size_t w_chunk = (size_t)n_rows_w * kBlockK * 2;
-  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * (gp.x3 ? 2 : 1) * kWarpStage + kConstBytes + 512;
+  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * kWarpStage + kConstBytes + 512;
   const size_t budget = 227 * 1024;
-  gp.w_resident = (w_bytes + fixed + 3 * kChunkA <= budget) ? 1 : 0;
+  static int wres = -1;                      // HFT_TC_WRES=0: never keep W resident (experiments)
+  if (wres < 0) { const char* e = getenv("HFT_TC_WRES"); wres = (e && e[0] == '0') ? 0 : 1; }
+  // split mode needs two A chunks (hi, lo) per k-chunk: below 4 slots the A stream starves (measured r01, pair K = 256: resident W +
+  // 3 A slots 1 284 ms/h of GEMM vs streamed W + 6 A / 4 W slots 1 193 ms/h); single-product modes are fine with 3 (573 vs 665 ms/h)
+  gp.w_resident = (wres && w_bytes + fixed + (gp.x3 ? 4 : 3) * kChunkA <= budget) ? 1 : 0;
   gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? 4 : 2);
   const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
   long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
