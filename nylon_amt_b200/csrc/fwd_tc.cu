@@ -408,7 +408,9 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   // split mode needs two A chunks (hi, lo) per k-chunk: below 4 slots the A stream starves (measured r01, pair K = 256: resident W +
   // 3 A slots 1 284 ms/h of GEMM vs streamed W + 6 A / 4 W slots 1 193 ms/h); single-product modes are fine with 3 (573 vs 665 ms/h)
   gp.w_resident = (wres && w_bytes + fixed + (gp.x3 ? 4 : 3) * kChunkA <= budget) ? 1 : 0;
-  gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? 4 : 2);
+  static int wst = -1;                       // HFT_TC_WSTAGES: W ring depth for 16 KB chunks (experiments; default 4)
+  if (wst < 0) { const char* e = getenv("HFT_TC_WSTAGES"); wst = e ? atoi(e) : 4; if (wst < 2 || wst > 8) wst = wst < 2 ? 2 : 8; }
+  gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? wst : 2);
   const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
   long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
   gp.a_stages = a_st > 8 ? 8 : (int)a_st;

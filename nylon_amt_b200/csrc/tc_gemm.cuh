@@ -95,12 +95,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_const) + kConstBytes);
   uint64_t* full_a = bars;               // [8]
   uint64_t* empty_a = bars + 8;          // [8]
-  uint64_t* full_w = bars + 16;          // [4]
-  uint64_t* empty_w = bars + 20;         // [4]
-  uint64_t* tfull = bars + 24;           // [2]
-  uint64_t* tempty = bars + 26;          // [2]
-  uint64_t* wbar = bars + 28;            // resident W landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  uint64_t* full_w = bars + 16;          // [8]
+  uint64_t* empty_w = bars + 24;         // [8]
+  uint64_t* tfull = bars + 32;           // [2]
+  uint64_t* tempty = bars + 34;          // [2]
+  uint64_t* wbar = bars + 36;            // resident W landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // persistent schedule: this CTA (pair) owns n-tile `nt` and walks m-tiles mt0, mt0 + m_step, ...
