@@ -9,6 +9,7 @@
 #include "tc_attn2.cuh"
 #include "tc_gemm.cuh"
 #include "tc_ffn.cuh"
+#include "tc_front.cuh"
 
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -43,6 +44,21 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HFT_REQUIRE(r == CUDA_SUCCESS, HFT_ERR_STATE, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows);
+  return HFT_OK;
+}
+
+// 3-D view [outer][mid][cols] of a row-major 16-bit tensor whose rows are (outer * mid_n + mid); box = 64 columns x 1 x 32 outer rows
+// (the front kernel's tile: 32 consecutive frames of one bin), 128-byte swizzle like the 2-D store boxes.
+static int make_map_front(CUtensorMap* m, const void* base, long long outer, long long mid_n, long long cols, long long ld, bool bf16) {
+  auto enc = get_encode();
+  HFT_REQUIRE(enc != nullptr, HFT_ERR_STATE, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)mid_n, (cuuint64_t)outer};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)mid_n};
+  cuuint32_t box[3] = {64, 1, 32};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HFT_REQUIRE(r == CUDA_SUCCESS, HFT_ERR_STATE, "cuTensorMapEncodeTiled (3-D front map) failed (%d)", (int)r);
   return HFT_OK;
 }
 
@@ -182,6 +198,7 @@ struct TcState {
   uint16_t* ws = nullptr;
   uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
   CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands / TMA-store targets, box 64 x 128
+  CUtensorMap sX3;                                  // X as [b * F + f][bin][column] for the front kernel's stores
   CUtensorMap sX, sHID, sT, sU, sQKV, sDQ, sCTX;    // TMA-store targets (projections, attention context), box 64 x 32 (one epilogue warp)
   CUtensorMap mPosRep;                              // repeated pitch-query table (residual of layer zero)
   uint16_t* pos_rep = nullptr;                      // [11*128, H]: pos_embedding_freq[row % 88] (lcm(88,128) = 1408 rows)
@@ -315,6 +332,7 @@ static int ensure_ws(Model* m, TcState& t, int B) {
   chk(make_map(&t.mDQ_kv, t.DQ, Rd, h3, h3, dh, 96, bf));
   chk(make_map(&t.mQ0, t.q0_16, 128, h1, h1, dh, 128, bf));
   chk(make_map(&t.sX, t.X, Re, h1, h1, 64, 32, bf));
+  chk(make_map_front(&t.sX3, t.X, Re / m->nbin, m->nbin, h1, h1, bf));
   chk(make_map(&t.sHID, t.HID, Re, p1, p1, 64, 32, bf));
   chk(make_map(&t.sT, t.T, Rd, h1, h1, 64, 32, bf));
   chk(make_map(&t.sU, t.U, Rd, h1, h1, 64, 32, bf));
@@ -695,7 +713,26 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   HFT_REQUIRE(m->nproc == 65, HFT_ERR_UNSUPPORTED, "front kernel is built for n_margin 32");
   {
     LaunchScope ls(HFT_KCLASS_FRONT, s);
-    if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
+    static int tc_front = -1;                       // HFT_TC_FRONT=0: the CUDA-core filter kernel (the only one for hid != 256)
+    if (tc_front < 0) { const char* e = getenv("HFT_TC_FRONT"); tc_front = (e && e[0] == '0') ? 0 : 1; }
+    if (tc_front && H == kFrontH && F == kFrontF) {
+      FrontParams fp{};
+      fp.spec = spec; fp.sb = sb; fp.sbin = sbin; fp.st = st;
+      fp.Wc = m->front_w; fp.bc = m->front_b; fp.pos = m->w[m->pos_freq];
+      fp.scale = sqrtH; fp.n_bin = NB; fp.n_tiles = B * NB; fp.x3 = t.x3 ? 1 : 0; fp.lo_off = H;
+      static int sms = num_sms();
+      const unsigned grid = (unsigned)(fp.n_tiles < sms ? fp.n_tiles : sms);
+      const size_t smem = sizeof(FrontSmem) + 1024;
+      if (bf) {
+        static bool set = false;
+        if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(front_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        front_tc_kernel<true><<<grid, kFrontThreads, smem, s>>>(t.sX3, fp);
+      } else {
+        static bool set = false;
+        if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(front_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        front_tc_kernel<false><<<grid, kFrontThreads, smem, s>>>(t.sX3, fp);
+      }
+    } else if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
     else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
   }
   for (size_t l = 0; l < m->enc.size(); ++l)
