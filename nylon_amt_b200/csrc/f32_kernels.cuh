@@ -233,6 +233,89 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__
   for (int c = 0; c < DH / 4; ++c) *reinterpret_cast<float4*>(op + c * 4) = make_float4(acc[c * 4], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
 }
 
+// Training forward (no probabilities returned): the broadcast reads of K / V rows from shared memory bound the kernel above
+// (one float delivered per warp and clock against four FMA issues), so here every thread owns TWO query rows -- each K / V
+// value read feeds both -- and the softmax is the one-pass online form (running max, rescale on a new max): K is read once.
+// Row log-sum-exp saved for the backward pass; dropout on the probabilities as above.
+template <int DH>
+__global__ void __launch_bounds__(128) attn_f32_r2_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
+                                                          const float* __restrict__ Vp, int ldkv, int Lq, int Lk, int heads, float inv_scale,
+                                                          float* __restrict__ ctx, int ldc, float* __restrict__ lse, Drop drop) {
+  extern __shared__ __align__(16) float smem_attn[];
+  float* sK = smem_attn;
+  float* sV = smem_attn + (size_t)Lk * DH;
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const float* kbase = Kp + (long long)seq * Lk * ldkv + head * DH;
+  const float* vbase = Vp + (long long)seq * Lk * ldkv + head * DH;
+  for (int i = threadIdx.x; i < Lk * (DH / 4); i += blockDim.x) {
+    int j = i / (DH / 4), c = i % (DH / 4);
+    reinterpret_cast<float4*>(sK)[i] = *reinterpret_cast<const float4*>(kbase + (long long)j * ldkv + c * 4);
+    reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(vbase + (long long)j * ldkv + c * 4);
+  }
+  __syncthreads();
+  const int r0 = 2 * threadIdx.x;
+  if (r0 >= Lq) return;
+  const bool two = r0 + 1 < Lq;
+  float q[2][DH], acc[2][DH];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float* qp = Q + (long long)seq * q_seq_stride + (long long)(r0 + (two ? u : 0)) * ldq + head * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      float4 t = *reinterpret_cast<const float4*>(qp + c * 4);
+      q[u][c * 4] = t.x * inv_scale; q[u][c * 4 + 1] = t.y * inv_scale; q[u][c * 4 + 2] = t.z * inv_scale; q[u][c * 4 + 3] = t.w * inv_scale;
+    }
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[u][c] = 0.f;
+  }
+  float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+  const long long pbase = (((long long)seq * heads + head) * Lq + r0) * Lk;
+  for (int j = 0; j < Lk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 t = kr[c];
+      s0 = fmaf(q[0][c * 4], t.x, s0); s0 = fmaf(q[0][c * 4 + 1], t.y, s0); s0 = fmaf(q[0][c * 4 + 2], t.z, s0); s0 = fmaf(q[0][c * 4 + 3], t.w, s0);
+      s1 = fmaf(q[1][c * 4], t.x, s1); s1 = fmaf(q[1][c * 4 + 1], t.y, s1); s1 = fmaf(q[1][c * 4 + 2], t.z, s1); s1 = fmaf(q[1][c * 4 + 3], t.w, s1);
+    }
+    float p[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float sv = u ? s1 : s0;
+      if (sv > mx[u]) {                                   // new running max: rescale what has been accumulated
+        const float f = expf(mx[u] - sv);
+        sum[u] *= f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[u][c] *= f;
+        mx[u] = sv;
+      }
+      p[u] = expf(sv - mx[u]);
+      sum[u] += p[u];
+      if (drop.thresh) p[u] = drop_keep(drop, (unsigned long long)(pbase + (long long)u * Lk + j)) ? p[u] * drop.scale : 0.f;
+    }
+    const float4* vr = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 t = vr[c];
+      acc[0][c * 4] = fmaf(p[0], t.x, acc[0][c * 4]); acc[0][c * 4 + 1] = fmaf(p[0], t.y, acc[0][c * 4 + 1]);
+      acc[0][c * 4 + 2] = fmaf(p[0], t.z, acc[0][c * 4 + 2]); acc[0][c * 4 + 3] = fmaf(p[0], t.w, acc[0][c * 4 + 3]);
+      acc[1][c * 4] = fmaf(p[1], t.x, acc[1][c * 4]); acc[1][c * 4 + 1] = fmaf(p[1], t.y, acc[1][c * 4 + 1]);
+      acc[1][c * 4 + 2] = fmaf(p[1], t.z, acc[1][c * 4 + 2]); acc[1][c * 4 + 3] = fmaf(p[1], t.w, acc[1][c * 4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (u == 1 && !two) break;
+    const float inv = 1.f / sum[u];
+    lse[((long long)seq * heads + head) * Lq + r0 + u] = mx[u] + logf(sum[u]);
+    float* op = ctx + ((long long)seq * Lq + r0 + u) * ldc + head * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c)
+      *reinterpret_cast<float4*>(op + c * 4) = make_float4(acc[u][c * 4] * inv, acc[u][c * 4 + 1] * inv, acc[u][c * 4 + 2] * inv, acc[u][c * 4 + 3] * inv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // y = LayerNorm(x + r) * g + b, eps 1e-5 (model_spec2midi.py:236,242: one LayerNorm module shared by the sites of
 // a layer).  One warp per row.  r is indexed by (row % r_rows) so the constant pitch queries can be broadcast.

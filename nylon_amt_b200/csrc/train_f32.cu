@@ -130,6 +130,12 @@ static void colsum(cudaStream_t s, const float* in, long long rows, long long co
   colsum_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)splits), 256, 0, s>>>(in, rows, cols, rps, out);
 }
 
+static bool attn_r2_enabled() {                    // HFT_TRAIN_ATTN_R2=0: the one-row-per-thread kernels
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TRAIN_ATTN_R2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
                     int Lq, int Lk, float* ctx, float* lse, Drop drop = Drop{0, 0, 0, 1.f}) {
   const int dh = m->dh;
@@ -142,6 +148,9 @@ static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long
   if (dh == 64) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
+  } else if (attn_r2_enabled()) {                    // two query rows per thread, one-pass softmax
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_r2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_f32_r2_kernel<32><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, lse, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
@@ -160,8 +169,14 @@ static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long lo
   const int t1 = (Lq + 31) / 32 * 32, t2 = (Lk + 31) / 32 * 32;
   HFT_REQUIRE(t1 <= 256 && t2 <= 256 && smem1 <= 200 * 1024 && smem2 <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention backward: Lq=%d Lk=%d", Lq, Lk);
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
-  HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
+  constexpr int DHR = DH <= 32 ? DH : 32;          // the two-row kernel exists for head_dim <= 32 only
+  if (DH <= 32 && attn_r2_enabled() && lddq % 4 == 0) {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_r2_kernel<DHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_bwd_dq_r2_kernel<DHR><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
+  } else {
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
+  }
   if (DH <= 32) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);

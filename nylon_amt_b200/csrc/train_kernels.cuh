@@ -255,6 +255,81 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restric
   Dout[((long long)seq * heads + head) * Lq + r] = D;
 }
 
+// Pass 1 with two query rows per thread (head_dim 32): every K / V value read from shared memory feeds both rows, which halves
+// the shared-memory read traffic that bounds the one-row kernel.
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_dq_r2_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
+                                                             const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, const float* __restrict__ O,
+                                                             int ldo, const float* __restrict__ lse, int Lq, int Lk, int heads, float c,
+                                                             float* __restrict__ dQ, int lddq, float* __restrict__ Dout, Drop drop) {
+  extern __shared__ __align__(16) float smem_bwd[];
+  float* sK = smem_bwd;
+  float* sV = smem_bwd + (size_t)Lk * DH;
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const float* kbase = Kp + (long long)seq * Lk * ldkv + head * DH;
+  const float* vbase = Vp + (long long)seq * Lk * ldkv + head * DH;
+  for (int i = threadIdx.x; i < Lk * (DH / 4); i += blockDim.x) {
+    int j = i / (DH / 4), cc = i % (DH / 4);
+    reinterpret_cast<float4*>(sK)[i] = *reinterpret_cast<const float4*>(kbase + (long long)j * ldkv + cc * 4);
+    reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(vbase + (long long)j * ldkv + cc * 4);
+  }
+  __syncthreads();
+  const int r0 = 2 * threadIdx.x;
+  if (r0 >= Lq) return;
+  const bool two = r0 + 1 < Lq;
+  float q[2][DH], go[2][DH], acc[2][DH];
+  float D[2] = {0.f, 0.f}, l[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int r = r0 + (two ? u : 0);
+    const float* qp = Q + (long long)seq * q_seq_stride + (long long)r * ldq + head * DH;
+    const float* gp = dO + ((long long)seq * Lq + r) * ldo + head * DH;
+    const float* op = O + ((long long)seq * Lq + r) * ldo + head * DH;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) { q[u][i] = qp[i]; go[u][i] = gp[i]; D[u] = fmaf(go[u][i], op[i], D[u]); acc[u][i] = 0.f; }
+    l[u] = lse[((long long)seq * heads + head) * Lq + r];
+  }
+  const long long pbase = (((long long)seq * heads + head) * Lq + r0) * Lk;
+  for (int j = 0; j < Lk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
+    const float4* vr = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
+    float s[2] = {0.f, 0.f}, dp[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DH / 4; ++i) {
+      const float4 k4 = kr[i], v4 = vr[i];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        s[u] = fmaf(q[u][4 * i], k4.x, s[u]); s[u] = fmaf(q[u][4 * i + 1], k4.y, s[u]); s[u] = fmaf(q[u][4 * i + 2], k4.z, s[u]); s[u] = fmaf(q[u][4 * i + 3], k4.w, s[u]);
+        dp[u] = fmaf(go[u][4 * i], v4.x, dp[u]); dp[u] = fmaf(go[u][4 * i + 1], v4.y, dp[u]);
+        dp[u] = fmaf(go[u][4 * i + 2], v4.z, dp[u]); dp[u] = fmaf(go[u][4 * i + 3], v4.w, dp[u]);
+      }
+    }
+    float ds[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (drop.thresh) dp[u] = drop_keep(drop, (unsigned long long)(pbase + (long long)u * Lk + j)) ? dp[u] * drop.scale : 0.f;
+      ds[u] = expf(s[u] * c - l[u]) * (dp[u] - D[u]) * c;
+    }
+#pragma unroll
+    for (int i = 0; i < DH / 4; ++i) {
+      const float4 k4 = kr[i];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        acc[u][4 * i] = fmaf(ds[u], k4.x, acc[u][4 * i]); acc[u][4 * i + 1] = fmaf(ds[u], k4.y, acc[u][4 * i + 1]);
+        acc[u][4 * i + 2] = fmaf(ds[u], k4.z, acc[u][4 * i + 2]); acc[u][4 * i + 3] = fmaf(ds[u], k4.w, acc[u][4 * i + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (u == 1 && !two) break;
+    float* out = dQ + ((long long)seq * Lq + r0 + u) * lddq + head * DH;
+#pragma unroll
+    for (int i = 0; i < DH / 4; ++i) *reinterpret_cast<float4*>(out + 4 * i) = make_float4(acc[u][4 * i], acc[u][4 * i + 1], acc[u][4 * i + 2], acc[u][4 * i + 3]);
+    Dout[((long long)seq * heads + head) * Lq + r0 + u] = D[u];
+  }
+}
+
 // MODE 0: dK and dV, 1: dK only, 2: dV only (head_dim 64 needs two passes to stay inside the register file)
 template <int DH, int MODE>
 __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
