@@ -92,9 +92,12 @@ static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int 
 static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, long long M, int N, int K) {
   HFT_REQUIRE(ldy % 4 == 0 && ldx % 4 == 0, HFT_ERR_UNSUPPORTED, "train dw gemm: ldy=%d ldx=%d", ldy, ldx);
   const int gx = (N + DWT - 1) / DWT, gy = (K + DWT - 1) / DWT;
-  long long splits = (M + 2047) / 2048;
-  const long long cap = 2048 / (gx * gy) > 1 ? 2048 / (gx * gy) : 1;      // bound the number of atomic waves
-  if (splits > cap) splits = cap;
+  // split M so that the grid fills the chip four CTAs deep (the tile count gx * gy is 1..6 for this model: without the split
+  // a [64 x 64] dW ran on 44..128 of the 148 SMs); every split ends in one wave of fp32 atomics on dW
+  static const int sms = num_sms();
+  long long splits = (4LL * sms + gx * gy - 1) / (gx * gy);
+  if (splits > (M + 63) / 64) splits = (M + 63) / 64;
+  if (splits < 1) splits = 1;
   long long rps = ((M + splits - 1) / splits + DWR - 1) / DWR * DWR;
   splits = (M + rps - 1) / rps;
   LaunchScope ls(HFT_KCLASS_GEMM, s);

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
 // grid (ceil(N/64), ceil(K/64), splits): every CTA reduces its slice of the M rows into a 64 x 64 tile held in registers
 // (4 x 4 per thread) and adds it to dW with fp32 atomics.  N, K arbitrary (guards); ldy % 4 == 0 and ldx % 4 == 0.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DWT = 64, DWR = 16;
+constexpr int DWT = 64, DWR = 32;
 __global__ void __launch_bounds__(256) dw_gemm_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW,
                                                       int ldw, float* __restrict__ db, long long M, int N, int K, long long rows_per_split) {
   __shared__ __align__(16) float Ys[DWR][DWT];
@@ -102,18 +102,21 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long long m = m_begin; m < m_end; m += DWR) {
-    const long long row = m + lr;
-    float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
-    if (row < m_end) {
-      const float* yp = dY + row * ldy + n0 + lc;
-      const float* xp = X + row * ldx + k0 + lc;
-      if (n0 + lc + 3 < N) y = *reinterpret_cast<const float4*>(yp);
-      else { if (n0 + lc < N) y.x = yp[0]; if (n0 + lc + 1 < N) y.y = yp[1]; if (n0 + lc + 2 < N) y.z = yp[2]; }
-      if (k0 + lc + 3 < K) x = *reinterpret_cast<const float4*>(xp);
-      else { if (k0 + lc < K) x.x = xp[0]; if (k0 + lc + 1 < K) x.y = xp[1]; if (k0 + lc + 2 < K) x.z = xp[2]; }
+#pragma unroll
+    for (int h = 0; h < DWR / 16; ++h) {
+      const long long row = m + lr + 16 * h;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
+      if (row < m_end) {
+        const float* yp = dY + row * ldy + n0 + lc;
+        const float* xp = X + row * ldx + k0 + lc;
+        if (n0 + lc + 3 < N) y = *reinterpret_cast<const float4*>(yp);
+        else { if (n0 + lc < N) y.x = yp[0]; if (n0 + lc + 1 < N) y.y = yp[1]; if (n0 + lc + 2 < N) y.z = yp[2]; }
+        if (k0 + lc + 3 < K) x = *reinterpret_cast<const float4*>(xp);
+        else { if (k0 + lc < K) x.x = xp[0]; if (k0 + lc + 1 < K) x.y = xp[1]; if (k0 + lc + 2 < K) x.z = xp[2]; }
+      }
+      *reinterpret_cast<float4*>(&Ys[lr + 16 * h][lc]) = y;
+      *reinterpret_cast<float4*>(&Xs[lr + 16 * h][lc]) = x;
     }
-    *reinterpret_cast<float4*>(&Ys[lr][lc]) = y;
-    *reinterpret_cast<float4*>(&Xs[lr][lc]) = x;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < DWR; ++r) {
