@@ -139,18 +139,31 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
     }
     __syncthreads();
   }
+  const bool vec = (ldc & 3) == 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-      if (col >= N) continue;
-      float v = acc[i][j] + (bias ? bias[col] : 0.f);
-      if (RELU) v = fmaxf(v, 0.f);
-      if (accum) v += C[(long long)row * ldc + col];
-      C[(long long)row * ldc + col] = v;
+    for (int g = 0; g < NJ / 4; ++g) {
+      const int col0 = n0 + g * 64 + tx * 4;
+      float v[4] = {acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]};
+      float* cp = C + (long long)row * ldc + col0;
+      if (vec && col0 + 3 < N) {                      // four consecutive columns: 16-byte accesses
+        if (bias) { v[0] += bias[col0]; v[1] += bias[col0 + 1]; v[2] += bias[col0 + 2]; v[3] += bias[col0 + 3]; }
+        if (RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+        if (accum) { const float4 c4 = *reinterpret_cast<const float4*>(cp); v[0] += c4.x; v[1] += c4.y; v[2] += c4.z; v[3] += c4.w; }
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (col0 + j >= N) continue;
+          float w = v[j] + (bias ? bias[col0 + j] : 0.f);
+          if (RELU) w = fmaxf(w, 0.f);
+          if (accum) w += cp[j];
+          cp[j] = w;
+        }
+      }
     }
   }
 }

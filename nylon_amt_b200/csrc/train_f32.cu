@@ -92,16 +92,18 @@ static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int 
 static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, long long M, int N, int K) {
   HFT_REQUIRE(ldy % 4 == 0 && ldx % 4 == 0, HFT_ERR_UNSUPPORTED, "train dw gemm: ldy=%d ldx=%d", ldy, ldx);
   const int gx = (N + DWT - 1) / DWT, gy = (K + DWT - 1) / DWT;
-  // split M so that the grid fills the chip four CTAs deep (the tile count gx * gy is 1..6 for this model: without the split
-  // a [64 x 64] dW ran on 44..128 of the 148 SMs); every split ends in one wave of fp32 atomics on dW
+  // split M so that the grid fills the chip two (256-thread, 128-register) CTAs deep (the tile count gx * gy is 1..6 for this model: without the split a
+  // [64 x 64] dW ran on 44..128 of the 148 SMs), with at least four stages per CTA so the closing atomics stay the minor part
   static const int sms = num_sms();
-  long long splits = (4LL * sms + gx * gy - 1) / (gx * gy);
-  if (splits > (M + 63) / 64) splits = (M + 63) / 64;
+  long long splits = (2LL * sms + gx * gy - 1) / (gx * gy);
+  if (splits > (M + 4 * DWR - 1) / (4 * DWR)) splits = (M + 4 * DWR - 1) / (4 * DWR);
   if (splits < 1) splits = 1;
   long long rps = ((M + splits - 1) / splits + DWR - 1) / DWR * DWR;
   splits = (M + rps - 1) / rps;
+  static bool set = false;
+  if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM)); set = true; }
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), 256, 0, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
+  dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), DWTHREADS, DW_SMEM, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
   return HFT_OK;
 }
 static void ln_fwd(Model* m, cudaStream_t s, const float* x, const float* r, long long r_rows, const LnW& ln, long long rows, float* y, float* sum_out,

@@ -64,81 +64,145 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
     }
     __syncthreads();
   }
+  const bool vec = (ldc & 3) == 0 && (!mask || (ldm & 3) == 0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-      if (col >= N) continue;
-      float v = acc[i][j];
-      if (mask) v = (mask[(long long)row * ldm + col] > 0.f) ? v * mask_scale : 0.f;
-      if (accum) v += C[(long long)row * ldc + col];
-      C[(long long)row * ldc + col] = v;
+    for (int g = 0; g < NJ / 4; ++g) {
+      const int col0 = n0 + g * 64 + tx * 4;
+      float v[4] = {acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]};
+      float* cp = C + (long long)row * ldc + col0;
+      if (vec && col0 + 3 < N) {                      // four consecutive columns: 16-byte accesses
+        if (mask) {
+          const float4 mk = *reinterpret_cast<const float4*>(mask + (long long)row * ldm + col0);
+          v[0] = mk.x > 0.f ? v[0] * mask_scale : 0.f; v[1] = mk.y > 0.f ? v[1] * mask_scale : 0.f;
+          v[2] = mk.z > 0.f ? v[2] * mask_scale : 0.f; v[3] = mk.w > 0.f ? v[3] * mask_scale : 0.f;
+        }
+        if (accum) { const float4 c4 = *reinterpret_cast<const float4*>(cp); v[0] += c4.x; v[1] += c4.y; v[2] += c4.z; v[3] += c4.w; }
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (col0 + j >= N) continue;
+          float w = v[j];
+          if (mask) w = (mask[(long long)row * ldm + col0 + j] > 0.f) ? w * mask_scale : 0.f;
+          if (accum) w += cp[j];
+          cp[j] = w;
+        }
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // dW[N,K] += dY[M,N]^T * X[M,K],  db[N] += colsum(dY)      (weight gradient of y = x W^T + b)
-// grid (ceil(N/64), ceil(K/64), splits): every CTA reduces its slice of the M rows into a 64 x 64 tile held in registers
-// (4 x 4 per thread) and adds it to dW with fp32 atomics.  N, K arbitrary (guards); ldy % 4 == 0 and ldx % 4 == 0.
+// grid (ceil(N/64), ceil(K/64), splits): every CTA reduces its slice of the M rows into a 64 x 64 tile.  256 threads = four
+// row groups of 64 threads; a group owns every fourth 16-row slab of the stage and holds the whole tile as 8 x 8 per thread
+// (64 FMAs per four 16-byte shared-memory reads).  Stages of 64 rows arrive through cp.async, double-buffered; at the end the
+// four groups' tiles are summed through shared memory and ONE set of fp32 atomics per CTA goes to dW (the M split is what
+// fills the chip -- dW itself is only 1..6 tiles -- so the atomics are the serial part and are kept four times rarer than
+// the accumulating threads).  N, K arbitrary (guards); ldy % 4 == 0 and ldx % 4 == 0.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DWT = 64, DWR = 32;
-__global__ void __launch_bounds__(256) dw_gemm_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW,
-                                                      int ldw, float* __restrict__ db, long long M, int N, int K, long long rows_per_split) {
-  __shared__ __align__(16) float Ys[DWR][DWT];
-  __shared__ __align__(16) float Xs[DWR][DWT];
+constexpr int DWT = 64, DWR = 64, DWTHREADS = 256;
+constexpr int DW_SMEM = 2 * 2 * DWR * DWT * 4;            // two stages x (dY | X) x 64 rows x 64 floats = 64 KB
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(DWTHREADS, 2) dw_gemm_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW,
+                                                            int ldw, float* __restrict__ db, long long M, int N, int K, long long rows_per_split) {
+  extern __shared__ __align__(16) float dw_smem[];
+  auto Ys = [&](int buf, int r) { return dw_smem + ((size_t)(buf * 2) * DWR + r) * DWT; };
+  auto Xs = [&](int buf, int r) { return dw_smem + ((size_t)(buf * 2 + 1) * DWR + r) * DWT; };
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * DWT, k0 = blockIdx.y * DWT;
   const long long m_begin = (long long)blockIdx.z * rows_per_split;
   const long long m_end = (m_begin + rows_per_split < M) ? m_begin + rows_per_split : M;
-  const int lr = tid >> 4, lc = (tid & 15) * 4;           // loader: row 0..15, 4 columns
-  const int tn = tid >> 4, tk = tid & 15;                 // compute: n = tn*4.., k = tk*4..
-  float acc[4][4], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int lr = tid >> 4, lc = (tid & 15) * 4;           // loader: rows lr + 16 h, 4 columns
+  const int grp = tid >> 6, t64 = tid & 63;
+  const int tn = t64 >> 3, tk = t64 & 7;                  // compute: n = tn*4.. and 32 + tn*4.., k = tk*4.. and 32 + tk*4..
+  const bool y_full = n0 + lc + 3 < N, x_full = k0 + lc + 3 < K;
+  float acc[8][8], bsum[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
+    bsum[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long m = m_begin; m < m_end; m += DWR) {
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+  auto load_stage = [&](int buf, long long m) {
 #pragma unroll
     for (int h = 0; h < DWR / 16; ++h) {
       const long long row = m + lr + 16 * h;
-      float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
-      if (row < m_end) {
-        const float* yp = dY + row * ldy + n0 + lc;
-        const float* xp = X + row * ldx + k0 + lc;
-        if (n0 + lc + 3 < N) y = *reinterpret_cast<const float4*>(yp);
-        else { if (n0 + lc < N) y.x = yp[0]; if (n0 + lc + 1 < N) y.y = yp[1]; if (n0 + lc + 2 < N) y.z = yp[2]; }
-        if (k0 + lc + 3 < K) x = *reinterpret_cast<const float4*>(xp);
-        else { if (k0 + lc < K) x.x = xp[0]; if (k0 + lc + 1 < K) x.y = xp[1]; if (k0 + lc + 2 < K) x.z = xp[2]; }
+      float* ys = Ys(buf, lr + 16 * h) + lc;
+      float* xs = Xs(buf, lr + 16 * h) + lc;
+      const float* yp = dY + row * ldy + n0 + lc;
+      const float* xp = X + row * ldx + k0 + lc;
+      if (row < m_end && y_full) cp_async16(ys, yp);
+      else {
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < m_end) { if (n0 + lc < N) y.x = yp[0]; if (n0 + lc + 1 < N) y.y = yp[1]; if (n0 + lc + 2 < N) y.z = yp[2]; }
+        *reinterpret_cast<float4*>(ys) = y;
       }
-      *reinterpret_cast<float4*>(&Ys[lr + 16 * h][lc]) = y;
-      *reinterpret_cast<float4*>(&Xs[lr + 16 * h][lc]) = x;
+      if (row < m_end && x_full) cp_async16(xs, xp);
+      else {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < m_end) { if (k0 + lc < K) x.x = xp[0]; if (k0 + lc + 1 < K) x.y = xp[1]; if (k0 + lc + 2 < K) x.z = xp[2]; }
+        *reinterpret_cast<float4*>(xs) = x;
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_stage(0, m_begin);
+  int buf = 0;
+  for (long long m = m_begin; m < m_end; m += DWR, buf ^= 1) {
+    if (m + DWR < m_end) { load_stage(buf ^ 1, m + DWR); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < DWR / 4; ++rr) {
+      const int r = rr * 4 + grp;                          // rows interleaved over the groups: the tail stage stays balanced
+      const float* yr = Ys(buf, r);
+      const float* xr = Xs(buf, r);
+      const float4 a0 = *reinterpret_cast<const float4*>(yr + tn * 4), a1 = *reinterpret_cast<const float4*>(yr + 32 + tn * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(xr + tk * 4), b1 = *reinterpret_cast<const float4*>(xr + 32 + tk * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int r = 0; r < DWR; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(&Ys[r][tn * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Xs[r][tk * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         bsum[i] += av[i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
     }
     __syncthreads();
   }
+  // sum the four groups' tiles: groups 1..3 park theirs in shared memory ([grp - 1][64 values][64 threads]: conflict-free)
+  float* red = dw_smem;
+  if (grp > 0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = n0 + tn * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[((size_t)(grp - 1) * 72 + i * 8 + j) * 64 + t64] = acc[i][j];
+      red[((size_t)(grp - 1) * 72 + 64 + i) * 64 + t64] = bsum[i];
+    }
+  }
+  __syncthreads();
+  if (grp > 0) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] += red[((size_t)g * 72 + i * 8 + j) * 64 + t64];
+      bsum[i] += red[((size_t)g * 72 + 64 + i) * 64 + t64];
+    }
+    const int n = n0 + (i < 4 ? tn * 4 + i : 32 + tn * 4 + i - 4);
     if (n >= N) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tk * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + (j < 4 ? tk * 4 + j : 32 + tk * 4 + j - 4);
       if (k < K) atomicAdd(dW + (long long)n * ldw + k, acc[i][j]);
     }
     if (db && blockIdx.y == 0 && tk == 0) atomicAdd(db + n, bsum[i]);
