@@ -182,7 +182,10 @@ static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long lo
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
   }
-  if (DH <= 32) {
+  if (DH == 32 && attn_r2_enabled() && lddkv % 4 == 0) {        // thread pairs: two keys x half the head dimension each
+    HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_bwd_dkv_pair_kernel<<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
+  } else if (DH <= 32) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
   } else {

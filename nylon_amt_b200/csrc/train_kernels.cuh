@@ -466,6 +466,87 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restri
   }
 }
 
+// Pass 2 for head_dim 32, register-tiled against the shared-memory read path that bounds the kernel above (every Q / dO value
+// read there feeds ONE key): a thread PAIR owns two key rows, each thread one half of the head dimension (16 columns of K, V,
+// dK, dV for both keys), the two half dot products meet through one shuffle.  Per query a thread reads 32 floats for 128 FMAs
+// (the one-key kernel: 64 floats for 128 FMAs).
+__global__ void __launch_bounds__(256) attn_bwd_dkv_pair_kernel(const float* __restrict__ Q, int ldq, long long q_seq_stride, const float* __restrict__ Kp,
+                                                                const float* __restrict__ Vp, int ldkv, const float* __restrict__ dO, int ldo,
+                                                                const float* __restrict__ lse, const float* __restrict__ Din, int Lq, int Lk, int heads, float c,
+                                                                float* __restrict__ dK, float* __restrict__ dV, int lddkv, Drop drop) {
+  constexpr int DH = 32, HD = 16;
+  extern __shared__ __align__(16) float smem_bwd[];
+  float* sQ = smem_bwd;
+  float* sG = smem_bwd + (size_t)Lq * DH;
+  float* sL = sG + (size_t)Lq * DH;
+  float* sD = sL + Lq;
+  const int seq = blockIdx.x, head = blockIdx.y;
+  for (int i = threadIdx.x; i < Lq * (DH / 4); i += blockDim.x) {
+    int j = i / (DH / 4), cc = i % (DH / 4);
+    reinterpret_cast<float4*>(sQ)[i] = *reinterpret_cast<const float4*>(Q + (long long)seq * q_seq_stride + (long long)j * ldq + head * DH + cc * 4);
+    reinterpret_cast<float4*>(sG)[i] = *reinterpret_cast<const float4*>(dO + ((long long)seq * Lq + j) * ldo + head * DH + cc * 4);
+  }
+  for (int i = threadIdx.x; i < Lq; i += blockDim.x) {
+    sL[i] = lse[((long long)seq * heads + head) * Lq + i];
+    sD[i] = Din[((long long)seq * heads + head) * Lq + i];
+  }
+  __syncthreads();
+  const int half = threadIdx.x & 1;
+  const int j0 = 2 * (threadIdx.x >> 1);                   // keys j0, j0 + 1 (whole warps stay alive for the shuffles)
+  const bool ok0 = j0 < Lk, ok1 = j0 + 1 < Lk;
+  float k[2][HD], v[2][HD], ak[2][HD], av[2][HD];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const bool ok = u ? ok1 : ok0;
+    const float* kp = Kp + ((long long)seq * Lk + j0 + u) * ldkv + head * DH + half * HD;
+    const float* vp = Vp + ((long long)seq * Lk + j0 + u) * ldkv + head * DH + half * HD;
+#pragma unroll
+    for (int i = 0; i < HD; ++i) { k[u][i] = ok ? kp[i] : 0.f; v[u][i] = ok ? vp[i] : 0.f; ak[u][i] = 0.f; av[u][i] = 0.f; }
+  }
+  const long long pbase = ((long long)seq * heads + head) * Lq;
+  for (int r = 0; r < Lq; ++r) {
+    const float4* qr = reinterpret_cast<const float4*>(sQ + (size_t)r * DH + half * HD);
+    const float4* gr = reinterpret_cast<const float4*>(sG + (size_t)r * DH + half * HD);
+    float q[HD], g[HD];
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 a = qr[i], b = gr[i];
+      q[4 * i] = a.x; q[4 * i + 1] = a.y; q[4 * i + 2] = a.z; q[4 * i + 3] = a.w;
+      g[4 * i] = b.x; g[4 * i + 1] = b.y; g[4 * i + 2] = b.z; g[4 * i + 3] = b.w;
+    }
+    float s[2] = {0.f, 0.f}, dp[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < HD; ++i) {
+      s[0] = fmaf(q[i], k[0][i], s[0]); s[1] = fmaf(q[i], k[1][i], s[1]);
+      dp[0] = fmaf(g[i], v[0][i], dp[0]); dp[1] = fmaf(g[i], v[1][i], dp[1]);
+    }
+    const float Lr = sL[r], Dr = sD[r];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+      dp[u] += __shfl_xor_sync(0xffffffffu, dp[u], 1);
+      const float p = expf(s[u] * c - Lr);
+      float keep_scale = 1.f;                              // dropout on the probabilities: O = (P . mask * scale) V
+      if (drop.thresh) keep_scale = drop_keep(drop, (unsigned long long)((pbase + r) * Lk + j0 + u)) ? drop.scale : 0.f;
+      const float pd = p * keep_scale;
+      const float ds = p * (dp[u] * keep_scale - Dr) * c;
+#pragma unroll
+      for (int i = 0; i < HD; ++i) { av[u][i] = fmaf(pd, g[i], av[u][i]); ak[u][i] = fmaf(ds, q[i], ak[u][i]); }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!(u ? ok1 : ok0)) continue;
+    float* ok_ = dK + ((long long)seq * Lk + j0 + u) * lddkv + head * DH + half * HD;
+    float* ov_ = dV + ((long long)seq * Lk + j0 + u) * lddkv + head * DH + half * HD;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      *reinterpret_cast<float4*>(ok_ + 4 * i) = make_float4(ak[u][4 * i], ak[u][4 * i + 1], ak[u][4 * i + 2], ak[u][4 * i + 3]);
+      *reinterpret_cast<float4*>(ov_ + 4 * i) = make_float4(av[u][4 * i], av[u][4 * i + 1], av[u][4 * i + 2], av[u][4 * i + 3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Loss of one head group (train.py:139-151) and its gradient with respect to the logits.
 //   logits [rows, ld]: columns 0..2 onset / offset / mpe (pre-sigmoid), 3..3+V-1 velocity; rows in (b,f,n) order, or
