@@ -148,3 +148,44 @@ def test_forward_tensor_core_vs_oracle(golden_dir, kind, size):
     assert err["attention"] <= 2e-2, err
     budget_vel_a = {"bf16": 0.15, "fp16": 0.03}[kind]
     assert err["velocity_A"] <= budget_vel_a, err
+
+
+def _forward_in_subprocess(golden_dir, env, out_path, strided):
+    """Run the paper-size fp16x3 forward in a fresh process (the library reads its experiment switches once per process)."""
+    import subprocess, sys
+    code = (
+        "import sys, os, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import nylon_amt_b200 as hft\n"
+        "g = np.load(os.path.join(%r, 'hft_paper.npz'))\n"
+        "model = hft.build_model(hft.default_config(), 256, 512, 3, 4, seed=1234, device='cuda')\n"
+        "model.precision = 'fp16x3'\n"
+        "spec = torch.from_numpy(g['spec']).cuda()\n"
+        "if %r:\n"
+        "    # the layout AMT.transcript hands over: windows of a [T, 256] feature, strides (128 * 256, 1, 256)\n"
+        "    B, NB, W = spec.shape\n"
+        "    feat = torch.zeros(128 * (B - 1) + W, NB, device='cuda')\n"
+        "    spec0 = spec[0].t().contiguous()\n"
+        "    feat[:W] = spec0\n"
+        "    spec = feat.as_strided((B, NB, W), (128 * NB, 1, NB))\n"
+        "out = model(spec)\n"
+        "np.savez(%r, *[t.float().cpu().numpy() for t in out])\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir, strided, out_path)
+    e = dict(os.environ)
+    e.update(env)
+    subprocess.run([sys.executable, "-c", code], check=True, env=e, timeout=300)
+    z = np.load(out_path)
+    return [z[k] for k in z.files]
+
+
+@pytest.mark.parametrize("strided", [False, True])
+def test_front_tensor_core_kernel_equals_cuda_core_filter(golden_dir, tmp_path, strided):
+    """front_tc_kernel (Toeplitz tiles on tcgen05, three split products) against the fp32 CUDA-core filter it replaces
+    (HFT_TC_FRONT=0), through the whole paper-size forward: contiguous [B, 256, 192] input and the strided window view of a
+    [T, 256] feature that AMT.transcript passes (reference amt.py:88-89)."""
+    a = _forward_in_subprocess(golden_dir, {"HFT_TC_FRONT": "1"}, str(tmp_path / "tc.npz"), strided)
+    b = _forward_in_subprocess(golden_dir, {"HFT_TC_FRONT": "0"}, str(tmp_path / "cc.npz"), strided)
+    worst = max(float(np.abs(x - y).max()) for x, y in zip(a, b))
+    print("front tc vs cuda-core, strided=%s: worst abs diff %.3e" % (strided, worst))
+    assert all(np.isfinite(x).all() for x in a)
+    assert worst <= 1e-3, worst
