@@ -379,6 +379,7 @@ def main():
     res_f = [torch.empty((n_seg * 128, 88), dtype=torch.float32).pin_memory() for _ in range(6)]
     res_v = [torch.empty((n_seg * 128, 88), dtype=torch.int8).pin_memory() for _ in range(2)]
     wav_stage = torch.empty_like(wav_dev)
+    vel_arg = [torch.empty((nb, 128, 88), device=dev, dtype=torch.int8) for _ in range(2)]
 
     def step_e2e():
         wav_stage.copy_(wav_host, non_blocking=True)
@@ -386,12 +387,13 @@ def main():
         for s0 in range(0, n_seg, nb):
             b = min(nb, n_seg - s0)
             o = [t[:b] for t in outs]
-            model.forward_into(spec_all[s0:s0 + b], o, want_attention=False)
+            o[3] = o[8] = None                                                 # as AMT.transcript: velocity leaves the heads GEMM as int8 argmax
+            model.forward_into(spec_all[s0:s0 + b], o, want_attention=False, velocity_argmax=[t[:b] for t in vel_arg])
             r0, r1 = s0 * 128, (s0 + b) * 128
             for dst, i in zip(res_f, (0, 1, 2, 5, 6, 7)):
                 dst[r0:r1].copy_(o[i].reshape(b * 128, 88), non_blocking=True)
-            for dst, i in zip(res_v, (3, 8)):
-                dst[r0:r1].copy_(o[i].argmax(3).reshape(b * 128, 88).to(torch.int8), non_blocking=True)
+            for dst, t in zip(res_v, vel_arg):
+                dst[r0:r1].copy_(t[:b].reshape(b * 128, 88), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
     def barrier():

@@ -130,6 +130,10 @@ int hft_model_set_weights(hft_model* model, const float* const* weights_dev, int
  *   onset/offset/mpe  [B][n_frame][n_note]  sigmoid probabilities
  *   velocity          [B][n_frame][n_note][n_velocity]  raw logits
  *   attention         [B][n_frame][n_heads][n_note][n_bin]  softmax of the last cross-attention
+ *   velocity_*_argmax [B][n_frame][n_note] int8   argmax over the velocity axis (first maximum, like torch.argmax), the only
+ *                                                 thing AMT.transcript keeps of the logits (reference amt.py:107,113: `.argmax(2)`);
+ *                                                 computed in the epilogue of the heads GEMM, so a caller that passes velocity_* =
+ *                                                 NULL never moves the 2 x 5.8 MB of logits per segment
  * Any pointer may be NULL to skip writing that output. */
 typedef struct hft_outputs {
   float* onset_A;
@@ -141,6 +145,8 @@ typedef struct hft_outputs {
   float* offset_B;
   float* mpe_B;
   float* velocity_B;
+  int8_t* velocity_A_argmax;
+  int8_t* velocity_B_argmax;
 } hft_outputs;
 
 /* spec_dev: [B][n_bin][n_margin + n_frame + n_margin] fp32 with element strides (the reference calls forward with

@@ -18,7 +18,7 @@ class hft_dims(ctypes.Structure):
 
 class hft_outputs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("onset_A", "offset_A", "mpe_A", "velocity_A", "attention",
-                                                "onset_B", "offset_B", "mpe_B", "velocity_B")]
+                                                "onset_B", "offset_B", "mpe_B", "velocity_B", "velocity_A_argmax", "velocity_B_argmax")]
 
 
 # every symbol include/hft_sm100.h declares: name -> (restype, argtypes)

@@ -240,16 +240,18 @@ class AMT():
         nb = min(chunk, n_win)
         V = cfg['midi']['num_velocity']
         opt = dict(device=dev, dtype=torch.float32)
-        bufs = [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [torch.empty((nb, F, n_note, V), **opt), None] + \
-               [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [torch.empty((nb, F, n_note, V), **opt)]
+        # the velocity logits themselves ([nb, F, n_note, V] x 2) are never materialised: only their argmax leaves the heads GEMM
+        bufs = [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [None, None] + [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [None]
+        vbuf = [torch.empty((nb, F, n_note), device=dev, dtype=torch.int8) for _ in range(2)]
+        del V
         with torch.no_grad():
             for w0 in range(0, n_win, chunk):
                 b = min(chunk, n_win - w0)
                 outs = [t[:b] if t is not None else None for t in bufs]
-                self.model.forward_into(spec_all[w0:w0 + b], outs, want_attention=False)
+                self.model.forward_into(spec_all[w0:w0 + b], outs, want_attention=False, velocity_argmax=[t[:b] for t in vbuf])
                 sl = slice(n_offset, n_offset + n_keep)
                 host = [outs[i][:, sl].reshape(b * n_keep, n_note).cpu().numpy() for i in (0, 1, 2, 5, 6, 7)]
-                vel = [outs[i][:, sl].argmax(3).reshape(b * n_keep, n_note).to(torch.int8).cpu().numpy() for i in (3, 8)]
+                vel = [t[:b, sl].reshape(b * n_keep, n_note).cpu().numpy() for t in vbuf]
                 r0 = w0 * n_keep
                 for dst, src in zip(res_f, host):
                     dst[r0:r0 + b * n_keep] = src[:max(0, min(b * n_keep, n_out_rows - r0))]

@@ -413,5 +413,27 @@ __global__ void heads_finish_f32_kernel(const float* __restrict__ HT, int ldh, i
   }
 }
 
+// argmax over the velocity logits of every row of HT (columns 3 .. 3+V-1), first maximum like torch.argmax (amt.py:107,113)
+__global__ void heads_argmax_f32_kernel(const float* __restrict__ HT, int ldh, int V, int F, int NN, long long rows, bool time_major,
+                                        signed char* __restrict__ out) {
+  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  long long orow = row;
+  if (time_major) {
+    int f = (int)(row % F);
+    long long bn = row / F;
+    int n = (int)(bn % NN);
+    orow = ((bn / NN) * F + f) * NN + n;
+  }
+  const float* p = HT + row * ldh + 3;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int j = 0; j < V; ++j) {
+    const float v = p[j];
+    if (v > best) { best = v; bi = j; }
+  }
+  out[orow] = (signed char)bi;
+}
+
 }  // namespace
 }  // namespace hft

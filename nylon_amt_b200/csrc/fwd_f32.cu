@@ -145,6 +145,7 @@ int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long 
   {
     LaunchScope ls(HFT_KCLASS_HEADS, s);
     heads_finish_f32_kernel<<<(unsigned)((Rd * NH + 255) / 256), 256, 0, s>>>(w.HID, NH, V, F, NN, Rd, false, o->onset_A, o->offset_A, o->mpe_A, o->velocity_A);
+    if (o->velocity_A_argmax) heads_argmax_f32_kernel<<<(unsigned)((Rd + 255) / 256), 256, 0, s>>>(w.HID, NH, V, F, NN, Rd, false, o->velocity_A_argmax);
   }
   // time re-layout + SAtime (:189-198)
   {
@@ -157,6 +158,7 @@ int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long 
   {
     LaunchScope ls(HFT_KCLASS_HEADS, s);
     heads_finish_f32_kernel<<<(unsigned)((Rd * NH + 255) / 256), 256, 0, s>>>(w.HID, NH, V, F, NN, Rd, true, o->onset_B, o->offset_B, o->mpe_B, o->velocity_B);
+    if (o->velocity_B_argmax) heads_argmax_f32_kernel<<<(unsigned)((Rd + 255) / 256), 256, 0, s>>>(w.HID, NH, V, F, NN, Rd, true, o->velocity_B_argmax);
   }
   HFT_CHECK_CUDA(cudaGetLastError());
   return HFT_OK;

@@ -778,7 +778,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   // heads A
   {
     GemmParams g{};
-    g.onset = o->onset_A; g.offset = o->offset_A; g.mpe = o->mpe_A; g.velocity = o->velocity_A; g.n_vel = V; g.time_major = 0; g.n_frame = F; g.n_note = NN;
+    g.onset = o->onset_A; g.offset = o->offset_A; g.mpe = o->mpe_A; g.velocity = o->velocity_A; g.vel_argmax = o->velocity_A_argmax; g.n_vel = V; g.time_major = 0; g.n_frame = F; g.n_note = NN;
     g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
     HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mT, t.headA, Rd, g, nullptr, nullptr, s));
   }
@@ -792,7 +792,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
   {
     GemmParams g{};
-    g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
+    g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.vel_argmax = o->velocity_B_argmax; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
     g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
     HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mU, t.headB, Rd, g, nullptr, nullptr, s));
   }

@@ -277,6 +277,8 @@ extern "C" int hft_forward(hft_model* model, int precision, const float* spec_de
     adv(o.onset_A, fn); adv(o.offset_A, fn); adv(o.mpe_A, fn); adv(o.velocity_A, fn * m->nvel);
     adv(o.attention, (long long)m->nframe * m->heads * m->nnote * m->nbin);
     adv(o.onset_B, fn); adv(o.offset_B, fn); adv(o.mpe_B, fn); adv(o.velocity_B, fn * m->nvel);
+    if (o.velocity_A_argmax) o.velocity_A_argmax += (long long)b0 * fn;
+    if (o.velocity_B_argmax) o.velocity_B_argmax += (long long)b0 * fn;
     const float* sp = spec_dev + (long long)b0 * stride_b;
     int rc = (precision == HFT_PREC_F32) ? forward_f32(m, sp, stride_b, stride_bin, stride_t, bc, &o, s)
                                          : forward_tc(m, precision, sp, stride_b, stride_bin, stride_t, bc, &o, s);

@@ -61,6 +61,7 @@ struct GemmParams {
   float* offset;
   float* mpe;
   float* velocity;
+  signed char* vel_argmax; // [rows] argmax over the n_vel velocity logits (first maximum), or NULL
   int n_vel;
   int time_major;         // rows are (b, note, frame): permute back to [B, frame, note]
   int n_frame, n_note;
@@ -414,6 +415,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           int n = (int)(bn % p.n_note);
           orow_idx = ((bn / p.n_note) * p.n_frame + f) * p.n_note + n;
         }
+        float best = -INFINITY;
+        int best_i = 0;
 #pragma unroll 1
         for (int c = 0; c < NT / 32; ++c) {
           uint32_t r[32];
@@ -421,6 +424,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           tmem_ld_wait();
           const int c0 = c * 32;
           if (c0 + 32 <= p.n_vel) {
+            if (p.vel_argmax) {                                 // running argmax of the row's velocity logits (strict >: first maximum)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+                if (v > best) { best = v; best_i = c0 + j; }
+              }
+            }
             if (p.velocity) {
               float4* dst = reinterpret_cast<float4*>(p.velocity + orow_idx * p.n_vel + c0);
               const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
@@ -438,6 +448,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               if (dsts[j]) dsts[j][orow_idx] = 1.f / (1.f + expf(-(__uint_as_float(r[j]) + s_bias[c0 + j])));
           }
         }
+        if (p.vel_argmax) p.vel_argmax[orow_idx] = (signed char)best_i;
       }
       fence_before_sync();
       __syncwarp();

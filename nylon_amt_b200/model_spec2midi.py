@@ -244,8 +244,11 @@ class Model_SPEC2MIDI(nn.Module):
                                               x.stride(2), B, ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward")
         return tuple(outs)
 
-    def forward_into(self, input_spec, outs, want_attention=True):
-        """Same computation writing into caller-owned output tensors (no allocation on the hot path)."""
+    def forward_into(self, input_spec, outs, want_attention=True, velocity_argmax=None):
+        """Same computation writing into caller-owned output tensors (no allocation on the hot path).  Entries of `outs`
+        may be None (that output is not written).  velocity_argmax: optional pair of int8 tensors [B, n_frame, n_note] that
+        receive argmax(velocity logits) of the A / B heads straight from the heads GEMM's epilogue (what AMT.transcript keeps
+        of the logits, reference amt.py:107,113)."""
         h = self.sync_weights()
         if h.max_batch != self.max_batch:
             _lib.check(_lib.lib().hft_model_set_max_batch(h.ptr, int(self.max_batch)), "hft_model_set_max_batch")
@@ -254,6 +257,11 @@ class Model_SPEC2MIDI(nn.Module):
         ptrs = [ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(None) for t in outs]
         if not want_attention:
             ptrs[4] = ctypes.c_void_p(None)
+        if velocity_argmax is not None:
+            for t in velocity_argmax:
+                if t.dtype != torch.int8 or not t.is_cuda or not t.is_contiguous():
+                    raise RuntimeError("velocity_argmax tensors must be contiguous CUDA int8")
+            ptrs += [ctypes.c_void_p(t.data_ptr()) for t in velocity_argmax]
         o = _lib.hft_outputs(*ptrs)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):

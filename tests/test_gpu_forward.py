@@ -200,3 +200,37 @@ def test_full_hour_paper_size_properties():
         for k in (0, 1, 2, 4, 5, 6):
             err = float((ref[k] - full[k][s0:s0 + ref[k].shape[0]]).abs().max())
             assert err <= TOL_FP32, (s0, k, err)
+
+
+@pytest.mark.parametrize("precision,size", [("fp32", "reduced"), ("fp16x3", "reduced"), ("fp16x3", "paper"), ("bf16", "paper")])
+def test_velocity_argmax_epilogue_equals_argmax_of_logits(golden_dir, precision, size):
+    """hft_outputs.velocity_*_argmax (what AMT.transcript keeps of the velocity logits, reference amt.py:107,113) must be
+    torch.argmax of the logits the same forward writes -- with and without the logits being written, and across the internal
+    max_batch loop."""
+    hid, pf, L, h = {"reduced": (64, 128, 2, 2), "paper": (256, 512, 3, 4)}[size]
+    g = np.load(os.path.join(golden_dir, "hft_%s.npz" % size))
+    model = hft.build_model(hft.default_config(), hid, pf, L, h, seed=1234, device="cuda")
+    model.precision = precision
+    spec = torch.from_numpy(g["spec"]).cuda()
+    spec = torch.cat([spec, spec.flip(0), spec * 0.5], 0)            # B = 3 x golden batch
+    B = spec.shape[0]
+    model.max_batch = 2                                             # forces the loop over sub-batches inside hft_forward
+    full = model(spec)
+    # (the attention-returning forward takes another kernel for the last cross-attention, so its logits differ in the last
+    #  bits: the argmax is checked against the logits of the SAME call, then against the call that skips the logits)
+    outs = [torch.empty_like(t) for t in full]
+    va = [torch.full((B, 128, 88), -7, device="cuda", dtype=torch.int8) for _ in range(2)]
+    model.forward_into(spec, outs, want_attention=False, velocity_argmax=va)
+    torch.cuda.synchronize()
+    for got, i in zip(va, (3, 8)):
+        ref = outs[i].argmax(3).to(torch.int8)
+        assert torch.equal(got, ref), (precision, size, int((got != ref).sum()))
+        assert float((outs[i] - full[i]).abs().max()) <= {"fp32": 1e-5, "fp16x3": 1e-4, "bf16": 0.25}[precision]
+    outs2 = [torch.empty_like(t) for t in full]
+    outs2[3] = outs2[8] = None
+    vb = [torch.full((B, 128, 88), -7, device="cuda", dtype=torch.int8) for _ in range(2)]
+    model.forward_into(spec, outs2, want_attention=False, velocity_argmax=vb)
+    torch.cuda.synchronize()
+    assert torch.equal(va[0], vb[0]) and torch.equal(va[1], vb[1])
+    for i in (0, 1, 2, 5, 6, 7):
+        assert torch.equal(outs[i], outs2[i])
