@@ -238,26 +238,59 @@ class AMT():
         res_v = [np.zeros((n_out_rows, n_note), dtype=np.int8) for _ in range(2)]
         spec_all = torch.as_strided(a_input, (n_win, n_bin, W), (hop * n_bin, 1, n_bin))
         nb = min(chunk, n_win)
-        V = cfg['midi']['num_velocity']
-        opt = dict(device=dev, dtype=torch.float32)
-        # the velocity logits themselves ([nb, F, n_note, V] x 2) are never materialised: only their argmax leaves the heads GEMM
-        bufs = [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [None, None] + [torch.empty((nb, F, n_note), **opt) for _ in range(3)] + [None]
-        vbuf = [torch.empty((nb, F, n_note), device=dev, dtype=torch.int8) for _ in range(2)]
-        del V
+        # Device outputs and pinned host staging are double-buffered per slot: the D2H copies of chunk i run behind the forward of
+        # chunk i+1, and the host only waits on the event of the slot it is about to reuse (the reference syncs 8 times per 2 s
+        # of audio, amt.py:104-113).  The velocity logits themselves ([nb, F, n_note, V] x 2) are never materialised: only their
+        # argmax leaves the heads GEMM.
+        slots = self._result_slots(dev, nb, F, n_keep, n_note)
+        sl = slice(n_offset, n_offset + n_keep)
+
+        def drain(slot):
+            r0, b = slot["r0"], slot["b"]
+            slot["event"].synchronize()
+            n = max(0, min(b * n_keep, n_out_rows - r0))
+            for dst, src in zip(res_f + res_v, slot["host"]):
+                dst[r0:r0 + n] = src[:n].numpy()
+            slot["b"] = 0
+
         with torch.no_grad():
-            for w0 in range(0, n_win, chunk):
+            for i, w0 in enumerate(range(0, n_win, chunk)):
                 b = min(chunk, n_win - w0)
-                outs = [t[:b] if t is not None else None for t in bufs]
-                self.model.forward_into(spec_all[w0:w0 + b], outs, want_attention=False, velocity_argmax=[t[:b] for t in vbuf])
-                sl = slice(n_offset, n_offset + n_keep)
-                host = [outs[i][:, sl].reshape(b * n_keep, n_note).cpu().numpy() for i in (0, 1, 2, 5, 6, 7)]
-                vel = [t[:b, sl].reshape(b * n_keep, n_note).cpu().numpy() for t in vbuf]
-                r0 = w0 * n_keep
-                for dst, src in zip(res_f, host):
-                    dst[r0:r0 + b * n_keep] = src[:max(0, min(b * n_keep, n_out_rows - r0))]
-                for dst, src in zip(res_v, vel):
-                    dst[r0:r0 + b * n_keep] = src[:max(0, min(b * n_keep, n_out_rows - r0))]
+                slot = slots[i % len(slots)]
+                if slot["b"]:
+                    drain(slot)
+                outs = [t[:b] if t is not None else None for t in slot["dev"]]
+                vel = [t[:b] for t in slot["vel"]]
+                self.model.forward_into(spec_all[w0:w0 + b], outs, want_attention=False, velocity_argmax=vel)
+                srcs = [outs[k] for k in (0, 1, 2, 5, 6, 7)] + vel
+                for dst, src in zip(slot["host"], srcs):
+                    dst[:b * n_keep].view(b, n_keep, n_note).copy_(src[:, sl], non_blocking=True)
+                slot["event"].record(torch.cuda.current_stream(dev))
+                slot["r0"], slot["b"] = w0 * n_keep, b
+            order = sorted((s_ for s_ in slots if s_["b"]), key=lambda s_: s_["r0"])
+            for slot in order:
+                drain(slot)
         return res_f[0], res_f[1], res_f[2], res_v[0], res_f[3], res_f[4], res_f[5], res_v[1]
+
+    def _result_slots(self, dev, nb, F, n_keep, n_note, n_slots=3):
+        """Per-chunk device outputs + pinned host staging + event, cached across calls (pinned allocation is slow)."""
+        cache = self.__dict__.setdefault("_slots", {})
+        key = (str(dev), nb, F, n_keep, n_note)
+        if key not in cache:
+            cache.clear()                                   # one geometry at a time: do not hoard pinned memory
+            slots = []
+            for _ in range(n_slots):
+                f32 = lambda: torch.empty((nb, F, n_note), device=dev, dtype=torch.float32)
+                slots.append(dict(
+                    dev=[f32(), f32(), f32(), None, None, f32(), f32(), f32(), None],
+                    vel=[torch.empty((nb, F, n_note), device=dev, dtype=torch.int8) for _ in range(2)],
+                    host=[torch.empty((nb * n_keep, n_note), dtype=torch.float32).pin_memory() for _ in range(6)] +
+                         [torch.empty((nb * n_keep, n_note), dtype=torch.int8).pin_memory() for _ in range(2)],
+                    event=torch.cuda.Event(), b=0, r0=0))
+            cache[key] = slots
+        for s_ in cache[key]:
+            s_["b"] = 0
+        return cache[key]
 
     def _to_device_feature(self, a_feature):
         if isinstance(a_feature, torch.Tensor):
