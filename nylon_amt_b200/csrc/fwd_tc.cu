@@ -1,8 +1,12 @@
-// Tensor-core forward of Model_SPEC2MIDI (reference hftt_code/model/model_spec2midi.py:15-35) -- HFT_PREC_BF16 /
-// HFT_PREC_F16: 16-bit operands on tcgen05 with fp32 accumulation in TMEM; softmax, LayerNorm, residuals, sigmoid in
-// fp32.  Activations live in HBM as 16-bit row-major [rows, H] tensors; every projection is one launch of the
-// persistent UMMA GEMM (tc_gemm.cuh) whose epilogue carries bias / ReLU / residual+LayerNorm / heads; attention is
-// tc_attn.cuh.  Host side: tensor maps are encoded once per (workspace, weights) and passed as __grid_constant__.
+// Tensor-core forward of Model_SPEC2MIDI (reference hftt_code/model/model_spec2midi.py:15-35) -- HFT_PREC_F16X3 (split fp16
+// operands, three products: the fp32-parity mode and the bench default), HFT_PREC_BF16 / HFT_PREC_F16 (one product): 16-bit
+// operands on tcgen05 with fp32 accumulation in TMEM; softmax, LayerNorm, residuals, sigmoid in fp32.  Activations live in
+// HBM as 16-bit row-major [rows, H] tensors (split mode: [rows, 2H] = hi | lo).  Launch sequence per chunk of segments:
+//   front_tc_kernel (tc_front.cuh)            collapsed 65-tap filter + positional row -> X
+//   per layer: gemm_kernel<EPI_STORE> (QKV)   -> attn2_kernel / attn_probs_kernel (tc_attn2.cuh) -> gemm_kernel<EPI_LN> (fc_o +
+//              residual + LayerNorm)          -> ffn_kernel (tc_ffn.cuh: fc_1, ReLU, fc_2, residual, LayerNorm in one launch)
+//   gemm_kernel<EPI_HEADS>                    the four heads of a group as one [rows, 192] GEMM, sigmoid / argmax in the epilogue
+// Host side: tensor maps are encoded once per (workspace, weights) and passed as __grid_constant__.
 #include "common.cuh"
 #include "model.h"
 #include "tc_attn.cuh"
