@@ -260,6 +260,34 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world):
         classes[n] = {"ms": round(t.value, 3), "launches": c.value}
     seg_s = world * B / (ms / 1e3)
     gflop = 3 * 16.57 * B                      # forward 16.57 GFLOP / segment, backward ~2x
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the same step (forward restatement + the 8 criteria + autograd backward + Adam restatement) of the oracle port on the host
+        # cores, and in eager PyTorch on this GPU ("what a user of the reference gets on this box today")
+        from oracle import train_oracle as to
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+
+        def oracle_step(device, n):
+            o = to.GradOracle(sd, 2, device=device)
+            mom = [{k: torch.zeros_like(v) for k, v in o.sd.items()} for _ in range(2)]
+            y = [t[:n].to(device) for t in lab]
+            t0 = time.perf_counter()
+            outs = o.forward_grad(spec[:n].to(device))
+            l = to.loss_from_outputs(outs, y[0], y[1], y[2], y[3])
+            l.backward()
+            with torch.no_grad():
+                to.adam_step(o.sd, {k: v.grad for k, v in o.sd.items()}, mom[0], mom[1], 1)
+            if device != "cpu":
+                torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
+        n_cpu = B                                            # the whole batch of one step (a few seconds per step on the host)
+        t_cpu = min(oracle_step("cpu", n_cpu) for _ in range(2))
+        oracle_step(dev, B)
+        t_gpu = min(oracle_step(dev, B) for _ in range(3))
+        cpu = {"value": n_cpu / t_cpu, "unit": "segments/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d segments of the batch: torch-CPU forward restatement + criteria + autograd backward + Adam restatement, %.2f s" % (n_cpu, t_cpu),
+               "eager_gpu": {"value": B / t_gpu, "unit": "segments/s", "what": "the same restatement in eager PyTorch on cuda:0, batch %d" % B}}
     if rank == 0:
         print(json.dumps({"metric": "training segments/sec (reduced hFT fwd+loss+bwd+Adam)", "value": seg_s, "unit": "segments/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -269,7 +297,7 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world):
                           "allreduce_ms": t_ar[0] / 3, "loss_after": loss, "classes": classes, "gpu_launches": int(n_launch), "clocks": clocks,
                           "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": 72.0, "unit": "TFLOP/s",
                                        "frac": gflop / ms / 72.0, "traffic": None, "peak_source": "148 SMs x 128 FMA lanes x 1.9 GHz (nominal fp32)"},
-                          "cpu_baseline": None}))
+                          "cpu_baseline": cpu}))
     return 0
 
 

@@ -44,13 +44,13 @@ def loss_from_outputs(outs, label_onset, label_offset, label_mpe, label_velocity
 class GradOracle(hft_oracle.Oracle):
     """The forward restatement with autograd enabled on every parameter."""
 
-    def __init__(self, state_dict, n_heads, dtype=torch.float32):
-        super().__init__(state_dict, n_heads, dtype=dtype)
+    def __init__(self, state_dict, n_heads, dtype=torch.float32, device="cpu"):
+        super().__init__(state_dict, n_heads, dtype=dtype, device=device)
         for v in self.sd.values():
             v.requires_grad_(True)
 
     def forward_grad(self, spec):
-        spec = torch.as_tensor(spec, dtype=self.dtype)
+        spec = torch.as_tensor(spec, dtype=self.dtype).to(self.device)
         return self.decoder(self.encoder(spec), spec.shape[0])
 
 
