@@ -631,6 +631,9 @@ static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx
   fp.x3 = t.x3 ? 1 : 0;
   fp.lo_off = m->H; fp.w1_lo_off = m->H; fp.w2_lo_off = m->P;
   fp.b1 = w1.bias; fp.b2 = w2.bias; fp.gamma = m->w[ln.g]; fp.beta = m->w[ln.b];
+  static int slots_env = -1;
+  if (slots_env < 0) { const char* e = getenv("HFT_TC_FFN_SLOTS"); slots_env = e ? atoi(e) : 0; }
+  if (slots_env >= 2 && slots_env < ffn_slots(fp.x3)) fp.slots = slots_env;
   static int sms = num_sms();
   int units = sms / 2;
   if (units > fp.m_tiles) units = fp.m_tiles;

@@ -29,6 +29,7 @@ struct FfnParams {
   const float* b2;          // [hid]
   const float* gamma;
   const float* beta;
+  int slots;                // 0 = ffn_slots(x3); smaller values only (the shared-memory layout is sized for the default)
 };
 
 constexpr int kFfnH = 256, kFfnP = 512, kFfnJB = 128, kFfnNJ = kFfnP / kFfnJB, kFfnKC = kFfnH / 64;
@@ -47,7 +48,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int parts = p.x3 ? 2 : 1;
-  const int kFfnSlots = ffn_slots(p.x3);
+  const int kFfnSlots = p.slots > 0 ? p.slots : ffn_slots(p.x3);   // p.slots < default: ring-depth experiment (HFT_TC_FFN_SLOTS)
   uint8_t* s_x = smem;                                                   // [parts][KC] chunks of 128 x 64
   uint8_t* s_ring = s_x + (size_t)parts * kFfnKC * kChunkA;              // [slots] x 16 KB
   uint8_t* s_i64 = s_ring + (size_t)kFfnSlots * kFfnSlot;                // 32 x 64 half identity
