@@ -66,6 +66,15 @@ static int make_map_front(CUtensorMap* m, const void* base, long long outer, lon
   return HFT_OK;
 }
 
+// Rows per TMA-store box of the GEMM epilogues (HFT_TC_STAGE_ROWS = 32 | 16 | 8).  A warp's staging block is rows x 128 bytes, so
+// 16 / 8 rows free 16 / 24 KB of shared memory, which in split mode is what lets the CTA's W slice (128 KB, K = 256) stay resident
+// next to a 4- / 5-deep A ring instead of streaming it from L2 for every row tile.
+static int gemm_stage_rows() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TC_STAGE_ROWS"); v = e ? atoi(e) : 32; if (v != 8 && v != 16) v = 32; }
+  return v;
+}
+
 // ---- small CUDA-core kernels of the 16-bit path -----------------------------------------------------------------
 // In x3 (split) mode every 16-bit tensor carries two column blocks: hi = round16(v) at [0, C) and lo = round16(v - hi)
 // at [C, 2C); hi + lo reproduces v to ~22 bits with fp16 parts.
@@ -202,6 +211,7 @@ struct TcState {
   uint16_t* ws = nullptr;
   uint16_t *X, *QKV, *CTX, *HID, *T, *DQ, *U;
   CUtensorMap mX, mCTX, mHID, mT, mU;               // GEMM A operands / TMA-store targets, box 64 x 128
+  CUtensorMap gX, gHID, gT, gU, gQKV, gDQ;          // the same targets with stage_rows-row boxes (GEMM epilogues, see gemm_stage_rows())
   CUtensorMap sX3;                                  // X as [b * F + f][bin][column] for the front kernel's stores
   CUtensorMap sX, sHID, sT, sU, sQKV, sDQ, sCTX;    // TMA-store targets (projections, attention context), box 64 x 32 (one epilogue warp)
   CUtensorMap mPosRep;                              // repeated pitch-query table (residual of layer zero)
@@ -343,6 +353,15 @@ static int ensure_ws(Model* m, TcState& t, int B) {
   chk(make_map(&t.sQKV, t.QKV, Re, h3, h3, 64, 32, bf));
   chk(make_map(&t.sDQ, t.DQ, Rd, h3, h3, 64, 32, bf));
   chk(make_map(&t.sCTX, t.CTX, Re, h1, h1, 64, 32, bf));
+  {
+    const int sr = gemm_stage_rows();
+    chk(make_map(&t.gX, t.X, Re, h1, h1, 64, sr, bf));
+    chk(make_map(&t.gHID, t.HID, Re, p1, p1, 64, sr, bf));
+    chk(make_map(&t.gT, t.T, Rd, h1, h1, 64, sr, bf));
+    chk(make_map(&t.gU, t.U, Rd, h1, h1, 64, sr, bf));
+    chk(make_map(&t.gQKV, t.QKV, Re, h3, h3, 64, sr, bf));
+    chk(make_map(&t.gDQ, t.DQ, Rd, h3, h3, 64, sr, bf));
+  }
   chk(make_map(&t.mPosRep, t.pos_rep, 11 * 128, h1, h1, 64, 128, bf));
   if (rc != HFT_OK) return rc;
   t.ws_batch = B;
@@ -423,7 +442,8 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   // through a ring of their own.
   const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (gp.x3 ? 2 : 1);
   const size_t w_chunk = (size_t)n_rows_w * kBlockK * 2;
-  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * kWarpStage + kConstBytes + 512;
+  const int stage_rows = gp.stage_rows ? gp.stage_rows : 32;
+  const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * stage_rows * 128 + kConstBytes + 512;
   const size_t budget = 227 * 1024;
   static int wres = -1;                      // HFT_TC_WRES=0: never keep W resident (experiments)
   if (wres < 0) { const char* e = getenv("HFT_TC_WRES"); wres = (e && e[0] == '0') ? 0 : 1; }
@@ -441,7 +461,7 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   int units = (units_max / gp.n_tiles) * gp.n_tiles;
   if (units > gp.m_tiles * gp.n_tiles) units = gp.m_tiles * gp.n_tiles;
   const int grid = pair ? 2 * units : units;
-  const size_t smem = gemm_smem_bytes(n_rows_w, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid);
+  const size_t smem = gemm_smem_bytes(n_rows_w, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid, stage_rows);
   HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "tc gemm: %zu bytes of shared memory needed", smem);
   const CUtensorMap& o = mo ? *mo : ma;
   const CUtensorMap& r = mr ? *mr : ma;
@@ -598,7 +618,14 @@ static int linear(TcState& t, cudaStream_t s, int epi, const CUtensorMap& a, con
   g.x3 = t.x3 ? 1 : 0;
   g.a_lo_off = w.K; g.w_lo_off = w.K; g.out_lo_off = out_width;
   if (ln) { g.gamma = m->w[ln->g]; g.beta = m->w[ln->b]; }
-  return launch_gemm(t.bf16, epi, a, w, M, g, &out, resid, s);
+  const CUtensorMap* o = &out;
+  if (gemm_stage_rows() != 32) {                   // the same target through the map with the smaller store box
+    const CUtensorMap* from[6] = {&t.sX, &t.sHID, &t.sT, &t.sU, &t.sQKV, &t.sDQ};
+    const CUtensorMap* to[6] = {&t.gX, &t.gHID, &t.gT, &t.gU, &t.gQKV, &t.gDQ};
+    for (int i = 0; i < 6; ++i)
+      if (o == from[i]) { o = to[i]; g.stage_rows = gemm_stage_rows(); break; }
+  }
+  return launch_gemm(t.bf16, epi, a, w, M, g, o, resid, s);
 }
 
 // mkv: K/V tensor map with box dh x LK (one-tile kernel); mkv_unit: box dh x 128 (or dh x 96) for the pipelined kernel

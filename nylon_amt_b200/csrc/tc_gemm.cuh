@@ -65,13 +65,16 @@ struct GemmParams {
   int n_vel;
   int time_major;         // rows are (b, note, frame): permute back to [B, frame, note]
   int n_frame, n_note;
+  int stage_rows;         // rows of one epilogue store box (= box rows of map_o): 32 (default when 0), 16 or 8 -- smaller boxes leave
+                          // shared memory to a resident W / a deeper A ring; a warp then stores its 32 rows in 32 / stage_rows passes
   int debug_flags;        // experiments only (HFT_TC_DEBUG): 1 = skip the TMA stores, 2 = skip the epilogue arithmetic
 };
 
 // n_rows_w: W rows staged per CTA (n_tile, or n_tile / 2 in PAIR mode)
-__host__ __device__ constexpr size_t gemm_smem_bytes(int n_rows_w, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid) {
+__host__ __device__ constexpr size_t gemm_smem_bytes(int n_rows_w, int k_chunks, int w_resident, int a_stages, int w_stages, int x3, int has_resid,
+                                                     int stage_rows = 32) {
   size_t w = w_resident ? (size_t)n_rows_w * kBlockK * 2 * k_chunks * (x3 ? 2 : 1) : (size_t)w_stages * n_rows_w * kBlockK * 2;
-  return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + (size_t)kEpiWarps * kWarpStage /*store staging*/ +
+  return 1024 /*align*/ + w + (size_t)a_stages * kChunkA + (has_resid ? 8192 : 0) /*I64*/ + (size_t)kEpiWarps * stage_rows * 128 /*store staging*/ +
          kConstBytes + 512 /*barriers*/;
 }
 
@@ -92,7 +95,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint8_t* s_i64 = s_a + (size_t)p.a_stages * kChunkA;                   // 64 x 64 identity, K-major SW128 (only with a residual)
   const int parts = p.x3 ? 2 : 1;
   uint8_t* s_out = s_i64 + (p.has_resid ? 8192 : 0);                     // [8 warps][32 x 64] staging (x3: hi, then lo through the same block)
-  float* s_const = reinterpret_cast<float*>(s_out + (size_t)kEpiWarps * kWarpStage);   // bias[NT] | gamma[NT] | beta[NT]
+  const int stage_rows = p.stage_rows ? p.stage_rows : 32;
+  float* s_const = reinterpret_cast<float*>(s_out + (size_t)kEpiWarps * stage_rows * 128);   // bias[NT] | gamma[NT] | beta[NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_const) + kConstBytes);
   uint64_t* full_a = bars;               // [8]
   uint64_t* empty_a = bars + 8;          // [8]
@@ -272,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int wg = ew >> 2;                             // accumulator buffer (= tile parity) drained by this warpgroup
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* my_stage = s_out + (size_t)ew * kWarpStage;
+    uint8_t* my_stage = s_out + (size_t)ew * stage_rows * 128;
     const float* s_bias = s_const;
     const float* s_gamma = s_const + NT;
     const float* s_beta = s_const + 2 * NT;
@@ -281,19 +285,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // (one 4 KB block per warp: in split mode the lo half follows the hi half through it, which leaves the shared memory to the
     //  operand rings / a resident W; the TMA read of the block overlaps the arithmetic of the next one)
     auto store_block = [&](const uint32_t (&pk)[32], const uint32_t (&pl)[32], int col, int row0) {
-      uint8_t* dst = my_stage + lane * 128;
+      uint8_t* dst = my_stage + (lane & (stage_rows - 1)) * 128;
       for (int part = 0; part < parts; ++part) {
-        if (lane == 0) tma_store_wait_read();           // the previous store of this warp has read the staging block
-        __syncwarp();
+        for (int pass = 0; pass * stage_rows < 32; ++pass) {   // one pass with the default 32-row boxes
+          if (lane == 0) tma_store_wait_read();         // the previous store of this warp has read the staging block
+          __syncwarp();
+          if (lane / stage_rows == pass) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(dst + ((q ^ (lane & 7)) << 4)) =
-              part ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && !(p.debug_flags & 1)) {
-          tma_store_2d(&map_o, my_stage, col + (part ? p.out_lo_off : 0), row0);
-          tma_store_commit();
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(dst + ((q ^ (lane & 7)) << 4)) =
+                  part ? make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]) : make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.debug_flags & 1)) {
+            tma_store_2d(&map_o, my_stage, col + (part ? p.out_lo_off : 0), row0 + pass * stage_rows);
+            tma_store_commit();
+          }
         }
       }
     };
