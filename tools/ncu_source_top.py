@@ -1,9 +1,9 @@
 """Top stall locations of one kernel of an .ncu-rep captured with --import-source on.
-usage: ncu_source_top.py REP KERNEL_ID [N]"""
+usage: ncu_source_top.py REP KERNEL_ID|- [N]   ("-": the report holds one kernel)"""
 import csv, subprocess, sys
 rep, kid = sys.argv[1], sys.argv[2]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", ":::" + kid], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + ([] if kid == "-" else ["--kernel-id", ":::" + kid]), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
