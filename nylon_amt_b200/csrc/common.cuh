@@ -32,6 +32,19 @@ enum : int { HFT_OK = 0, HFT_ERR_ARG = 10001, HFT_ERR_UNSUPPORTED = 10002, HFT_E
 
 int num_sms();
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is per device; one process may drive
+// several GPUs even though the usual deployment is one process per GPU).
+#define HFT_SET_MAX_SMEM(fn, bytes)                                                                                   \
+  do {                                                                                                                \
+    static bool done_[64] = {};                                                                                       \
+    int dev_ = 0;                                                                                                     \
+    cudaGetDevice(&dev_);                                                                                             \
+    if (!done_[dev_ & 63]) {                                                                                          \
+      HFT_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));            \
+      done_[dev_ & 63] = true;                                                                                        \
+    }                                                                                                                 \
+  } while (0)
+
 #ifdef __CUDACC__
 // ---- mbarrier / bulk-copy PTX (sm_90+; UBLKCP in SASS) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -678,12 +678,10 @@ static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx
   cfg.numAttrs = 1;
   LaunchScope ls(HFT_KCLASS_GEMM, s);
   if (t.bf16) {
-    static bool set = false;
-    if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    HFT_SET_MAX_SMEM(ffn_kernel<true>, 227 * 1024);
     HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<true>, mx, w1.map64, w2.map2, sx, fp));
   } else {
-    static bool set = false;
-    if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    HFT_SET_MAX_SMEM(ffn_kernel<false>, 227 * 1024);
     HFT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<false>, mx, w1.map64, w2.map2, sx, fp));
   }
   return HFT_OK;
@@ -758,12 +756,10 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
       const unsigned grid = (unsigned)(fp.n_tiles < sms ? fp.n_tiles : sms);
       const size_t smem = sizeof(FrontSmem) + 1024;
       if (bf) {
-        static bool set = false;
-        if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(front_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        HFT_SET_MAX_SMEM(front_tc_kernel<true>, smem);
         front_tc_kernel<true><<<grid, kFrontThreads, smem, s>>>(t.sX3, fp);
       } else {
-        static bool set = false;
-        if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(front_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        HFT_SET_MAX_SMEM(front_tc_kernel<false>, smem);
         front_tc_kernel<false><<<grid, kFrontThreads, smem, s>>>(t.sX3, fp);
       }
     } else if (bf) front16_kernel<true, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);

@@ -100,8 +100,7 @@ static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int
   if (splits < 1) splits = 1;
   long long rps = ((M + splits - 1) / splits + DWR - 1) / DWR * DWR;
   splits = (M + rps - 1) / rps;
-  static bool set = false;
-  if (!set) { HFT_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM)); set = true; }
+  HFT_SET_MAX_SMEM(dw_gemm_kernel, DW_SMEM);
   LaunchScope ls(HFT_KCLASS_GEMM, s);
   dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), DWTHREADS, DW_SMEM, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
   return HFT_OK;
