@@ -189,3 +189,24 @@ def test_front_tensor_core_kernel_equals_cuda_core_filter(golden_dir, tmp_path, 
     print("front tc vs cuda-core, strided=%s: worst abs diff %.3e" % (strided, worst))
     assert all(np.isfinite(x).all() for x in a)
     assert worst <= 1e-3, worst
+
+
+_SWITCH_BASELINE = {}
+
+
+@pytest.mark.parametrize("switch", ["HFT_TC_FFN=0", "HFT_TC_PAIR=0", "HFT_TC_ATTN2=0", "HFT_TC_ATTN_PROBS=0", "HFT_TC_WRES=0", "HFT_TC_STAGE_ROWS=16",
+                                    "HFT_TC_STAGE_ROWS=8", "HFT_TC_WSTAGES=6"])
+def test_experiment_switches_select_equivalent_kernels(golden_dir, tmp_path, switch):
+    """Every alternative kernel kept behind an experiment switch ('Experiment switches') computes the same paper-size
+    fp16x3 forward as the default path: within 1e-3 abs of it on every output, and inside the 2e-3 budget against the golden."""
+    from test_gpu_forward import _golden_check, TOL_FP32
+    if "base" not in _SWITCH_BASELINE:
+        _SWITCH_BASELINE["base"] = _forward_in_subprocess(golden_dir, {}, str(tmp_path / "base.npz"), False)
+    base = _SWITCH_BASELINE["base"]
+    k, v = switch.split("=")
+    got = _forward_in_subprocess(golden_dir, {k: v}, str(tmp_path / "alt.npz"), False)
+    worst = max(float(np.abs(x - y).max()) for x, y in zip(got, base))
+    print(switch, "worst abs diff to the default path %.3e" % worst)
+    assert worst <= 1e-3, (switch, worst)
+    g = np.load(os.path.join(golden_dir, "hft_paper.npz"))
+    _golden_check([torch.from_numpy(x) for x in got], g, TOL_FP32)
