@@ -304,7 +304,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
         const float4* bp = reinterpret_cast<const float4*>(s_b2 + c * 32);
-        if (c == 0) shift = __uint_as_float(r[0]) + s_b2[0];
+        if (c == 0) {                                       // shift = mean of the row's first 32 values (close to the row mean: no cancellation)
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += __uint_as_float(r[j]) + s_b2[j];
+            shift = t * (1.f / 32.f);
+          }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 b4 = bp[q];

@@ -355,7 +355,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         continue;                                               // tempty already signalled
       } else if (EPI == EPI_LN) {
         // v = acc (+ residual already accumulated by the identity MMA) + bias; LayerNorm over the row of NT values.
-        // Pass 1 over TMEM: shifted one-pass statistics (shift = the row's first value, so E[d^2] - E[d]^2 does not cancel).
+        // Pass 1 over TMEM: shifted one-pass statistics (shift = the mean of the row's first 32 values, so E[d^2] - E[d]^2 does not cancel).
         float shift = 0.f, sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int c = 0; c < NT / 32; ++c) {
@@ -363,7 +363,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
           const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 32);
-          if (c == 0) shift = __uint_as_float(r[0]) + s_bias[0];
+          if (c == 0) {                                       // shift = mean of the row's first 32 values (close to the row mean: no cancellation)
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += __uint_as_float(r[j]) + s_bias[j];
+            shift = t * (1.f / 32.f);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = bp[j];
