@@ -112,6 +112,9 @@ typedef struct hft_dims {
 #define HFT_PREC_F16 2      /* fp16 operands on tcgen05 tensor cores (3 more mantissa bits than bf16) */
 #define HFT_PREC_F16X3 3    /* split fp16 operands (hi + lo): a*w = ah*wh + al*wh + ah*wl on tcgen05, ~22 mantissa bits:
                                the tensor-core path that meets the fp32 parity budget (2e-3) */
+#define HFT_PREC_MIXED 4    /* the 16-bit-class mode: split-fp16 storage with a per-GEMM plan of ONE or THREE products (single: every P V
+                               product outside encoder layer 0, the decoder's score products, time layers >= 1, both head GEMMs); meets
+                               the 16-bit parity budget (2e-2) on all eight head outputs; paper-size geometry (head_dim 64) only */
 
 int hft_model_create(hft_model** model, const hft_dims* dims);
 int hft_model_destroy(hft_model* model);
@@ -244,6 +247,24 @@ int hft_trainer_destroy(hft_trainer* trainer);
 int hft_train_forward_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
                                const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
                                const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream);
+
+/* The same step on the first `batch` <= capacity segments (the reference's DataLoader keeps the last, partial batch of an epoch:
+ * drop_last=False, m_training.py; every mean of the loss is taken over the rows actually present). */
+int hft_train_forward_backward_n(hft_trainer* trainer, int32_t batch, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                                 const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
+                                 const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream);
+
+/* The two halves of the step for a host that computes the loss itself (the reference does: train.py:90 `model(input_spec)` in train mode,
+ * :139-151 its own criteria, :157 `loss.backward()`, then a stock torch optimiser):
+ *   hft_train_forward   Model_SPEC2MIDI.forward with model.train(): fills the tape, applies dropout, writes the eight head outputs
+ *                       (onset/offset/mpe A and B as sigmoid probabilities, velocity A and B as raw logits; outputs->attention and the
+ *                       argmax members are ignored -- train.py never reads the attention);
+ *   hft_train_backward  dLoss/dParam from dLoss/d(output) of those eight tensors (out_grads: same struct, NULL member = zero gradient),
+ *                       for the LAST hft_train_forward on this trainer and the same spec_dev.  grads_dev is overwritten. */
+int hft_train_forward(hft_trainer* trainer, int32_t batch, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                      const hft_outputs* outputs, void* stream);
+int hft_train_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t, const hft_outputs* out_grads,
+                       float* grads_dev, void* stream);
 
 /* Dropout of the training forward (nn.Dropout(p) of the reference modules; the reference trains with p = 0.1, m_training.py).
  * Masks are counter based: element idx of site `site` is kept iff hash(seed, site, idx) >= p * 2^32 and scaled by 1 / (1 - p);

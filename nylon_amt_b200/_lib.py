@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhft_sm100.so")
 
-PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x3": 3}
+PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x3": 3, "mixed": 4}
 
 c_float_p = ctypes.c_void_p
 
@@ -70,6 +70,13 @@ SYMBOLS = {
     "hft_train_forward_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_train_forward_backward_n": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_train_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.POINTER(hft_outputs), ctypes.c_void_p]),
+    "hft_train_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(hft_outputs),
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "hft_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]),
     "hft_profile_enable": (ctypes.c_int, [ctypes.c_int]),

@@ -218,7 +218,29 @@ struct TcState {
   uint16_t* pos_rep = nullptr;                      // [11*128, H]: pos_embedding_freq[row % 88] (lcm(88,128) = 1408 rows)
   CUtensorMap mQKV_q, mQKV_kv, mDQ_q, mDQ_kv, mQ0;  // attention operands, box dh x {128, Lk}
   int cm() const { return x3 ? 2 : 1; }
+  // HFT_PREC_MIXED: the split (hi | lo) state with a per-site plan of one or three products (see SitePlan)
+  bool mixed = false;
 };
+
+// Products per site in HFT_PREC_MIXED.  Every tensor keeps the hi | lo layout; a "single" site multiplies only the hi halves.
+// The plan comes from the per-site sensitivity study on the seeded-weights fixture (tools/precision_plan.py, plan A): with these
+// weights the time stack amplifies upstream rounding ~20x, so everything that feeds time layer 0's scores keeps three products; single are
+//   * every P V product except encoder layer 0's,   * the decoder's score products (self and cross),
+//   * time layers >= 1 entirely (projections, FFN, both attention products),   * both head GEMMs.
+// Worst error of the CPU emulation over 5 signal families: 6.2e-3 on velocity B (budget 2e-2), 1.7e-3 on velocity A, <= 1.1e-3 on the probabilities.
+struct SitePlan {
+  bool lin = false;       // projections + FFN of the layer
+  bool scores = false;    // Q K^T
+  bool pv = false;        // P V
+};
+static SitePlan plan_for(const TcState& t, char kind, int layer) {   // kind: 'e' encoder, 'd' decoder (0 = layer zero), 't' time
+  SitePlan p;
+  if (!t.mixed) return p;
+  if (kind == 'e') { p.pv = layer > 0; }
+  else if (kind == 'd') { p.scores = true; p.pv = true; }
+  else { p.pv = true; if (layer > 0) { p.lin = true; p.scores = true; } }
+  return p;
+}
 
 struct TcBoth { TcState st[3]; };   // [0] = fp16, [1] = bf16, [2] = fp16 x3
 
@@ -440,7 +462,8 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   // W stays resident when this CTA's slice fits beside a >= 3-deep A ring, the identity block and the store staging
   // (measured r01, bf16 K = 256: resident W + 3 A slots 573 ms/h vs streamed W 665 ms/h); otherwise W chunks stream
   // through a ring of their own.
-  const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (gp.x3 ? 2 : 1);
+  const bool x3p = gp.x3 && !gp.single;
+  const size_t w_bytes = (size_t)n_rows_w * w.K * 2 * (x3p ? 2 : 1);
   const size_t w_chunk = (size_t)n_rows_w * kBlockK * 2;
   const int stage_rows = gp.stage_rows ? gp.stage_rows : 32;
   const size_t fixed = 1024 + (gp.has_resid ? 8192 : 0) + (size_t)kEpiWarps * stage_rows * 128 + kConstBytes + 512;
@@ -449,19 +472,19 @@ static int launch_gemm(bool bf16, int epi, const CUtensorMap& ma, const W16& w, 
   if (wres < 0) { const char* e = getenv("HFT_TC_WRES"); wres = (e && e[0] == '0') ? 0 : 1; }
   // split mode needs two A chunks (hi, lo) per k-chunk: below 4 slots the A stream starves (measured r01, pair K = 256: resident W +
   // 3 A slots 1 284 ms/h of GEMM vs streamed W + 6 A / 4 W slots 1 193 ms/h); single-product modes are fine with 3 (573 vs 665 ms/h)
-  gp.w_resident = (wres && w_bytes + fixed + (gp.x3 ? 4 : 3) * kChunkA <= budget) ? 1 : 0;
+  gp.w_resident = (wres && w_bytes + fixed + (x3p ? 4 : 3) * kChunkA <= budget) ? 1 : 0;
   static int wst = -1;                       // HFT_TC_WSTAGES: W ring depth for 16 KB chunks (experiments; default 4)
   if (wst < 0) { const char* e = getenv("HFT_TC_WSTAGES"); wst = e ? atoi(e) : 4; if (wst < 2 || wst > 8) wst = wst < 2 ? 2 : 8; }
   gp.w_stages = gp.w_resident ? 0 : (w_chunk <= 16384 ? wst : 2);
   const size_t w_smem = gp.w_resident ? w_bytes : gp.w_stages * w_chunk;
   long long a_st = (long long)(budget - fixed - w_smem) / kChunkA;
   gp.a_stages = a_st > 8 ? 8 : (int)a_st;
-  HFT_REQUIRE(gp.a_stages >= (gp.x3 ? 3 : 2), HFT_ERR_UNSUPPORTED, "tc gemm: no room for the operand rings (N tile %d, K %d)", w.n_tile, w.K);
+  HFT_REQUIRE(gp.a_stages >= (x3p ? 3 : 2), HFT_ERR_UNSUPPORTED, "tc gemm: no room for the operand rings (N tile %d, K %d)", w.n_tile, w.K);
   const int units_max = pair ? sms / 2 : sms;
   int units = (units_max / gp.n_tiles) * gp.n_tiles;
   if (units > gp.m_tiles * gp.n_tiles) units = gp.m_tiles * gp.n_tiles;
   const int grid = pair ? 2 * units : units;
-  const size_t smem = gemm_smem_bytes(n_rows_w, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, gp.x3, gp.has_resid, stage_rows);
+  const size_t smem = gemm_smem_bytes(n_rows_w, gp.k_chunks, gp.w_resident, gp.a_stages, gp.w_stages, x3p, gp.has_resid, stage_rows);
   HFT_REQUIRE(smem <= 227 * 1024, HFT_ERR_UNSUPPORTED, "tc gemm: %zu bytes of shared memory needed", smem);
   const CUtensorMap& o = mo ? *mo : ma;
   const CUtensorMap& r = mr ? *mr : ma;
@@ -549,6 +572,7 @@ static int launch_attn2(int heads, bool bf16, bool x3, int LK, const CUtensorMap
   ap.n_rounds = (int)((items + 1) / 2);
   ap.shared_kv = ap.q_tiles == 2 ? 1 : 0;
   ap.probs = a.probs;
+  ap.s_single = a.s_single; ap.pv_single = a.pv_single;
   HFT_REQUIRE(!ap.probs || LK == 256, HFT_ERR_UNSUPPORTED, "tc attention: probabilities are returned for 256-key sequences only");
   LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   if (x3) {
@@ -584,6 +608,7 @@ static int launch_attn_probs(int heads, bool bf16, bool x3, const CUtensorMap& m
   ap.scale_log2e = 1.4426950408889634f / sqrtf(64.f);
   ap.ctx = a.ctx; ap.ld_ctx = a.ld_ctx; ap.q_lo_off = a.q_lo_off; ap.kv_lo_off = a.kv_lo_off; ap.ctx_lo_off = a.ctx_lo_off;
   ap.probs = a.probs;
+  ap.s_single = a.s_single; ap.pv_single = a.pv_single;
   const long long items = n_seq * heads;
   HFT_REQUIRE(items < (1ll << 30) && a.lq <= 128 && a.lk == 256, HFT_ERR_UNSUPPORTED, "tc attention (probabilities): lq=%d lk=%d unsupported", a.lq, a.lk);
   ap.n_items = (int)items;
@@ -611,11 +636,12 @@ static bool attn2_probs_enabled() {
 
 // one projection launch: out[:, out_col0 ..] = epilogue(A * W^T); out_width = columns of the output tensor's hi block
 static int linear(TcState& t, cudaStream_t s, int epi, const CUtensorMap& a, const W16& w, long long M, const CUtensorMap& out, int out_col0,
-                  int out_width, const CUtensorMap* resid = nullptr, const LnW* ln = nullptr, Model* m = nullptr, int resid_period = 0) {
+                  int out_width, const CUtensorMap* resid = nullptr, const LnW* ln = nullptr, Model* m = nullptr, int resid_period = 0, bool single = false) {
   GemmParams g{};
   g.out_col0 = out_col0;
   g.resid_period = resid_period;
   g.x3 = t.x3 ? 1 : 0;
+  g.single = (t.x3 && single) ? 1 : 0;
   g.a_lo_off = w.K; g.w_lo_off = w.K; g.out_lo_off = out_width;
   if (ln) { g.gamma = m->w[ln->g]; g.beta = m->w[ln->b]; }
   const CUtensorMap* o = &out;
@@ -652,10 +678,12 @@ static bool ffn_fused_enabled(bool x3) {
 }
 static bool ffn_fusable(Model* m, const TcState& t, long long R) { return ffn_fused_enabled(t.x3) && m->H == kFfnH && m->P == kFfnP && R % (2 * kBlockM) == 0; }
 
-static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, long long R, const W16& w1, const W16& w2, const LnW& ln) {
+static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, long long R, const W16& w1, const W16& w2, const LnW& ln,
+                     bool single = false) {
   FfnParams fp{};
   fp.m_tiles = (int)(R / (2 * kBlockM));
   fp.x3 = t.x3 ? 1 : 0;
+  fp.single = (t.x3 && single) ? 1 : 0;
   fp.lo_off = m->H; fp.w1_lo_off = m->H; fp.w2_lo_off = m->P;
   fp.b1 = w1.bias; fp.b2 = w2.bias; fp.gamma = m->w[ln.g]; fp.beta = m->w[ln.b];
   static int slots_env = -1;
@@ -689,17 +717,18 @@ static int ffn_fused(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx
 
 // EncoderLayer (model_spec2midi.py:230-245) over S sequences of L tokens held in x [S*L, H] (16-bit, updated in place)
 static int encoder_layer_tc(Model* m, TcState& t, cudaStream_t s, const CUtensorMap& mx, const CUtensorMap& sx, const CUtensorMap& sqkv, const CUtensorMap& mq,
-                            const CUtensorMap& mkv, const CUtensorMap& mkv_unit, int LK, long long S, int L, const TcLayer& lw, const LnW& ln) {
+                            const CUtensorMap& mkv, const CUtensorMap& mkv_unit, int LK, long long S, int L, const TcLayer& lw, const LnW& ln, SitePlan sp = SitePlan()) {
   const int H = m->H, P = m->P;
   const long long R = S * L;
-  HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, sqkv, 0, 3 * H));
+  HFT_TRY(linear(t, s, EPI_STORE, mx, lw.qkv, R, sqkv, 0, 3 * H, nullptr, nullptr, nullptr, 0, sp.lin));
   AttnParams a{};
   a.lq = L; a.lk = L; a.q_seq_rows = L; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = nullptr;
+  a.s_single = sp.scores; a.pv_single = sp.pv;
   HFT_TRY(attention(m, t, s, LK, mq, mkv, mkv_unit, a, S, 3 * H));
-  HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_o(ctx))
-  if (ffn_fusable(m, t, R)) return ffn_fused(m, t, s, mx, sx, R, lw.w1, lw.w2, ln);   // x = LN(x + fc_2(relu(fc_1(x)))), hidden kept in TMEM
-  HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P));
-  HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m));          // x = LN(x + fc_2(relu(fc_1(x))))
+  HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.o, R, sx, 0, H, &mx, &ln, m, 0, sp.lin));          // x = LN(x + fc_o(ctx))
+  if (ffn_fusable(m, t, R)) return ffn_fused(m, t, s, mx, sx, R, lw.w1, lw.w2, ln, sp.lin);   // x = LN(x + fc_2(relu(fc_1(x)))), hidden kept in TMEM
+  HFT_TRY(linear(t, s, EPI_RELU, mx, lw.w1, R, t.sHID, 0, P, nullptr, nullptr, nullptr, 0, sp.lin));
+  HFT_TRY(linear(t, s, EPI_LN, t.mHID, lw.w2, R, sx, 0, H, &mx, &ln, m, 0, sp.lin));          // x = LN(x + fc_2(relu(fc_1(x))))
   return HFT_OK;
 }
 
@@ -729,13 +758,15 @@ static TcState& state_for(Model* m, int precision) {
     b->st[2].x3 = true;
     m->tc = b;
   }
-  return reinterpret_cast<TcBoth*>(m->tc)->st[precision == HFT_PREC_BF16 ? 1 : precision == HFT_PREC_F16X3 ? 2 : 0];
+  return reinterpret_cast<TcBoth*>(m->tc)->st[precision == HFT_PREC_BF16 ? 1 : (precision == HFT_PREC_F16X3 || precision == HFT_PREC_MIXED) ? 2 : 0];
 }
 
 int forward_tc(Model* m, int precision, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s) {
   if (B == 0) return HFT_OK;
   HFT_REQUIRE(m->H == 64 || m->H == 128 || m->H == 256, HFT_ERR_UNSUPPORTED, "tensor-core path supports hid_dim 64 / 128 / 256 (got %d)", m->H);
   TcState& t = state_for(m, precision);
+  t.mixed = precision == HFT_PREC_MIXED;          // shares weights and workspace with HFT_PREC_F16X3; only the per-site product counts differ
+  HFT_REQUIRE(!t.mixed || (m->dh == 64 && attn2_enabled()), HFT_ERR_UNSUPPORTED, "HFT_PREC_MIXED is built for head_dim 64 (the pipelined attention kernels)");
   const bool bf = t.bf16;
   if (!t.weights_ready) HFT_TRY(prepare_weights(m, t, s));
   HFT_TRY(ensure_ws(m, t, B > m->max_batch ? B : m->max_batch));
@@ -766,7 +797,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else front16_kernel<false, 65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, t.x3, t.X);
   }
   for (size_t l = 0; l < m->enc.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.sX, t.sQKV, t.mQKV_q, t.mQKV_kv, t.mQKV_q, 256, Se, NB, t.enc[l], m->enc[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mX, t.sX, t.sQKV, t.mQKV_q, t.mQKV_kv, t.mQKV_q, 256, Se, NB, t.enc[l], m->enc[l].ln, plan_for(t, 'e', (int)l)));
 
   const int n_cross = 1 + (int)m->dec.size();
   auto ffn = [&](const TcDecLayer& lw, const LnW& ln) -> int {
@@ -779,6 +810,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     HFT_TRY(linear(t, s, EPI_STORE, t.mX, lw.ca_kv, Re, t.sQKV, H, 3 * H));   // K | V of the 256-bin memory at columns [H, 3H)
     AttnParams a{};
     a.lq = NN; a.lk = NB; a.k_col0 = H; a.v_col0 = 2 * H; a.probs = probs; a.q_col0 = 0;
+    { const SitePlan sp = plan_for(t, 'd', 0); a.s_single = sp.scores; a.pv_single = sp.pv; }
     if (zero) {
       a.q_seq_rows = 0;
       HFT_TRY(attention(m, t, s, 256, t.mQ0, t.mQKV_kv, t.mQKV_q, a, Se, H));
@@ -800,6 +832,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     HFT_TRY(linear(t, s, EPI_STORE, t.mT, lw.sa_qkv, Rd, t.sDQ, 0, 3 * H));
     AttnParams a{};
     a.lq = NN; a.lk = NN; a.q_seq_rows = NN; a.q_col0 = 0; a.k_col0 = H; a.v_col0 = 2 * H;
+    { const SitePlan sp = plan_for(t, 'd', (int)l + 1); a.s_single = sp.scores; a.pv_single = sp.pv; }
     HFT_TRY(attention(m, t, s, 96, t.mDQ_q, t.mDQ_kv, t.mDQ_kv, a, Se, 3 * H));
     HFT_TRY(linear(t, s, EPI_LN, t.mCTX, lw.sa_o, Rd, t.sT, 0, H, &t.mT, &ln, m));
     HFT_TRY(cross(lw, ln, false, ((int)l + 2 == n_cross) ? o->attention : nullptr));
@@ -809,7 +842,7 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
   {
     GemmParams g{};
     g.onset = o->onset_A; g.offset = o->offset_A; g.mpe = o->mpe_A; g.velocity = o->velocity_A; g.vel_argmax = o->velocity_A_argmax; g.n_vel = V; g.time_major = 0; g.n_frame = F; g.n_note = NN;
-    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
+    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H; g.single = t.mixed ? 1 : 0;
     HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mT, t.headA, Rd, g, nullptr, nullptr, s));
   }
   {
@@ -819,11 +852,11 @@ int forward_tc(Model* m, int precision, const float* spec, long long sb, long lo
     else time_relayout16_kernel<false><<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(t.T, m->w[m->pos_time], sqrtH, F, NN, H, t.x3, total8, t.U);
   }
   for (size_t l = 0; l < m->tim.size(); ++l)
-    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln));
+    HFT_TRY(encoder_layer_tc(m, t, s, t.mU, t.sU, t.sDQ, t.mDQ_q, t.mDQ_q, t.mDQ_q, 128, (long long)B * NN, F, t.tim[l], m->tim[l].ln, plan_for(t, 't', (int)l)));
   {
     GemmParams g{};
     g.onset = o->onset_B; g.offset = o->offset_B; g.mpe = o->mpe_B; g.velocity = o->velocity_B; g.vel_argmax = o->velocity_B_argmax; g.n_vel = V; g.time_major = 1; g.n_frame = F; g.n_note = NN;
-    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H;
+    g.x3 = t.x3; g.a_lo_off = H; g.w_lo_off = H; g.single = t.mixed ? 1 : 0;
     HFT_TRY(launch_gemm(bf, EPI_HEADS, t.mU, t.headB, Rd, g, nullptr, nullptr, s));
   }
   HFT_CHECK_CUDA(cudaGetLastError());

@@ -266,7 +266,7 @@ extern "C" int hft_forward(hft_model* model, int precision, const float* spec_de
   Model* m = reinterpret_cast<Model*>(model);
   HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_forward: call hft_model_set_weights first");
   HFT_REQUIRE(batch >= 0 && (spec_dev || batch == 0), HFT_ERR_ARG, "hft_forward: bad batch / spec");
-  HFT_REQUIRE(precision == HFT_PREC_F32 || precision == HFT_PREC_BF16 || precision == HFT_PREC_F16 || precision == HFT_PREC_F16X3, HFT_ERR_ARG, "hft_forward: unknown precision %d", precision);
+  HFT_REQUIRE(precision == HFT_PREC_F32 || precision == HFT_PREC_BF16 || precision == HFT_PREC_F16 || precision == HFT_PREC_F16X3 || precision == HFT_PREC_MIXED, HFT_ERR_ARG, "hft_forward: unknown precision %d", precision);
   reset_launch_count();
   cudaStream_t s = (cudaStream_t)stream;
   const long long fn = (long long)m->nframe * m->nnote;

@@ -30,6 +30,7 @@ struct AttnParams {
   int q_lo_off, kv_lo_off;   // x3: column distance between the hi and lo halves of the Q tensor / the K,V tensor
   int ctx_lo_off;         // x3: same for ctx
   int tma_store;          // 1: ctx tile written by TMA (needs lq % 128 == 0 and dh == 64)
+  int s_single, pv_single;   // mixed-precision plan (x3 layout): scores / P V as ONE product (tc_attn2.cuh kernels only; this file's kernel ignores them)
 };
 
 template <int DH, int LK, bool X3 = false>

@@ -41,6 +41,8 @@ struct Attn2Params {
   int n_rounds;           // ceil(n_items / 2)
   int shared_kv;          // 1: q_tiles == 2, both warpgroups use the same K / V half-tiles
   float* probs;           // PROBS: fp32 [n_seq, heads, lq, lk]
+  int s_single;           // X3 layout, mixed-precision plan: S = Qh Kh only (the lo halves of Q and K are not loaded)
+  int pv_single;          // X3 layout, mixed-precision plan: O = Ph Vh only (the lo half of V is not loaded; P is still written hi | lo)
 };
 
 template <int DH, bool X3>
@@ -114,13 +116,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
     if (lane == 0) {
       int slot = 0;
       uint32_t ph = 0, qph[2] = {0, 0};
+      const int k_parts = (X3 && !p.s_single) ? 2 : 1, v_parts = (X3 && !p.pv_single) ? 2 : 1;   // operand halves actually multiplied
       auto load_kv = [&](int tile, int col0, int half) {                  // one K or V half-tile into the next ring slot
         int seq, head, qt;
         decode(tile, seq, head, qt);
+        const int np = col0 == p.v_col0 ? v_parts : k_parts;
         mbar_wait(&ring_empty[slot], ph ^ 1);
-        mbar_expect_tx(&ring_full[slot], (uint32_t)(NKEY * DH * 2 * kParts));
-#pragma unroll
-        for (int part = 0; part < kParts; ++part)
+        mbar_expect_tx(&ring_full[slot], (uint32_t)(NKEY * DH * 2 * np));
+        for (int part = 0; part < np; ++part)
           tma_load_2d(s_ring + (size_t)slot * L::slot_bytes + part * L::tile_bytes, &map_kv, part * p.kv_lo_off + col0 + head * DH, seq * p.lk + half * NKEY,
                       &ring_full[slot]);
         if (++slot == NS) { slot = 0; ph ^= 1; }
@@ -129,9 +132,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         int seq, head, qt;
         decode(tile, seq, head, qt);
         mbar_wait(&q_empty[w], qph[w] ^ 1);
-        mbar_expect_tx(&q_full[w], (uint32_t)(L::tile_bytes * kParts));
-#pragma unroll
-        for (int part = 0; part < kParts; ++part)
+        mbar_expect_tx(&q_full[w], (uint32_t)(L::tile_bytes * k_parts));
+        for (int part = 0; part < k_parts; ++part)
           tma_load_2d(s_q + (size_t)w * L::q_bytes + part * L::tile_bytes, &map_q, part * p.q_lo_off + p.q_col0 + head * DH, seq * p.q_seq_rows + qt * 128, &q_full[w]);
         qph[w] ^= 1;
       };
@@ -171,8 +173,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
       auto issue_s = [&](int w, int kslot) {                                // S(w)[128, NKEY] = Q(w) K^T;  x3: Qh Kh + Ql Kh + Qh Kl
         const uint32_t qa = smem_u32(s_q + (size_t)w * L::q_bytes), ka = smem_u32(s_ring + (size_t)kslot * L::slot_bytes);
         uint32_t acc = 0;
-#pragma unroll
-        for (int part = 0; part < (X3 ? 3 : 1); ++part) {
+        const int n_prod = (X3 && !p.s_single) ? 3 : 1;
+        for (int part = 0; part < n_prod; ++part) {
           const uint32_t qp = qa + (part == 1 ? L::tile_bytes : 0), kp = ka + (part == 2 ? L::tile_bytes : 0);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) {
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         const uint32_t va = smem_u32(s_ring + (size_t)vslot * L::slot_bytes);
         const uint32_t tp = tmem_base + w * 256;
         uint32_t acc = 0;
-#pragma unroll
-        for (int part = 0; part < (X3 ? 3 : 1); ++part) {
+        const int n_prod = (X3 && !p.pv_single) ? 3 : 1;
+        for (int part = 0; part < n_prod; ++part) {
           const uint32_t vp = va + (part == 2 ? L::tile_bytes : 0);
 #pragma unroll
           for (int k = 0; k < NKEY / 16; ++k) {
@@ -449,17 +451,17 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
       uint32_t ph = 0, qph = 0;
       for (int tile = blockIdx.x; tile < p.n_items; tile += gridDim.x) {
         const int head = tile % p.heads, seq = tile / p.heads;
+        const int k_parts = (X3 && !p.s_single) ? 2 : 1, v_parts = (X3 && !p.pv_single) ? 2 : 1;
         mbar_wait(q_empty, qph ^ 1);
-        mbar_expect_tx(q_full, (uint32_t)L::q_bytes);
-#pragma unroll
-        for (int part = 0; part < kParts; ++part)
+        mbar_expect_tx(q_full, (uint32_t)(128 * 64 * 2 * k_parts));
+        for (int part = 0; part < k_parts; ++part)
           tma_load_2d(s_q + part * (128 * 64 * 2), &map_q, part * p.q_lo_off + p.q_col0 + head * DH, seq * p.q_seq_rows, q_full);
         qph ^= 1;
         for (int kv = 0; kv < 2; ++kv) {                                  // K, then V
+          const int np = kv ? v_parts : k_parts;
           mbar_wait(&ring_empty[slot], ph ^ 1);
-          mbar_expect_tx(&ring_full[slot], (uint32_t)L::slot_bytes);
-#pragma unroll
-          for (int part = 0; part < kParts; ++part)
+          mbar_expect_tx(&ring_full[slot], (uint32_t)(L::kv_part * np));
+          for (int part = 0; part < np; ++part)
             tma_load_2d(s_ring + (size_t)slot * L::slot_bytes + part * L::kv_part, &map_kv, part * p.kv_lo_off + (kv ? p.v_col0 : p.k_col0) + head * DH, seq * p.lk,
                         &ring_full[slot]);
           if (++slot == 2) { slot = 0; ph ^= 1; }
@@ -486,8 +488,8 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
         fence_after_sync();
         const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_ring + (size_t)ks * L::slot_bytes);
         uint32_t acc = 0;
-#pragma unroll
-        for (int part = 0; part < (X3 ? 3 : 1); ++part) {                 // S = Qh Kh + Ql Kh + Qh Kl
+        const int s_prod = (X3 && !p.s_single) ? 3 : 1, pv_prod = (X3 && !p.pv_single) ? 3 : 1;
+        for (int part = 0; part < s_prod; ++part) {                       // S = Qh Kh + Ql Kh + Qh Kl
           const uint32_t qp = qa + (part == 1 ? 128 * 64 * 2 : 0), kp = ka + (part == 2 ? L::kv_part : 0);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) {
@@ -503,8 +505,7 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
         fence_after_sync();
         const uint32_t va = smem_u32(s_ring + (size_t)vs * L::slot_bytes);
         acc = 0;
-#pragma unroll
-        for (int part = 0; part < (X3 ? 3 : 1); ++part) {                 // O = Ph Vh + Pl Vh + Ph Vl, A = P from TMEM
+        for (int part = 0; part < pv_prod; ++part) {                      // O = Ph Vh + Pl Vh + Ph Vl, A = P from TMEM
           const uint32_t vp = va + (part == 2 ? L::kv_part : 0);
 #pragma unroll
           for (int k = 0; k < LK / 16; ++k) {

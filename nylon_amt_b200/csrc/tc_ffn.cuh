@@ -22,7 +22,9 @@ namespace tc {
 
 struct FfnParams {
   int m_tiles;              // M / 256 (pair tiles)
-  int x3;
+  int x3;                   // split (hi | lo) layout of x / y / W1 / W2
+  int single;               // x3 layout, single product: only x_hi W1_hi and P_hi W2_hi are accumulated (the lo halves of W1 / W2 are not loaded);
+                            // the residual still adds x_hi + x_lo and y is stored hi | lo
   int lo_off;               // column distance between the hi and lo halves of x / y (= hid_dim)
   int w1_lo_off, w2_lo_off; // same for W1 ([pf, 2 hid]) and W2 ([hid, 2 pf])
   const float* b1;          // [pf]
@@ -48,6 +50,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int parts = p.x3 ? 2 : 1;
+  const bool x3p = p.x3 && !p.single;                                    // three products
+  const int wparts = x3p ? 2 : 1;                                        // W1 / W2 halves streamed
   const int kFfnSlots = p.slots > 0 ? p.slots : ffn_slots(p.x3);   // p.slots < default: ring-depth experiment (HFT_TC_FFN_SLOTS)
   uint8_t* s_x = smem;                                                   // [parts][KC] chunks of 128 x 64
   uint8_t* s_ring = s_x + (size_t)parts * kFfnKC * kChunkA;              // [slots] x 16 KB
@@ -122,7 +126,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         for (int j = 0; j < kFfnNJ; ++j) {
           // GEMM1_j operands: per pair of k-chunks W1 hi, then W1 lo (64 rows of this CTA's half, 2 x 64 columns per slot)
           for (int u = 0; u < kFfnKC / 2; ++u)
-            for (int part = 0; part < parts; ++part) {
+            for (int part = 0; part < wparts; ++part) {
               uint8_t* dst = ring_next(2 * 8192);
               for (int h = 0; h < 2; ++h)
                 tma_load_2d_2cta(dst + h * 8192, &map_w1, part * p.w1_lo_off + (2 * u + h) * 64, j * kFfnJB + (int)rank * 64, map_to_rank(&rfull[slot], 0));
@@ -132,14 +136,14 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
           const int jj = j - 1;
           if (jj >= 0)
             for (int kc2 = 0; kc2 < 2; ++kc2)
-              for (int part = 0; part < parts; ++part) {
+              for (int part = 0; part < wparts; ++part) {
                 uint8_t* dst = ring_next(16384);
                 tma_load_2d_2cta(dst, &map_w2, part * p.w2_lo_off + jj * kFfnJB + kc2 * 64, (int)rank * 128, map_to_rank(&rfull[slot], 0));
                 ring_adv();
               }
         }
         for (int kc2 = 0; kc2 < 2; ++kc2)                                 // GEMM2 of the last block
-          for (int part = 0; part < parts; ++part) {
+          for (int part = 0; part < wparts; ++part) {
             uint8_t* dst = ring_next(16384);
             tma_load_2d_2cta(dst, &map_w2, part * p.w2_lo_off + (kFfnNJ - 1) * kFfnJB + kc2 * 64, (int)rank * 128, map_to_rank(&rfull[slot], 0));
             ring_adv();
@@ -177,7 +181,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           const int sh = take();
           const uint32_t wh = smem_u32(s_ring + (size_t)sh * kFfnSlot);
-          for (int part = 0; part < parts; ++part)                       // Ph W2h, Pl W2h
+          for (int part = 0; part < wparts; ++part)                      // Ph W2h, Pl W2h
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int ks = kc2 * 4 + k;
@@ -185,7 +189,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
               umma_f16_ts_2cta(tmem_base + kYCol, tp + pcol, make_sdesc(wh + k * 32, 16, 1024, kSwz128), id2, 1u);
             }
           umma_commit_2cta(&rempty[sh]);
-          if (p.x3) {
+          if (x3p) {
             const int sl = take();
             const uint32_t wl = smem_u32(s_ring + (size_t)sl * kFfnSlot);
 #pragma unroll
@@ -222,10 +226,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             for (int h = 0; h < 2; ++h) {
               const int kc = 2 * u + h;
               ss4(d, smem_u32(s_x + (size_t)kc * kChunkA), wh + h * 8192, id1, acc);                       // xh W1h
-              if (p.x3) ss4(d, smem_u32(s_x + (size_t)(kFfnKC + kc) * kChunkA), wh + h * 8192, id1, acc);  // xl W1h
+              if (x3p) ss4(d, smem_u32(s_x + (size_t)(kFfnKC + kc) * kChunkA), wh + h * 8192, id1, acc);   // xl W1h
             }
             umma_commit_2cta(&rempty[sh]);
-            if (p.x3) {
+            if (x3p) {
               const int sl = take();
               const uint32_t wl = smem_u32(s_ring + (size_t)sl * kFfnSlot);
               for (int h = 0; h < 2; ++h) ss4(d, smem_u32(s_x + (size_t)(2 * u + h) * kChunkA), wl + h * 8192, id1, acc);   // xh W1l

@@ -50,7 +50,9 @@ struct GemmParams {
   int w_stages;           // depth of the W ring (n_tile x 64 slots; 0 when W is resident)
   int has_resid;          // EPI_LN: residual tile added through the identity MMA
   int resid_period;       // > 0: residual row tile index = m_tile % resid_period (constant pitch-query table)
-  int x3;                 // split-operand mode (A/W/out/resid are [rows, 2*cols]: hi | lo)
+  int x3;                 // split-operand LAYOUT (A/W/out/resid are [rows, 2*cols]: hi | lo)
+  int single;             // x3 layout, but only the A_hi W_hi product is accumulated (mixed-precision plan): the lo halves of A and W are
+                          // neither loaded nor multiplied; the output (and the residual) keep both halves
   int out_col0;           // first output column inside the output tensor
   int a_lo_off, w_lo_off, out_lo_off;   // x3: column distance between the hi and lo halves of A / W / out
   const float* bias;      // [N]
@@ -89,7 +91,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr uint32_t kCtas = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int kc_w = p.k_chunks * (p.x3 ? 2 : 1);                         // W chunks held when resident
+  const bool x3p = p.x3 && !p.single;                                    // three products (A_hi W_hi + A_lo W_hi + A_hi W_lo)
+  const int kc_w = p.k_chunks * (x3p ? 2 : 1);                           // W chunks held when resident
   uint8_t* s_w = smem;                                                   // resident W: [kc_w][n_tile x 64]; else the W ring
   uint8_t* s_a = s_w + (p.w_resident ? (size_t)kc_w * w_chunk : (size_t)p.w_stages * w_chunk);   // A ring: a_stages x 16 KB
   uint8_t* s_i64 = s_a + (size_t)p.a_stages * kChunkA;                   // 64 x 64 identity, K-major SW128 (only with a residual)
@@ -182,7 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           if (!p.w_resident) load_w(kc * kBlockK);
           load_a(&map_a, kc * kBlockK, row_tile(mt) * kBlockM);
-          if (p.x3) {
+          if (x3p) {
             load_a(&map_a, p.a_lo_off + kc * kBlockK, row_tile(mt) * kBlockM);
             if (!p.w_resident) load_w(p.w_lo_off + kc * kBlockK);
           }
@@ -241,7 +244,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const uint32_t wh = p.w_resident ? smem_u32(s_w + (size_t)kc * w_chunk) : wait_w();
           const uint32_t ah = wait_a();
           mma4(d_tmem, ah, wh, idesc);
-          if (!p.x3) {
+          if (!x3p) {
             free_a();
             if (!p.w_resident) free_w();
           } else {

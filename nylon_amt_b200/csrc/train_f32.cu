@@ -33,7 +33,8 @@ struct DecTape {
 
 struct Trainer {
   Model* m = nullptr;
-  int B = 0;
+  int B = 0;                     // capacity: the tape is sized for B segments
+  int Bc = 0;                    // segments of the current step (<= B: the last batch of an epoch may be partial, train.py:72 with drop_last=False)
   float* arena = nullptr;
   size_t arena_bytes = 0;
   std::vector<LayerTape> enc, tim;
@@ -305,7 +306,7 @@ static int pack_heads(Trainer& t, cudaStream_t s) {
 
 static int train_forward(Trainer& t, const float* spec, long long sb, long long sbin, long long st, cudaStream_t s) {
   Model* m = t.m;
-  const int B = t.B, H = m->H, P = m->P, F = m->nframe, NB = m->nbin, NN = m->nnote;
+  const int B = t.Bc, H = m->H, P = m->P, F = m->nframe, NB = m->nbin, NN = m->nnote;
   const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
   const float sqrtH = sqrtf((float)H);
   float* tmp = t.gX;                                      // scratch [Re, H] (the gradient buffers are idle during the forward)
@@ -366,7 +367,7 @@ static int train_forward(Trainer& t, const float* spec, long long sb, long long 
 static int heads_bwd(Trainer& t, cudaStream_t s, int which, const float* x, float* gx, bool accum, float* G) {
   Model* m = t.m;
   const int H = m->H;
-  const long long Rd = (long long)t.B * m->nframe * m->nnote;
+  const long long Rd = (long long)t.Bc * m->nframe * m->nnote;
   const int* idx = which == 0 ? m->head_freq : m->head_time;
   HFT_CHECK_CUDA(cudaMemsetAsync(t.g_head_w, 0, (size_t)t.NP * H * sizeof(float), s));
   HFT_CHECK_CUDA(cudaMemsetAsync(t.g_head_b, 0, (size_t)t.NP * sizeof(float), s));
@@ -390,28 +391,46 @@ static int dec_ffn_bwd(Trainer& t, cudaStream_t s, DecTape& D, const DecLayerW& 
   return HFT_OK;
 }
 
-static int train_backward(Trainer& t, const float* spec, long long sb, long long sbin, long long st, const float* y_on, const float* y_off, const float* y_mpe,
-                          const long long* y_vel, float wA, float wB, float* loss, float* G, cudaStream_t s) {
+// Where dL/dlogits comes from: the library's own 8-term loss (train.py:139-151; hft_train_forward_backward) or the gradients autograd hands
+// back for the eight head outputs (hft_train_backward: the host computed the loss itself from the tensors hft_train_forward returned).
+struct GradSource {
+  const float *y_on = nullptr, *y_off = nullptr, *y_mpe = nullptr;
+  const long long* y_vel = nullptr;
+  float wA = 1.f, wB = 1.f;
+  float* loss = nullptr;
+  const hft_outputs* g = nullptr;          // non-NULL: output gradients (any member may be NULL = zero gradient)
+};
+
+static void head_logit_grads(Trainer& t, cudaStream_t s, int which, const GradSource& gs) {
   Model* m = t.m;
-  const int B = t.B, H = m->H, F = m->nframe, NB = m->nbin, NN = m->nnote, V = m->nvel;
+  const int F = m->nframe, NN = m->nnote, V = m->nvel;
+  const long long Rd = (long long)t.Bc * F * NN;
+  const float* logits = which ? t.logits_b : t.logits_a;
+  LaunchScope ls(HFT_KCLASS_HEADS, s);
+  if (gs.g) {
+    const hft_outputs* g = gs.g;
+    heads_outgrad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(logits, t.NP, V, F, NN, Rd, which != 0, which ? g->onset_B : g->onset_A, which ? g->offset_B : g->offset_A,
+                                                                  which ? g->mpe_B : g->mpe_A, which ? g->velocity_B : g->velocity_A, t.gLOG);
+  } else {
+    loss_grad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(logits, t.NP, V, F, NN, Rd, which != 0, gs.y_on, gs.y_off, gs.y_mpe, gs.y_vel, which ? gs.wB : gs.wA, t.gLOG, gs.loss);
+  }
+}
+
+static int train_backward(Trainer& t, const float* spec, long long sb, long long sbin, long long st, const GradSource& gs, float* G, cudaStream_t s) {
+  Model* m = t.m;
+  const int B = t.Bc, H = m->H, F = m->nframe, NB = m->nbin, NN = m->nnote;
   const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
   const float sqrtH = sqrtf((float)H);
-  HFT_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  if (gs.loss) HFT_CHECK_CUDA(cudaMemsetAsync(gs.loss, 0, sizeof(float), s));
   // ---- heads B + time stack ----
-  {
-    LaunchScope ls(HFT_KCLASS_HEADS, s);
-    loss_grad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t.logits_b, t.NP, V, F, NN, Rd, true, y_on, y_off, y_mpe, y_vel, wB, t.gLOG, loss);
-  }
+  head_logit_grads(t, s, 1, gs);
   HFT_TRY(heads_bwd(t, s, 1, t.u_out, t.gU, false, G));
   for (int l = (int)m->tim.size() - 1; l >= 0; --l)
     HFT_TRY(enc_layer_bwd(t, s, t.tim[l], (long long)B * NN, F, m->tim[l], m->tim_qkv[l], t.gU, t.gDQ, t.gCTX, t.gHID, G, t.site_time(l)));
   dropout_inplace(s, t.gU, Rd * H, t.drop(t.site_time_emb()));                           // back through the time-embedding dropout
   colsum(s, t.gU, (long long)B * NN, (long long)F * H, gof(m, G, m->pos_time));          // pos_embedding_time
   // ---- heads A + re-layout ----
-  {
-    LaunchScope ls(HFT_KCLASS_HEADS, s);
-    loss_grad_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t.logits_a, t.NP, V, F, NN, Rd, false, y_on, y_off, y_mpe, y_vel, wA, t.gLOG, loss);
-  }
+  head_logit_grads(t, s, 0, gs);
   HFT_TRY(heads_bwd(t, s, 0, t.t_out, t.gT, false, G));
   {
     LaunchScope ls(HFT_KCLASS_NORM, s);
@@ -575,12 +594,65 @@ extern "C" int hft_train_forward_backward(hft_trainer* trainer, const float* spe
   HFT_REQUIRE(trainer && spec_dev && label_onset_dev && label_offset_dev && label_mpe_dev && label_velocity_dev && loss_dev && grads_dev, HFT_ERR_ARG,
               "hft_train_forward_backward: NULL argument");
   Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  return hft_train_forward_backward_n(trainer, t->B, spec_dev, stride_b, stride_bin, stride_t, label_onset_dev, label_offset_dev, label_mpe_dev, label_velocity_dev,
+                                      weight_A, weight_B, loss_dev, grads_dev, stream);
+}
+
+extern "C" int hft_train_forward_backward_n(hft_trainer* trainer, int32_t batch, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                                            const float* label_onset_dev, const float* label_offset_dev, const float* label_mpe_dev,
+                                            const int64_t* label_velocity_dev, float weight_A, float weight_B, float* loss_dev, float* grads_dev, void* stream) {
+  HFT_REQUIRE(trainer && spec_dev && label_onset_dev && label_offset_dev && label_mpe_dev && label_velocity_dev && loss_dev && grads_dev, HFT_ERR_ARG,
+              "hft_train_forward_backward: NULL argument");
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  HFT_REQUIRE(batch >= 1 && batch <= t->B, HFT_ERR_ARG, "hft_train_forward_backward: batch %d outside [1, %d] (the capacity given to hft_trainer_create)", batch, t->B);
+  t->Bc = batch;
   cudaStream_t s = (cudaStream_t)stream;
   reset_launch_count();
   HFT_CHECK_CUDA(cudaMemsetAsync(grads_dev, 0, (size_t)hft_model_param_floats(reinterpret_cast<hft_model*>(t->m)) * sizeof(float), s));
   HFT_TRY(train_forward(*t, spec_dev, stride_b, stride_bin, stride_t, s));
-  return train_backward(*t, spec_dev, stride_b, stride_bin, stride_t, label_onset_dev, label_offset_dev, label_mpe_dev,
-                        reinterpret_cast<const long long*>(label_velocity_dev), weight_A, weight_B, loss_dev, grads_dev, s);
+  GradSource gs;
+  gs.y_on = label_onset_dev; gs.y_off = label_offset_dev; gs.y_mpe = label_mpe_dev; gs.y_vel = reinterpret_cast<const long long*>(label_velocity_dev);
+  gs.wA = weight_A; gs.wB = weight_B; gs.loss = loss_dev;
+  return train_backward(*t, spec_dev, stride_b, stride_bin, stride_t, gs, grads_dev, s);
+}
+
+// Train-mode forward on its own (model(input_spec) of train.py:90 with model.train()): fills the tape and writes the eight head outputs
+// (sigmoid probabilities / raw velocity logits, the layouts of hft_outputs; attention and the argmax members are ignored).
+extern "C" int hft_train_forward(hft_trainer* trainer, int32_t batch, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
+                                 const hft_outputs* outputs, void* stream) {
+  HFT_REQUIRE(trainer && spec_dev && outputs, HFT_ERR_ARG, "hft_train_forward: NULL argument");
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  HFT_REQUIRE(batch >= 1 && batch <= t->B, HFT_ERR_ARG, "hft_train_forward: batch %d outside [1, %d]", batch, t->B);
+  t->Bc = batch;
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_launch_count();
+  HFT_TRY(train_forward(*t, spec_dev, stride_b, stride_bin, stride_t, s));
+  Model* m = t->m;
+  const long long Rd = (long long)batch * m->nframe * m->nnote;
+  {
+    LaunchScope ls(HFT_KCLASS_HEADS, s);
+    heads_out_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t->logits_a, t->NP, m->nvel, m->nframe, m->nnote, Rd, false, outputs->onset_A, outputs->offset_A, outputs->mpe_A,
+                                                              outputs->velocity_A);
+    heads_out_kernel<<<(unsigned)((Rd + 7) / 8), 256, 0, s>>>(t->logits_b, t->NP, m->nvel, m->nframe, m->nnote, Rd, true, outputs->onset_B, outputs->offset_B, outputs->mpe_B,
+                                                              outputs->velocity_B);
+  }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
+// loss.backward() of train.py:157 for a loss the host built from the outputs of the LAST hft_train_forward on this trainer: out_grads holds
+// dLoss/d(output) in the output layouts (NULL member = zero); grads_dev is overwritten with dLoss/dParam.  spec_dev must be the same input.
+extern "C" int hft_train_backward(hft_trainer* trainer, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t, const hft_outputs* out_grads,
+                                  float* grads_dev, void* stream) {
+  HFT_REQUIRE(trainer && spec_dev && out_grads && grads_dev, HFT_ERR_ARG, "hft_train_backward: NULL argument");
+  Trainer* t = reinterpret_cast<Trainer*>(trainer);
+  HFT_REQUIRE(t->Bc >= 1, HFT_ERR_STATE, "hft_train_backward: no forward on this trainer yet");
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_launch_count();
+  HFT_CHECK_CUDA(cudaMemsetAsync(grads_dev, 0, (size_t)hft_model_param_floats(reinterpret_cast<hft_model*>(t->m)) * sizeof(float), s));
+  GradSource gs;
+  gs.g = out_grads;
+  return train_backward(*t, spec_dev, stride_b, stride_bin, stride_t, gs, grads_dev, s);
 }
 
 extern "C" int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,

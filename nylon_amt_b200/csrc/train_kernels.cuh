@@ -618,6 +618,55 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
   }
 }
 
+// The eight head outputs of a train-mode forward from the packed logits [rows, ld] (columns 0..2 onset / offset / mpe, 3..3+V-1 velocity):
+// sigmoid probabilities [B, F, NN] and raw velocity logits [B, F, NN, V] (model_spec2midi.py:172-175, :203-206).  One warp per row.
+__global__ void __launch_bounds__(256) heads_out_kernel(const float* __restrict__ logits, int ld, int V, int F, int NN, long long rows, bool time_major,
+                                                        float* __restrict__ on, float* __restrict__ off, float* __restrict__ mpe, float* __restrict__ vel) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  long long lrow = row;
+  if (time_major) {
+    int f = (int)(row % F);
+    long long bn = row / F;
+    int n = (int)(bn % NN);
+    lrow = ((bn / NN) * F + f) * NN + n;
+  }
+  const float* lp = logits + row * ld;
+  if (vel)
+    for (int col = lane; col < V; col += 32) vel[lrow * V + col] = lp[3 + col];
+  if (lane < 3) {
+    float* dst = lane == 0 ? on : (lane == 1 ? off : mpe);
+    if (dst) dst[lrow] = 1.f / (1.f + expf(-lp[lane]));
+  }
+}
+
+// dlogits from the gradients of the eight outputs (autograd's loss.backward() reaching the module outputs): through the sigmoid for the three
+// probability outputs (dz = g * p * (1 - p)), identity for the velocity logits.  A NULL gradient pointer means zero.
+__global__ void __launch_bounds__(256) heads_outgrad_kernel(const float* __restrict__ logits, int ld, int V, int F, int NN, long long rows, bool time_major,
+                                                            const float* __restrict__ g_on, const float* __restrict__ g_off, const float* __restrict__ g_mpe,
+                                                            const float* __restrict__ g_vel, float* __restrict__ dlogits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  long long lrow = row;
+  if (time_major) {
+    int f = (int)(row % F);
+    long long bn = row / F;
+    int n = (int)(bn % NN);
+    lrow = ((bn / NN) * F + f) * NN + n;
+  }
+  const float* lp = logits + row * ld;
+  float* gp = dlogits + row * ld;
+  for (int col = lane; col < V; col += 32) gp[3 + col] = g_vel ? g_vel[lrow * V + col] : 0.f;
+  if (lane < 3) {
+    const float* gg = lane == 0 ? g_on : (lane == 1 ? g_off : g_mpe);
+    const float p = 1.f / (1.f + expf(-lp[lane]));
+    gp[lane] = gg ? gg[lrow] * p * (1.f - p) : 0.f;
+  }
+  for (int col = 3 + V + lane; col < ld; col += 32) gp[col] = 0.f;       // padding columns
+}
+
 // out[c] += sum_r in[r, c]   (embedding gradients: the same table row is added to many sequences).  grid (ceil(cols/256), splits)
 __global__ void colsum_kernel(const float* __restrict__ in, long long rows, long long cols, long long rows_per_split, float* __restrict__ out) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -217,8 +217,8 @@ class Model_SPEC2MIDI(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------------------
     def forward(self, input_spec):
-        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules()):
-            raise NotImplementedError("training-mode forward (dropout) is not on the B200 hot path yet; call model.eval()")
+        if self.training:
+            return self._forward_train(input_spec)
         if not input_spec.is_cuda:
             raise RuntimeError("input_spec is on %s: the B200 path has no CPU fallback" % input_spec.device)
         e, d = self.encoder_spec2midi, self.decoder_spec2midi
@@ -269,7 +269,111 @@ class Model_SPEC2MIDI(nn.Module):
                                               x.stride(2), x.shape[0], ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward")
         return outs
 
+    # ---- train mode (train.py:89-90: model.train(); outputs = model(input_spec)) ------------------------------------------
+    def _check_input(self, input_spec):
+        if not input_spec.is_cuda:
+            raise RuntimeError("input_spec is on %s: the B200 path has no CPU fallback" % input_spec.device)
+        e = self.encoder_spec2midi
+        x = input_spec if input_spec.dtype == torch.float32 else input_spec.float()
+        if x.dim() != 3 or x.shape[1] != e.n_bin or x.shape[2] != e.n_frame + e.n_proc - 1:
+            raise RuntimeError("input_spec must be [B, %d, %d], got %s" % (e.n_bin, e.n_frame + e.n_proc - 1, tuple(x.shape)))
+        return x
+
+    def _trainer(self, batch):
+        """hft_trainer (activation tape) of this module, grown to `batch` segments on demand."""
+        t = self.__dict__.get("_hft_trainer")
+        if t is None or t.capacity < batch:
+            t = _Trainer(self._handle(), batch, next(self.parameters()).device)
+            self.__dict__["_hft_trainer"] = t
+        return t
+
+    def _forward_train(self, input_spec):
+        """Train-mode forward: dropout active (the p of the module's nn.Dropout layers), fp32 kernels with an activation tape, and -- when
+        autograd is recording -- a graph node whose backward is hft_train_backward, so the reference's loop (criteria on the outputs,
+        loss.backward(), a stock torch optimiser; train.py:139-158) runs unchanged.  The attention member of the 9-tuple is None in train
+        mode (train.py never reads it; the tape keeps row log-sum-exps, not the probabilities)."""
+        x = self._check_input(input_spec)
+        ps = sorted({float(m.p) for m in self.modules() if isinstance(m, nn.Dropout)})
+        if len(ps) > 1:
+            raise NotImplementedError("the B200 training step applies ONE dropout probability to every site (the reference does too); got %r" % (ps,))
+        p_drop = ps[0] if ps else 0.0
+        names = self._handle().names
+        sd = dict(self.named_parameters())
+        outs = _TrainForward.apply(self, x, p_drop, *[sd[n] for n in names])
+        return tuple(outs[:4]) + (None,) + tuple(outs[4:])
+
     def __getstate__(self):
+        opt = self.__dict__.get("_hft_trained_by")
+        opt = opt() if opt is not None else None
+        if opt is not None:
+            opt.sync_if_stale()       # pickle.dump(model) after training (m_training.py:373) must see the trained weights
         st = self.__dict__.copy()
-        st.pop("_hft", None)          # the device handle is rebuilt lazily after unpickling
+        for k in ("_hft", "_hft_trainer", "_hft_trained_by"):   # device handles are rebuilt lazily after unpickling
+            st.pop(k, None)
         return st
+
+
+class _Trainer:
+    """Owns one hft_trainer handle (activation tape + gradient work space) and the flat gradient bucket."""
+
+    def __init__(self, handle, capacity, device):
+        self.capacity, self.device, self.handle = int(capacity), device, handle
+        self.ptr = ctypes.c_void_p()
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            _lib.check(L.hft_trainer_create(ctypes.byref(self.ptr), handle.ptr, self.capacity), "hft_trainer_create")
+        self.n = int(L.hft_model_param_floats(handle.ptr))
+        self.offsets = [int(L.hft_model_param_offset(handle.ptr, i)) for i in range(len(handle.names))]
+        self.grads = torch.zeros(self.n, device=device)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().hft_trainer_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class _TrainForward(torch.autograd.Function):
+    """model(input_spec) in train mode as ONE autograd node: forward = hft_train_forward, backward = hft_train_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, p_drop, *params):
+        h = model.sync_weights()
+        e, d = model.encoder_spec2midi, model.decoder_spec2midi
+        B, F, N, V = x.shape[0], e.n_frame, d.n_note, d.n_velocity
+        t = model._trainer(B)
+        dev = x.device
+        opt = dict(device=dev, dtype=torch.float32)
+        outs = [torch.empty((B, F, N), **opt) for _ in range(3)] + [torch.empty((B, F, N, V), **opt)] + \
+               [torch.empty((B, F, N), **opt) for _ in range(3)] + [torch.empty((B, F, N, V), **opt)]
+        ptrs = [ctypes.c_void_p(o.data_ptr()) for o in outs]
+        o = _lib.hft_outputs(ptrs[0], ptrs[1], ptrs[2], ptrs[3], None, ptrs[4], ptrs[5], ptrs[6], ptrs[7], None, None)
+        # dropout masks: counter-based, seeded from torch's CPU generator so torch.manual_seed() governs the run
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p_drop > 0.0 else 0
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            _lib.check(L.hft_trainer_set_dropout(t.ptr, float(p_drop), seed), "hft_trainer_set_dropout")
+            _lib.check(L.hft_train_forward(t.ptr, B, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), ctypes.byref(o),
+                                           ctypes.c_void_p(stream)), "hft_train_forward")
+        ctx.model, ctx.trainer, ctx.x, ctx.handle = model, t, x, h
+        ctx.tape_id = t.__dict__["tape_id"] = t.__dict__.get("tape_id", 0) + 1
+        ctx.shapes = [p.shape for p in params]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        t, x = ctx.trainer, ctx.x
+        if t.__dict__.get("tape_id") != ctx.tape_id:
+            raise RuntimeError("backward through a train-mode forward whose activation tape was overwritten by a later forward of the same module")
+        keep = [None if g is None else (g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()) for g in gouts]
+        ptrs = [ctypes.c_void_p(g.data_ptr()) if g is not None else None for g in keep]
+        o = _lib.hft_outputs(ptrs[0], ptrs[1], ptrs[2], ptrs[3], None, ptrs[4], ptrs[5], ptrs[6], ptrs[7], None, None)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hft_train_backward(t.ptr, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), ctypes.byref(o),
+                                                     ctypes.c_void_p(t.grads.data_ptr()), ctypes.c_void_p(stream)), "hft_train_backward")
+        grads = [t.grads[off:off + shp.numel()].view(shp).clone() for off, shp in zip(t.offsets, ctx.shapes)]
+        return (None, None, None) + tuple(grads)

@@ -164,3 +164,134 @@ def test_paper_size_gradients_match_cpu_oracle(golden_dir):
         if err > 3 * noise + 2e-4 * float(ref.abs().max()) + 1e-5 * gmax:
             bad[name] = (err, noise, float(ref.abs().max()))
     assert not bad, bad
+
+
+# ---- the reference's own loop against the mirror module: model.train(); model(x); criteria; loss.backward(); stock optimiser ----------------
+
+def _reference_loop_loss(model, spec, on, off, mpe, vel, wA=1.0, wB=1.0):
+    """train.py:89-151 restated: forward in train mode, the 8 criteria the reference builds (m_training.py:150-160), weighted sum."""
+    bce, ce = torch.nn.BCELoss(), torch.nn.CrossEntropyLoss()
+    oA, fA, mA, vA, attention, oB, fB, mB, vB = model(spec)
+    assert attention is None
+    lA = bce(oA.contiguous().view(-1), on.view(-1)) + bce(fA.contiguous().view(-1), off.view(-1)) + bce(mA.contiguous().view(-1), mpe.view(-1)) + \
+        ce(vA.contiguous().view(-1, vA.shape[-1]), vel.view(-1))
+    lB = bce(oB.contiguous().view(-1), on.view(-1)) + bce(fB.contiguous().view(-1), off.view(-1)) + bce(mB.contiguous().view(-1), mpe.view(-1)) + \
+        ce(vB.contiguous().view(-1, vB.shape[-1]), vel.view(-1))
+    return wA * lA + wB * lB
+
+
+def test_train_mode_forward_autograd_and_stock_adam_match_reference(golden_dir):
+    """The UNMODIFIED reference loop (train.py:89-158) against nylon_amt_b200.Model_SPEC2MIDI: train-mode forward (hft_train_forward) ->
+    torch criteria -> loss.backward() (hft_train_backward behind one autograd node) -> torch.optim.Adam.step(); loss, all 115 gradients,
+    the parameters after the step and the loss of the second iteration against the fixture the reference wrote."""
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    model = _model(golden_dir).train()
+    optimizer = torch.optim.Adam(model.parameters(), lr=float(t["lr"]))
+    batch = _batch(t)
+    optimizer.zero_grad()
+    loss = _reference_loop_loss(model, *batch)
+    assert abs(float(loss.item()) - float(t["loss"])) <= 2e-5 * abs(float(t["loss"])), (float(loss.item()), float(t["loss"]))
+    loss.backward()
+    gmax = max(float(np.abs(t[k]).max()) for k in t.files if k.startswith("g:"))
+    bad = {}
+    for name, p in model.named_parameters():
+        ref = torch.from_numpy(t["g:" + name])
+        assert p.grad is not None, name
+        err = float((p.grad.cpu() - ref).abs().max())
+        if err > 2e-4 * float(ref.abs().max()) + 1e-5 * gmax:
+            bad[name] = err
+    assert not bad, bad
+    optimizer.step()
+    for name, p in model.named_parameters():
+        ref, g = torch.from_numpy(t["p1:" + name]), torch.from_numpy(t["g:" + name])
+        firm = g.abs() > 1e-3 * gmax
+        assert float((p.detach().cpu() - ref)[firm].abs().max() if firm.any() else 0.0) <= 2e-7, name
+    optimizer.zero_grad()
+    loss2 = _reference_loop_loss(model, *batch)          # the forward re-uploads the parameters the stock optimiser changed in place
+    assert abs(float(loss2.item()) - float(t["loss2"])) <= 1e-4 * abs(float(t["loss2"])), (float(loss2.item()), float(t["loss2"]))
+
+
+def test_train_mode_forward_outputs_equal_eval_forward_without_dropout(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hft_reduced.npz"))
+    model = _model(golden_dir)
+    spec = torch.from_numpy(g["spec"]).cuda()
+    model.eval()
+    model.precision = "fp32"
+    ev = [x.clone() for x in model(spec)]
+    model.train()
+    with torch.no_grad():
+        tr = model(spec)
+    for i in (0, 1, 2, 3, 5, 6, 7, 8):
+        assert float((tr[i] - ev[i]).abs().max()) <= 2e-4, i
+    # with p = 0.1 the outputs move, and differ from call to call
+    md = _model(golden_dir, dropout=0.1).train()
+    a = md(spec)[5].detach().clone()
+    b = md(spec)[5].detach()
+    assert float((a - ev[5]).abs().max()) > 1e-4 and not torch.equal(a, b)
+
+
+def test_partial_last_batch(golden_dir):
+    """DataLoader(drop_last=False): the last batch of an epoch is smaller than the trainer's capacity; result = a trainer of that size."""
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    batch = [x[:1] for x in _batch(t)]
+    big = hft.training.Adam(_model(golden_dir), batch_size=3)
+    one = hft.training.Adam(_model(golden_dir), batch_size=1)
+    lb = float(big.forward_backward(*batch).item())
+    lo = float(one.forward_backward(*batch).item())
+    assert lb == lo
+    assert torch.equal(big.grads, one.grads)
+    with pytest.raises(RuntimeError):
+        big.forward_backward(*[torch.cat([x, x, x, x]) for x in batch])
+
+
+def test_adam_is_a_torch_optimizer_with_checkpoint_round_trip(golden_dir, tmp_path):
+    """m_training.py:147 ReduceLROnPlateau(optimizer); :373-384 pickle.dump(model) / state_dict / optimizer_dict; :277-278 resume."""
+    import pickle
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    batch = _batch(t)
+    model = _model(golden_dir)
+    opt = hft.training.Adam(model, lr=1e-3, batch_size=2)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=0)
+    for _ in range(2):
+        hft.training.train_step(model, opt, *batch)
+    sched.step(1.0); sched.step(2.0)                       # a plateau: lr halves, and the next step uses it
+    assert abs(opt.lr - 5e-4) < 1e-12
+    # checkpoint: the module's state_dict sees the trained weights without an explicit sync
+    sd_model = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    flat = opt._flat_params()
+    for name, (off, numel) in opt._slot.items():
+        assert torch.equal(sd_model[name].reshape(-1), flat[off:off + numel]), name
+    blob = pickle.dumps(model)
+    assert torch.equal(pickle.loads(blob).state_dict()["decoder_spec2midi.fc_onset_time.bias"].cpu(), sd_model["decoder_spec2midi.fc_onset_time.bias"].cpu())
+    sd_opt = opt.state_dict()
+    torch.save({"model_dict": sd_model, "optimizer_dict": sd_opt, "scheduler_dict": sched.state_dict()}, str(tmp_path / "ck.pt"))
+    l3 = float(hft.training.train_step(model, opt, *batch).item())
+    # resume in a fresh module + optimiser: step 3 reproduces
+    ck = torch.load(str(tmp_path / "ck.pt"), weights_only=False)
+    model2 = _model(golden_dir)
+    model2.load_state_dict(ck["model_dict"])
+    opt2 = hft.training.Adam(model2, lr=1e-3, batch_size=2)
+    opt2.load_state_dict(ck["optimizer_dict"])
+    assert abs(opt2.lr - 5e-4) < 1e-12 and opt2.step_count == 2
+    l3b = float(hft.training.train_step(model2, opt2, *batch).item())
+    assert l3b == l3, (l3, l3b)
+    opt.sync_to_module(); opt2.sync_to_module()
+    for (n, a), (_, b) in zip(model.named_parameters(), model2.named_parameters()):
+        assert torch.equal(a, b), n
+    # the same optimizer_dict loads into a stock torch.optim.Adam over the same parameters
+    stock = torch.optim.Adam(model2.parameters(), lr=1e-3)
+    stock.load_state_dict(ck["optimizer_dict"])
+    assert len(stock.state) == len(list(model2.parameters()))
+
+
+def test_train_returns_with_module_synced(golden_dir):
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    model = _model(golden_dir)
+    before = model.decoder_spec2midi.fc_onset_time.bias.detach().clone()
+    opt = hft.training.Adam(model, lr=1e-3, batch_size=2)
+    batch = _batch(t)
+    it = [tuple(x[:2] for x in batch), tuple(x[:1] for x in batch)]          # second batch is partial
+    hft.training.train(model, it, opt)
+    after = model.decoder_spec2midi.fc_onset_time.bias.detach()
+    assert not torch.equal(before, after) and not opt._stale

@@ -61,8 +61,8 @@ def test_no_cpu_fallback():
     model = hft.build_model(hft.default_config(), 64, 128, 2, 2, seed=1, device="cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(torch.zeros(1, 256, 192))
-    model.train()
-    with pytest.raises(NotImplementedError):
+    model.train()                      # train mode runs the CUDA training forward (hft_train_forward): no CPU fallback either
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(torch.zeros(1, 256, 192))
 
 
