@@ -76,6 +76,11 @@ int hft_logmel_host_f32(hft_logmel_plan* plan, const float* wav_host, int64_t n_
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct hft_resample_plan hft_resample_plan;
 int hft_resample_create(hft_resample_plan** plan, const float* kernel_host, int32_t orig_reduced, int32_t new_reduced, int32_t width);
+/* The same table built by the library (double-precision restatement of torchaudio's formula, fp32 result within 1e-7 of torchaudio's):
+ * hft_resample_build_table is host-only (no device needed) and returns the number of floats the table takes ([new_reduced][2*width+orig_reduced]);
+ * it fills table_host when capacity suffices.  hft_resample_create_hz = build + hft_resample_create. */
+int64_t hft_resample_build_table(int32_t orig_hz, int32_t new_hz, float* table_host, int64_t capacity, int32_t* orig_reduced, int32_t* new_reduced, int32_t* width);
+int hft_resample_create_hz(hft_resample_plan** plan, int32_t orig_hz, int32_t new_hz);
 int hft_resample_destroy(hft_resample_plan* plan);
 int64_t hft_resample_num_samples(const hft_resample_plan* plan, int64_t n_in);
 /* wav_dev [channels][n_in] fp32 (channel-major, like torchaudio.load) -> out_dev [n_out] fp32 mono at the new rate. */

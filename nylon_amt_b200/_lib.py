@@ -34,6 +34,9 @@ SYMBOLS = {
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "hft_logmel_host_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "hft_resample_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    "hft_resample_build_table": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32),
+                                                  ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "hft_resample_create_hz": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32]),
     "hft_resample_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "hft_resample_num_samples": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64]),
     "hft_resample_mono_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),

@@ -62,11 +62,9 @@ class _LogmelPlan:
 
 
 class _ResamplePlan:
-    def __init__(self, kernel, orig_reduced, new_reduced, width):
+    def __init__(self, orig_hz, new_hz):
         self.ptr = ctypes.c_void_p()
-        self.kernel = kernel
-        _lib.check(_lib.lib().hft_resample_create(ctypes.byref(self.ptr), ctypes.c_void_p(kernel.data_ptr()), orig_reduced, new_reduced, width),
-                   "hft_resample_create")
+        _lib.check(_lib.lib().hft_resample_create_hz(ctypes.byref(self.ptr), int(orig_hz), int(new_hz)), "hft_resample_create_hz")
 
     def __del__(self):
         try:
@@ -168,17 +166,11 @@ class AMT():
         return outs
 
     def _resample_plan(self, sr):
-        """Plan of torchaudio.transforms.Resample(sr, 16000) (amt.py:57): the polyphase table comes from the same torchaudio
-        function the reference calls, so the coefficients are bit-identical."""
+        """Plan of torchaudio.transforms.Resample(sr, 16000) (amt.py:57): the polyphase table is built inside the library
+        (hft_resample_create_hz; within 1e-7 of torchaudio's own table, tests/test_resample.py)."""
         plans = self.__dict__.setdefault("_rs_plans", {})
         if sr not in plans:
-            import math
-            from torchaudio.functional.functional import _get_sinc_resample_kernel
-            new = int(self.config['feature']['sr'])
-            g = math.gcd(int(sr), new)
-            kernel, width = _get_sinc_resample_kernel(int(sr), new, g)           # [new/g, 1, 2*width + sr/g] fp32
-            k = kernel.reshape(kernel.shape[0], -1).contiguous().float()
-            plans[sr] = _ResamplePlan(k, int(sr) // g, new // g, int(width))
+            plans[sr] = _ResamplePlan(int(sr), int(self.config['feature']['sr']))
         return plans[sr]
 
     def wave2mono16k(self, wave, sr):

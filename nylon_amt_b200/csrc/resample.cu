@@ -4,8 +4,9 @@
 // torchaudio's Resample is a polyphase FIR (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99): with o = orig/gcd,
 // n = new/gcd and the table K[n][2*width + o] it computes, on the signal zero-padded by (width, width + o),
 //     y[i*n + p] = sum_t xpad[i*o + t] * K[p][t]          (F.conv1d with stride o, one output channel per phase p)
-// truncated to ceil(n * length / o) samples.  The table is built on the host by the SAME torchaudio function the
-// reference calls (bit-identical coefficients) and handed to hft_resample_create.
+// truncated to ceil(n * length / o) samples.  The table is built on the host by hft_resample_build_table (this file: the published
+// sinc_interp_hann formula in double precision, within 1e-7 of torchaudio's own table -- tests/test_resample.py) or handed in by
+// the caller (hft_resample_create).
 //
 // Kernel: one CTA per 32 consecutive i.  The mono-mixed input span (32*o + kw samples) is staged once in shared memory;
 // warp w walks the phases p = w, w + warps, ...; lane = i, so the coefficient K[p][t] is a broadcast load and the 32 lanes
@@ -62,6 +63,54 @@ __global__ void __launch_bounds__(kRsWarps * 32) resample_mono_kernel(const floa
 }  // namespace hft
 
 using namespace hft;
+
+#include <cmath>
+#include <numeric>
+
+// The polyphase table of torchaudio's sinc_interp_hann resampler (functional.py _get_sinc_resample_kernel with the defaults the
+// reference uses: lowpass_filter_width 6, rolloff 0.99), in double precision, rounded to fp32 at the end:
+//   base = min(o, n) * rolloff;  width = ceil(lpw * o / base);  idx = (-width .. width + o - 1) / o
+//   t[p][k] = clamp((float(-p) / float(n) + idx[k]) * base, -lpw, lpw)    (the phase offset is rounded to fp32 first, as torchaudio does)
+//   K[p][k] = sinc(pi t) * cos^2(pi t / (2 lpw)) * base / o
+extern "C" int64_t hft_resample_build_table(int32_t orig_hz, int32_t new_hz, float* table_host, int64_t capacity, int32_t* orig_reduced, int32_t* new_reduced,
+                                            int32_t* width_out) {
+  if (orig_hz < 1 || new_hz < 1) return -1;
+  const int g = std::gcd(orig_hz, new_hz);
+  const int o = orig_hz / g, n = new_hz / g;
+  const double lpw = 6.0, rolloff = 0.99;
+  const double base = (double)(o < n ? o : n) * rolloff;
+  const int width = (int)std::ceil(lpw * o / base);
+  const int kw = 2 * width + o;
+  if (orig_reduced) *orig_reduced = o;
+  if (new_reduced) *new_reduced = n;
+  if (width_out) *width_out = width;
+  const int64_t need = (int64_t)n * kw;
+  if (!table_host || capacity < need) return need;
+  const double pi = 3.14159265358979323846;
+  for (int p = 0; p < n; ++p) {
+    const double phase = (double)((float)(-p) / (float)n);
+    for (int k = 0; k < kw; ++k) {
+      double t = (phase + (double)(k - width) / (double)o) * base;
+      t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+      const double c = std::cos(t * pi / lpw / 2.0);
+      const double a = t * pi;
+      const double sinc = a == 0.0 ? 1.0 : std::sin(a) / a;
+      table_host[(int64_t)p * kw + k] = (float)(sinc * c * c * (base / (double)o));
+    }
+  }
+  return need;
+}
+
+extern "C" int hft_resample_create(hft_resample_plan** out, const float* kernel_host, int32_t orig_reduced, int32_t new_reduced, int32_t width);
+
+extern "C" int hft_resample_create_hz(hft_resample_plan** out, int32_t orig_hz, int32_t new_hz) {
+  HFT_REQUIRE(out && orig_hz >= 1 && new_hz >= 1, HFT_ERR_ARG, "hft_resample_create_hz: bad argument");
+  int32_t o = 0, n = 0, width = 0;
+  const int64_t need = hft_resample_build_table(orig_hz, new_hz, nullptr, 0, &o, &n, &width);
+  std::vector<float> table((size_t)need);
+  hft_resample_build_table(orig_hz, new_hz, table.data(), need, &o, &n, &width);
+  return hft_resample_create(out, table.data(), o, n, width);
+}
 
 extern "C" int hft_resample_create(hft_resample_plan** out, const float* kernel_host, int32_t orig_reduced, int32_t new_reduced, int32_t width) {
   HFT_REQUIRE(out && kernel_host && orig_reduced >= 1 && new_reduced >= 1 && width >= 0, HFT_ERR_ARG, "hft_resample_create: bad argument");

@@ -302,11 +302,20 @@ class Model_SPEC2MIDI(nn.Module):
         outs = _TrainForward.apply(self, x, p_drop, *[sd[n] for n in names])
         return tuple(outs[:4]) + (None,) + tuple(outs[4:])
 
-    def __getstate__(self):
+    def _sync_trained(self):
+        """The fused training step (nylon_amt_b200.training.Adam) keeps the current parameters in the library's arena between steps;
+        anything that reads the module's tensors from outside (state_dict, pickle) first copies them back."""
         opt = self.__dict__.get("_hft_trained_by")
         opt = opt() if opt is not None else None
         if opt is not None:
-            opt.sync_if_stale()       # pickle.dump(model) after training (m_training.py:373) must see the trained weights
+            opt.sync_if_stale()
+
+    def state_dict(self, *args, **kwargs):                # m_training.py:384 torch.save({'model_dict': model.state_dict(), ...})
+        self._sync_trained()
+        return super().state_dict(*args, **kwargs)
+
+    def __getstate__(self):
+        self._sync_trained()          # pickle.dump(model) after training (m_training.py:373) must see the trained weights
         st = self.__dict__.copy()
         for k in ("_hft", "_hft_trainer", "_hft_trained_by"):   # device handles are rebuilt lazily after unpickling
             st.pop(k, None)

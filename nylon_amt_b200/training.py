@@ -62,9 +62,9 @@ class Adam(torch.optim.Optimizer):
             dist.broadcast(flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
             self._write_flat_params(flat)
         self.seed = int(seed) * 1000003 + self._rank
-        # state_dict() / pickling of the module must see the trained weights, which live in the library's arena between steps
+        # state_dict() / pickling of the module must see the trained weights, which live in the library's arena between steps:
+        # Model_SPEC2MIDI.state_dict / __getstate__ look this reference up and call sync_if_stale()
         model.__dict__["_hft_trained_by"] = weakref.ref(self)
-        self._hook = model.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self.sync_if_stale())
 
     def __del__(self):
         try:

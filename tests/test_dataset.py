@@ -47,6 +47,24 @@ def test_items_follow_the_reference_slicing(pickles):
     assert np.array_equal(ds3.idx.numpy(), a["idx"][:n // 3 * 3][::3])
 
 
+def test_raw_memory_mapped_layout_equals_pickles(pickles):
+    """convert_to_raw: every split array as a flat .npy; MyDataset memory-maps it (no host copy) and returns the same items."""
+    from nylon_amt_b200.dataset import convert_to_raw
+    files, a = pickles
+    raw = {k: convert_to_raw(v) for k, v in files.items()}
+    for k, path in raw.items():
+        m = np.load(path, mmap_mode="r")
+        assert isinstance(m, np.memmap) and m.dtype == a[k].dtype and m.shape == a[k].shape and np.array_equal(m, a[k])
+        assert os.path.getsize(path) == a[k].nbytes + 128                         # the reference's bytes behind one header
+    ds_raw, ds_pkl = _make(raw), _make(files)
+    assert isinstance(ds_raw.feature.numpy().base, np.memmap) or ds_raw.feature.data_ptr() != ds_pkl.feature.data_ptr()
+    assert len(ds_raw) == len(ds_pkl)
+    for k in (0, 9, len(ds_raw) - 1):
+        for x, y in zip(ds_raw[k], ds_pkl[k]):
+            assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y)
+    assert torch.equal(_make(raw, n_slice=3).idx, _make(files, n_slice=3).idx)
+
+
 def test_reference_class_agrees_when_available(pickles):
     from oracle import _refload
     if not _refload.available():
@@ -83,6 +101,26 @@ def test_device_batches_equal_items(pickles):
     r1 = [b[1] for b in ds.batches(4, generator=torch.Generator().manual_seed(2), rank=1, world=2)]
     full = [b[1] for b in ds.batches(8, generator=torch.Generator().manual_seed(2))]
     assert len(r0) == len(r1) == len(full) and torch.equal(torch.cat([r0[0], r1[0]]), full[0])
+
+
+@pytest.mark.gpu
+def test_raw_layout_streams_to_the_device(pickles):
+    """to_device() from the memory-mapped files (staged through pinned memory in pieces) equals the upload of the unpickled arrays."""
+    from nylon_amt_b200 import dataset as dsmod
+    files, _ = pickles
+    raw = {k: dsmod.convert_to_raw(v) for k, v in files.items()}
+    old = dsmod._STAGE_BYTES
+    dsmod._STAGE_BYTES = 300 * 1024                  # force many pieces (2000 x 256 floats = 2 MB)
+    try:
+        a = _make(raw).to_device()
+    finally:
+        dsmod._STAGE_BYTES = old
+    b = _make(files).to_device()
+    for k in ("feature", "onset", "offset", "mpe", "velocity", "idx"):
+        assert a._dev[k].dtype == b._dev[k].dtype and torch.equal(a._dev[k], b._dev[k]), k
+    sel = torch.tensor([1, 40, 7], device="cuda")
+    for x, y in zip(a.gather(sel), b.gather(sel)):
+        assert torch.equal(x, y)
 
 
 @pytest.mark.gpu

@@ -35,6 +35,11 @@ def test_matches_reference_golden(amt, golden_dir):
         assert out.shape == ref.shape, name
         ok, worst = lo.close_logmel(out, ref, tol=1e-4, fft_noise=256.0 if name in TONAL else 0.0)
         assert ok, (name, worst)
+        miss, cells, strict = lo.strict_misses(out, ref)
+        if name in TONAL:              # how far the allowance reaches: cells that miss the strict 1e-4 rule (all at the log(1e-8) floor under a pure tone)
+            print("log-mel %-12s strict-rule misses %d / %d cells, worst strict ratio %.2e" % (name, miss, cells, strict))
+        else:
+            assert miss == 0
 
 
 def test_wav2feature_file_api(amt, golden_dir, tmp_path):

@@ -238,8 +238,9 @@ def test_partial_last_batch(golden_dir):
     one = hft.training.Adam(_model(golden_dir), batch_size=1)
     lb = float(big.forward_backward(*batch).item())
     lo = float(one.forward_backward(*batch).item())
-    assert lb == lo
-    assert torch.equal(big.grads, one.grads)
+    assert abs(lb - lo) <= 1e-6 * abs(lo), (lb, lo)                            # fp32 atomics: the summation order differs from run to run
+    gmax = float(one.grads.abs().max())
+    assert float((big.grads - one.grads).abs().max()) <= 1e-5 * gmax
     with pytest.raises(RuntimeError):
         big.forward_backward(*[torch.cat([x, x, x, x]) for x in batch])
 

@@ -37,6 +37,26 @@ def test_oracle_table_equals_torchaudio():
         assert float(np.abs(mine - k.reshape(n, -1).numpy()).max()) <= 1e-7
 
 
+def test_library_table_equals_torchaudio():
+    """hft_resample_build_table (host-only entry point of libhft_sm100.so) against torchaudio's own table and the oracle's."""
+    import ctypes
+    import math
+    from nylon_amt_b200 import _lib
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+    L = _lib.lib()
+    for sr in (44100, 48000, 22050, 8000, 32000, 11025):
+        o, n, w = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        need = L.hft_resample_build_table(sr, 16000, None, 0, ctypes.byref(o), ctypes.byref(n), ctypes.byref(w))
+        buf = np.zeros(need, np.float32)
+        assert L.hft_resample_build_table(sr, 16000, buf.ctypes.data_as(ctypes.c_void_p), need, ctypes.byref(o), ctypes.byref(n), ctypes.byref(w)) == need
+        g = math.gcd(sr, 16000)
+        k, width = _get_sinc_resample_kernel(sr, 16000, g)
+        assert (o.value, n.value, w.value) == (sr // g, 16000 // g, width)
+        mine = buf.reshape(n.value, 2 * w.value + o.value)
+        assert float(np.abs(mine - k.reshape(n.value, -1).numpy()).max()) <= 1e-7, sr
+        assert float(np.abs(mine - resample_oracle.sinc_kernel(sr, 16000)[0]).max()) <= 1e-7, sr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_resample_matches_reference(fx, name):
