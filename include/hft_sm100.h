@@ -162,8 +162,18 @@ typedef struct hft_outputs {
 int hft_forward(hft_model* model, int precision, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t,
                 int32_t batch, const hft_outputs* outputs, void* stream);
 
+/* The two halves as separate calls -- Encoder_SPEC2MIDI.forward (model_spec2midi.py:60-106): spec [B, n_bin, n_frame + 2 margin] ->
+ * enc_out_dev fp32 [B, n_frame, n_bin, hid];  Decoder_SPEC2MIDI.forward (:145-216): that memory -> the nine outputs.  fp32 CUDA-core
+ * kernels (eval semantics); hft_forward is the fused hot path. */
+int hft_forward_encoder(hft_model* model, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t, int32_t batch,
+                        float* enc_out_dev, void* stream);
+int hft_forward_decoder(hft_model* model, const float* enc_dev, int32_t batch, const hft_outputs* outputs, void* stream);
+
 /* Largest batch one hft_forward call processes at once (bigger batches are looped internally). */
 int hft_model_set_max_batch(hft_model* model, int32_t max_batch);
+/* Give the activation work spaces back to the driver (they are sized by max_batch and only grow; lowering max_batch releases them too).
+ * Synchronises the device.  Weights stay registered; the next hft_forward re-allocates what it needs. */
+int hft_model_release_workspace(hft_model* model);
 
 /* Number of kernels the last hft_forward / hft_logmel call on this thread launched (bench bookkeeping). */
 int64_t hft_last_launch_count(void);

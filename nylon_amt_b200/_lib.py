@@ -52,6 +52,7 @@ SYMBOLS = {
     "hft_model_weight_numel": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
     "hft_model_set_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
     "hft_model_set_max_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "hft_model_release_workspace": (ctypes.c_int, [ctypes.c_void_p]),
     "hft_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int32, ctypes.POINTER(hft_outputs), ctypes.c_void_p]),
     "hft_last_launch_count": (ctypes.c_int64, []),
@@ -70,6 +71,8 @@ SYMBOLS = {
     "hft_trainer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "hft_trainer_set_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32]),
     "hft_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_forward_encoder": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "hft_forward_decoder": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(hft_outputs), ctypes.c_void_p]),
     "hft_train_forward_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]),

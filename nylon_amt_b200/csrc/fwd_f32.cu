@@ -95,7 +95,9 @@ static int encoder_layer_f32(Model* m, cudaStream_t s, Ws32& w, float* x, long l
   return HFT_OK;
 }
 
-int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s) {
+// stage 0: whole forward.  stage 1: encoder only (model_spec2midi.py:60-106), the memory [B, n_frame, n_bin, hid] is copied to enc_io.
+// stage 2: decoder only (model_spec2midi.py:145-216) on the memory read from enc_io.
+int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s, int stage, float* enc_io) {
   if (B == 0) return HFT_OK;
   Ws32 w;
   HFT_TRY(ensure_ws(m, B, w));
@@ -103,12 +105,21 @@ int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long 
   const long long Se = (long long)B * F, Re = Se * NB, Rd = Se * NN;
   const float sqrtH = sqrtf((float)H);
   HFT_REQUIRE(m->nproc == 65, HFT_ERR_UNSUPPORTED, "front kernel is built for n_margin 32");
-  // encoder front
-  {
-    LaunchScope ls(HFT_KCLASS_FRONT, s);
-    front_f32_kernel<65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, w.X);
+  if (stage == 2) {
+    HFT_CHECK_CUDA(cudaMemcpyAsync(w.X, enc_io, (size_t)Re * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    // encoder front
+    {
+      LaunchScope ls(HFT_KCLASS_FRONT, s);
+      front_f32_kernel<65><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, m->front_w, m->front_b, m->w[m->pos_freq], sqrtH, H, F, NB, w.X);
+    }
+    for (size_t l = 0; l < m->enc.size(); ++l) HFT_TRY(encoder_layer_f32(m, s, w, w.X, Se, NB, m->enc[l], m->enc_qkv[l]));
+    if (stage == 1) {
+      HFT_CHECK_CUDA(cudaMemcpyAsync(enc_io, w.X, (size_t)Re * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      HFT_CHECK_CUDA(cudaGetLastError());
+      return HFT_OK;
+    }
   }
-  for (size_t l = 0; l < m->enc.size(); ++l) HFT_TRY(encoder_layer_f32(m, s, w, w.X, Se, NB, m->enc[l], m->enc_qkv[l]));
   // decoder: layer zero (cross-attention of the constant pitch queries + FFN), model_spec2midi.py:255-272
   const int n_cross = 1 + (int)m->dec.size();
   {

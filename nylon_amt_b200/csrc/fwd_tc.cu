@@ -749,6 +749,13 @@ void tc_destroy(Model* m) {
   m->tc = nullptr;
 }
 
+// drop the activation workspaces of every precision mode (the 16-bit weight copies stay); the next forward re-allocates for its max_batch
+void tc_release_workspace(Model* m) {
+  if (!m->tc) return;
+  TcBoth* b = reinterpret_cast<TcBoth*>(m->tc);
+  for (auto& t : b->st) { cudaFree(t.ws); t.ws = nullptr; t.ws_batch = 0; }
+}
+
 static TcState& state_for(Model* m, int precision) {
   if (!m->tc) {
     TcBoth* b = new TcBoth();

@@ -51,7 +51,7 @@ struct SmemLayout {
   static constexpr int twr = tw2 + 1024 * 8;
   static constexpr int melw = twr + 520 * 8;
   static constexpr int melinfo = melw + kMaxMelW * 4;
-  static constexpr int warp0 = melinfo + kNmels * 4;
+  static constexpr int warp0 = melinfo + kMelInfo * 4;
   static constexpr int tile_bytes = 32 * kTStride * 8;                       // T / Z; P[0..1024] overlays it once Z is consumed
   static constexpr int per_warp = tile_bytes;
   static constexpr int bars = warp0 + kWarps * per_warp;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const __grid_con
   for (int i = tid; i < 1024; i += kWarps * 32) s_tw2[i] = p.tw2[i];
   for (int i = tid; i < 513; i += kWarps * 32) s_twr[i] = p.twr[i];
   for (int i = tid; i < kMaxMelW; i += kWarps * 32) s_melw[i] = p.melw[i];
-  for (int i = tid; i < kNmels; i += kWarps * 32) s_melinfo[i] = p.melinfo[i];
+  for (int i = tid; i < kMelInfo; i += kWarps * 32) s_melinfo[i] = p.melinfo[i];
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -223,22 +223,11 @@ extern "C" int hft_logmel_create(hft_logmel_plan** out, const float* window_host
   std::vector<float> win, fb;
   if (window_host) win.assign(window_host, window_host + kNfft); else default_window(win);
   if (fb_host) fb.assign(fb_host, fb_host + (size_t)kNfreq * kNmels); else default_fb(fb);
-  // pack the filterbank into bands
+  // pack the filterbank into lane-major band weights (logmel_core.cuh)
   std::vector<float> melw(kMaxMelW, 0.f);
-  std::vector<uint32_t> melinfo(kNmels);
-  int off = 0;
-  for (int m = 0; m < kNmels; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < kNfreq; ++k)
-      if (fb[(size_t)k * kNmels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-    int len = lo < 0 ? 0 : hi - lo + 1;
-    HFT_REQUIRE(len <= 31 && off + len <= kMaxMelW, HFT_ERR_UNSUPPORTED,
-                "hft_logmel_create: mel filter %d spans %d FFT bins (packed %d); the fused kernel supports bands <= 31 bins and <= %d weights",
-                m, len, off + len, kMaxMelW);
-    for (int i = 0; i < len; ++i) melw[off + i] = fb[(size_t)(lo + i) * kNmels + m];
-    melinfo[m] = mel_pack(lo < 0 ? 0 : lo, len, off);
-    off += len;
-  }
+  std::vector<uint32_t> melinfo(kMelInfo);
+  HFT_REQUIRE(lm_pack_filterbank(fb.data(), melw.data(), melinfo.data()) == 0, HFT_ERR_UNSUPPORTED,
+              "hft_logmel_create: the fused kernel supports mel bands of <= 31 FFT bins and <= %d taps summed over the 8 bin groups", kMaxMelTaps);
   std::vector<float2> tw2(1024), twr(513);
   for (int k2 = 0; k2 < 32; ++k2)
     for (int n1 = 0; n1 < 32; ++n1) {
@@ -256,12 +245,12 @@ extern "C" int hft_logmel_create(hft_logmel_plan** out, const float* window_host
   HFT_CHECK_CUDA(cudaMalloc(&pl->d_tw2, 1024 * 8));
   HFT_CHECK_CUDA(cudaMalloc(&pl->d_twr, 513 * 8));
   HFT_CHECK_CUDA(cudaMalloc(&pl->d_melw, kMaxMelW * 4));
-  HFT_CHECK_CUDA(cudaMalloc(&pl->d_melinfo, kNmels * 4));
+  HFT_CHECK_CUDA(cudaMalloc(&pl->d_melinfo, kMelInfo * 4));
   HFT_CHECK_CUDA(cudaMemcpy(pl->d_window, win.data(), kNfft * 4, cudaMemcpyHostToDevice));
   HFT_CHECK_CUDA(cudaMemcpy(pl->d_tw2, tw2.data(), 1024 * 8, cudaMemcpyHostToDevice));
   HFT_CHECK_CUDA(cudaMemcpy(pl->d_twr, twr.data(), 513 * 8, cudaMemcpyHostToDevice));
   HFT_CHECK_CUDA(cudaMemcpy(pl->d_melw, melw.data(), kMaxMelW * 4, cudaMemcpyHostToDevice));
-  HFT_CHECK_CUDA(cudaMemcpy(pl->d_melinfo, melinfo.data(), kNmels * 4, cudaMemcpyHostToDevice));
+  HFT_CHECK_CUDA(cudaMemcpy(pl->d_melinfo, melinfo.data(), kMelInfo * 4, cudaMemcpyHostToDevice));
   HFT_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total));
   *out = reinterpret_cast<hft_logmel_plan*>(pl);
   return HFT_OK;

@@ -27,10 +27,48 @@ constexpr int kHop = 256;
 constexpr int kNmels = 256;
 constexpr int kNfreq = 1025;
 constexpr int kTStride = 33;          // float2 row stride of the 32x32 transpose tile (conflict-free)
-constexpr int kMaxMelW = 2048;        // packed band weights (2 036 for the reference's filterbank)
+constexpr int kMelGroups = kNmels / 32;   // lane handles mel bins lane + 32 j, j = 0..7
+constexpr int kMaxMelTaps = 80;           // sum over the groups of the longest band in the group (76 for the reference's filterbank)
+constexpr int kMaxMelW = kMaxMelTaps * 32;
+constexpr int kMelInfo = kNmels + 2 * kMelGroups;
 
-// melinfo[m] = start | len << 11 | offset << 16     (start < 2048, len < 32, offset < 65536)
-HFT_HD uint32_t mel_pack(int start, int len, int off) { return (uint32_t)start | ((uint32_t)len << 11) | ((uint32_t)off << 16); }
+// Band weights in a lane-major layout: the 32 bins of group j run the SAME number of taps n_j (= the longest band of the group; shorter
+// bands are zero padded), tap i of bin lane + 32 j is melw[(base_j + i) * 32 + lane] -- a conflict-free shared-memory read for every (j, i)
+// (the packed [bin][tap] layout read at offsets that differ by the band length from lane to lane: 2.9 wavefronts per load on average).
+// The 0.25 of the power spectrum (lm_power_regs) is folded into the weights: exact, a power of two.
+// melinfo[m] = first FFT bin of band m; melinfo[kNmels + j] = base_j; melinfo[kNmels + kMelGroups + j] = n_j.
+// Returns 0, or 1 when a band is longer than 31 bins / the table does not fit.  fb = [kNfreq][kNmels].
+inline int lm_pack_filterbank(const float* fb, float* melw, uint32_t* melinfo) {
+  int lo_[kNmels], len_[kNmels];
+  for (int m = 0; m < kNmels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < kNfreq; ++k)
+      if (fb[(long)k * kNmels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    lo_[m] = lo < 0 ? 0 : lo;
+    len_[m] = lo < 0 ? 0 : hi - lo + 1;
+    if (len_[m] > 31) return 1;
+  }
+  for (int i = 0; i < kMaxMelW; ++i) melw[i] = 0.f;
+  int base = 0;
+  for (int j = 0; j < kMelGroups; ++j) {
+    int n = 0;
+    for (int l = 0; l < 32; ++l) n = len_[l + 32 * j] > n ? len_[l + 32 * j] : n;
+    if (base + n > kMaxMelTaps) return 1;
+    for (int l = 0; l < 32; ++l) {
+      const int m = l + 32 * j;
+      // bins 0 and 1024 of the power spectrum are stored unscaled (lm_power_regs): their weights keep the factor 1
+      for (int i = 0; i < len_[m]; ++i) {
+        const int k = lo_[m] + i;
+        melw[(base + i) * 32 + l] = fb[(long)k * kNmels + m] * ((k == 0 || k == kNfreq - 1) ? 1.0f : 0.25f);
+      }
+      melinfo[m] = (uint32_t)lo_[m];
+    }
+    melinfo[kNmels + j] = (uint32_t)base;
+    melinfo[kNmels + kMelGroups + j] = (uint32_t)n;
+    base += n;
+  }
+  return 0;
+}
 
 // Step 1+2+3: lane n1.  xs = this frame's 2048 samples (8-byte aligned), win = Hann[2048],
 // tw2[k2*32 + n1] = W_1024^{n1 k2}.  Writes T[k2*kTStride + n1].
@@ -65,7 +103,7 @@ HFT_HD void lm_cols_store(int lane, const float2 (&u)[32], float2* Z) {
 }
 
 // Step 5: real-input untangle + power.  twr[k] = exp(-2 pi i k / 2048), k = 0..512.
-// P[k] = |X[k]|^2 for k = 0..1024.  The lane's 32 (+1) powers are computed into registers first (lm_power_regs) and
+// P[k] = 4 |X[k]|^2 for k = 1..1023 and |X[k]|^2 for k = 0, 1024 (the mel weights carry the 0.25).  The lane's 32 (+1) powers are computed into registers first (lm_power_regs) and
 // stored afterwards (lm_power_store), so that P may overlay Z in shared memory (a __syncwarp() goes between the two).
 HFT_HD void lm_power_regs(int lane, const float2* Z, const float2* twr, float (&plo)[16], float (&phi)[16], float& p0, float& p1024) {
 #pragma unroll
@@ -77,8 +115,8 @@ HFT_HD void lm_power_regs(int lane, const float2* Z, const float2* twr, float (&
     float orr = bi, oi = -br;                        // O2 = B / i                    (= 2 O[k])
     float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;   // T2 = W^k O2
     float xr = ar + tr, xi = ai + ti, yr = ar - tr, yi = ai - ti;
-    plo[j] = 0.25f * (xr * xr + xi * xi);
-    phi[j] = 0.25f * (yr * yr + yi * yi);
+    plo[j] = xr * xr + xi * xi;                      // 4 |X[k]|^2: the 0.25 lives in the mel weights (lm_pack_filterbank)
+    phi[j] = yr * yr + yi * yi;
   }
   p0 = 0.f; p1024 = 0.f;
   if (lane == 0) {
@@ -103,15 +141,24 @@ HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {  
   lm_power_store(lane, plo, phi, p0, p1024, P);
 }
 
-// Step 6+7: banded mel sums and log.  Lane handles mel bins lane + 32 j.
+// Step 6+7: banded mel sums and log.  Lane handles mel bins lane + 32 j; every bin of a group runs the group's tap count (uniform trip
+// count, no divergence); reads past a band's end meet zero weights (P is followed by finite tile contents).
 HFT_HD void lm_mel(int lane, const float* P, const float* melw, const uint32_t* melinfo, float log_offset, float* out_row) {
 #pragma unroll
-  for (int j = 0; j < kNmels / 32; ++j) {
-    int m = lane + 32 * j;
-    uint32_t info = melinfo[m];
-    int start = info & 2047, len = (info >> 11) & 31, off = info >> 16;
+  for (int j = 0; j < kMelGroups; ++j) {
+    const int m = lane + 32 * j;
+    const float* p = P + melinfo[m];
+    const float* w = melw + melinfo[kNmels + j] * 32 + lane;
+    const int n = (int)melinfo[kNmels + kMelGroups + j];
     float acc = 0.f;
-    for (int i = 0; i < len; ++i) acc += P[start + i] * melw[off + i];
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+      acc = fmaf(p[i], w[i * 32], acc);
+      acc = fmaf(p[i + 1], w[(i + 1) * 32], acc);
+      acc = fmaf(p[i + 2], w[(i + 2) * 32], acc);
+      acc = fmaf(p[i + 3], w[(i + 3) * 32], acc);
+    }
+    for (; i < n; ++i) acc = fmaf(p[i], w[i * 32], acc);
 #ifdef __CUDA_ARCH__
     out_row[m] = logf(acc + log_offset);
 #else

@@ -254,9 +254,59 @@ extern "C" int hft_model_set_weights(hft_model* model, const float* const* weigh
   return HFT_OK;
 }
 
+// The two halves of the forward as separate calls (the reference exposes them as modules: Encoder_SPEC2MIDI.forward model_spec2midi.py:60-106,
+// Decoder_SPEC2MIDI.forward :145-216).  fp32 CUDA-core kernels; the fused hft_forward is the hot path.
+extern "C" int hft_forward_encoder(hft_model* model, const float* spec_dev, int64_t stride_b, int64_t stride_bin, int64_t stride_t, int32_t batch,
+                                   float* enc_out_dev, void* stream) {
+  HFT_REQUIRE(model && enc_out_dev && (spec_dev || batch == 0) && batch >= 0, HFT_ERR_ARG, "hft_forward_encoder: bad argument");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_forward_encoder: call hft_model_set_weights first");
+  reset_launch_count();
+  const long long per = (long long)m->nframe * m->nbin * m->H;
+  for (int b0 = 0; b0 < batch; b0 += m->max_batch) {
+    const int bc = batch - b0 < m->max_batch ? batch - b0 : m->max_batch;
+    { int rc = forward_f32(m, spec_dev + (long long)b0 * stride_b, stride_b, stride_bin, stride_t, bc, nullptr, (cudaStream_t)stream, 1, enc_out_dev + b0 * per); if (rc != HFT_OK) return rc; }
+  }
+  return HFT_OK;
+}
+
+extern "C" int hft_forward_decoder(hft_model* model, const float* enc_dev, int32_t batch, const hft_outputs* outputs, void* stream) {
+  HFT_REQUIRE(model && outputs && (enc_dev || batch == 0) && batch >= 0, HFT_ERR_ARG, "hft_forward_decoder: bad argument");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_REQUIRE(m->weights_set, HFT_ERR_STATE, "hft_forward_decoder: call hft_model_set_weights first");
+  reset_launch_count();
+  const long long fn = (long long)m->nframe * m->nnote, per = (long long)m->nframe * m->nbin * m->H;
+  for (int b0 = 0; b0 < batch; b0 += m->max_batch) {
+    const int bc = batch - b0 < m->max_batch ? batch - b0 : m->max_batch;
+    hft_outputs o = *outputs;
+    auto adv = [&](float*& p, long long n) { if (p) p += (long long)b0 * n; };
+    adv(o.onset_A, fn); adv(o.offset_A, fn); adv(o.mpe_A, fn); adv(o.velocity_A, fn * m->nvel);
+    adv(o.attention, (long long)m->nframe * m->heads * m->nnote * m->nbin);
+    adv(o.onset_B, fn); adv(o.offset_B, fn); adv(o.mpe_B, fn); adv(o.velocity_B, fn * m->nvel);
+    if (o.velocity_A_argmax) o.velocity_A_argmax += (long long)b0 * fn;
+    if (o.velocity_B_argmax) o.velocity_B_argmax += (long long)b0 * fn;
+    { int rc = forward_f32(m, nullptr, 0, 0, 0, bc, &o, (cudaStream_t)stream, 2, const_cast<float*>(enc_dev) + b0 * per); if (rc != HFT_OK) return rc; }
+  }
+  return HFT_OK;
+}
+
 extern "C" int hft_model_set_max_batch(hft_model* model, int32_t max_batch) {
   HFT_REQUIRE(model && max_batch >= 1, HFT_ERR_ARG, "hft_model_set_max_batch: bad argument");
-  reinterpret_cast<Model*>(model)->max_batch = max_batch;
+  Model* m = reinterpret_cast<Model*>(model);
+  if (max_batch < m->max_batch) hft_model_release_workspace(model);      // a smaller bound gives the memory back (work spaces only grow otherwise)
+  m->max_batch = max_batch;
+  return HFT_OK;
+}
+
+// Frees the activation work spaces of all precision modes (48 segments per call in fp16x3: 14 GB); weights and derived tensors stay.
+// The device is synchronised first: a forward still in flight may be using them.
+extern "C" int hft_model_release_workspace(hft_model* model) {
+  HFT_REQUIRE(model, HFT_ERR_ARG, "hft_model_release_workspace: NULL model");
+  Model* m = reinterpret_cast<Model*>(model);
+  HFT_CHECK_CUDA(cudaDeviceSynchronize());
+  tc_release_workspace(m);
+  cudaFree(m->ws);
+  m->ws = nullptr; m->ws_bytes = 0;
   return HFT_OK;
 }
 

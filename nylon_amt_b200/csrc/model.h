@@ -69,9 +69,10 @@ struct Model {
 };
 
 int model_build_schema(Model* m);
-int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s);
+int forward_f32(Model* m, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s, int stage = 0, float* enc_io = nullptr);
 int forward_tc(Model* m, int precision, const float* spec, long long sb, long long sbin, long long st, int B, const hft_outputs* o, cudaStream_t s);
 int tc_prepare_weights(Model* m, cudaStream_t s);
 void tc_destroy(Model* m);
+void tc_release_workspace(Model* m);
 
 }  // namespace hft

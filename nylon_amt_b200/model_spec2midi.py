@@ -98,7 +98,10 @@ class Encoder_SPEC2MIDI(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, spec_in):
-        raise NotImplementedError("the B200 path fuses encoder and decoder; call Model_SPEC2MIDI.forward")
+        """model_spec2midi.py:60-106: spec_in [B, n_bin, n_frame + 2 margin] -> [B, n_frame, n_bin, hid_dim] (eval semantics, fp32
+        CUDA-core kernels through hft_forward_encoder).  The library model holds both halves, so the module must belong to a
+        Model_SPEC2MIDI; the fused Model_SPEC2MIDI.forward is the hot path."""
+        return _parent_of(self)._forward_encoder(spec_in)
 
 
 class Decoder_SPEC2MIDI(nn.Module):
@@ -129,7 +132,28 @@ class Decoder_SPEC2MIDI(nn.Module):
         self.fc_velocity_time = nn.Linear(hid_dim, self.n_velocity)
 
     def forward(self, enc_spec):
-        raise NotImplementedError("the B200 path fuses encoder and decoder; call Model_SPEC2MIDI.forward")
+        """model_spec2midi.py:145-216: enc_spec [B, n_frame, n_bin, hid_dim] -> (onset_A, offset_A, mpe_A, velocity_A, attention,
+        onset_B, offset_B, mpe_B, velocity_B) (eval semantics, fp32 CUDA-core kernels through hft_forward_decoder)."""
+        return _parent_of(self)._forward_decoder(enc_spec)
+
+
+def _child_getstate(self):
+    st = self.__dict__.copy()
+    st.pop("_hft_parent", None)         # a weak reference does not pickle; Model_SPEC2MIDI.__setstate__ restores the link
+    return st
+
+
+Encoder_SPEC2MIDI.__getstate__ = _child_getstate
+Decoder_SPEC2MIDI.__getstate__ = _child_getstate
+
+
+def _parent_of(module):
+    ref = module.__dict__.get("_hft_parent")
+    parent = ref() if ref is not None else None
+    if parent is None:
+        raise RuntimeError("%s.forward needs the Model_SPEC2MIDI it belongs to (libhft_sm100 keeps encoder and decoder weights in one "
+                           "model handle); construct Model_SPEC2MIDI(encoder, decoder) first" % type(module).__name__)
+    return parent
 
 
 class _Handle:
@@ -165,6 +189,8 @@ class Model_SPEC2MIDI(nn.Module):
         super().__init__()
         self.encoder_spec2midi = encoder
         self.decoder_spec2midi = decoder
+        import weakref
+        encoder.__dict__["_hft_parent"] = decoder.__dict__["_hft_parent"] = weakref.ref(self)
 
     # ---- handle / weights ---------------------------------------------------------------------------------
     def _dims(self):
@@ -215,6 +241,12 @@ class Model_SPEC2MIDI(nn.Module):
             h.stamp = stamp
         return h
 
+    def release_workspace(self):
+        """Give the library's activation work spaces back (AMT.transcript sizes them for 48 segments per call: 14 GB in fp16x3)."""
+        h = self.__dict__.get("_hft")
+        if h is not None:
+            _lib.check(_lib.lib().hft_model_release_workspace(h.ptr), "hft_model_release_workspace")
+
     # ---- forward ------------------------------------------------------------------------------------------
     def forward(self, input_spec):
         if self.training:
@@ -242,6 +274,47 @@ class Model_SPEC2MIDI(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().hft_forward(h.ptr, _lib.PREC[self.precision], ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1),
                                               x.stride(2), B, ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward")
+        return tuple(outs)
+
+    # ---- the two halves as separate calls (Encoder_SPEC2MIDI.forward / Decoder_SPEC2MIDI.forward of the reference) -----------------
+    def _prepare(self):
+        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules()):
+            raise NotImplementedError("the separate encoder / decoder calls have eval semantics; train through Model_SPEC2MIDI.forward")
+        h = self.sync_weights()
+        if h.max_batch != self.max_batch:
+            _lib.check(_lib.lib().hft_model_set_max_batch(h.ptr, int(self.max_batch)), "hft_model_set_max_batch")
+            h.max_batch = self.max_batch
+        return h
+
+    def _forward_encoder(self, spec_in):
+        x = self._check_input(spec_in)
+        h = self._prepare()
+        e = self.encoder_spec2midi
+        out = torch.empty((x.shape[0], e.n_frame, e.n_bin, e.hid_dim), device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hft_forward_encoder(h.ptr, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), x.shape[0],
+                                                      ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)), "hft_forward_encoder")
+        return out
+
+    def _forward_decoder(self, enc_spec):
+        e, d = self.encoder_spec2midi, self.decoder_spec2midi
+        if not enc_spec.is_cuda:
+            raise RuntimeError("enc_spec is on %s: the B200 path has no CPU fallback" % enc_spec.device)
+        if enc_spec.dim() != 4 or tuple(enc_spec.shape[1:]) != (e.n_frame, e.n_bin, e.hid_dim):
+            raise RuntimeError("enc_spec must be [B, %d, %d, %d], got %s" % (e.n_frame, e.n_bin, e.hid_dim, tuple(enc_spec.shape)))
+        x = enc_spec.float().contiguous()
+        h = self._prepare()
+        B, F, N, V = x.shape[0], e.n_frame, d.n_note, d.n_velocity
+        heads = e.layers_freq[0].self_attention.n_heads
+        opt = dict(device=x.device, dtype=torch.float32)
+        outs = [torch.empty((B, F, N), **opt) for _ in range(3)] + [torch.empty((B, F, N, V), **opt), torch.empty((B, F, heads, N, e.n_bin), **opt)] + \
+               [torch.empty((B, F, N), **opt) for _ in range(3)] + [torch.empty((B, F, N, V), **opt)]
+        ptrs = [ctypes.c_void_p(t.data_ptr()) for t in outs]
+        o = _lib.hft_outputs(*ptrs, None, None)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hft_forward_decoder(h.ptr, ctypes.c_void_p(x.data_ptr()), B, ctypes.byref(o), ctypes.c_void_p(stream)), "hft_forward_decoder")
         return tuple(outs)
 
     def forward_into(self, input_spec, outs, want_attention=True, velocity_argmax=None):
@@ -313,6 +386,12 @@ class Model_SPEC2MIDI(nn.Module):
     def state_dict(self, *args, **kwargs):                # m_training.py:384 torch.save({'model_dict': model.state_dict(), ...})
         self._sync_trained()
         return super().state_dict(*args, **kwargs)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        import weakref
+        for child in (self.encoder_spec2midi, self.decoder_spec2midi):
+            child.__dict__["_hft_parent"] = weakref.ref(self)
 
     def __getstate__(self):
         self._sync_trained()          # pickle.dump(model) after training (m_training.py:373) must see the trained weights

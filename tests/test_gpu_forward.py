@@ -234,3 +234,50 @@ def test_velocity_argmax_epilogue_equals_argmax_of_logits(golden_dir, precision,
     assert torch.equal(va[0], vb[0]) and torch.equal(va[1], vb[1])
     for i in (0, 1, 2, 5, 6, 7):
         assert torch.equal(outs[i], outs2[i])
+
+
+def test_encoder_and_decoder_modules_called_separately(reduced):
+    """The reference exposes the two halves as modules (model_spec2midi.py:60 Encoder_SPEC2MIDI.forward, :145 Decoder_SPEC2MIDI.forward;
+    Model_SPEC2MIDI.forward is decoder(encoder(x)), :15-35): enc = model.encoder_spec2midi(x); model.decoder_spec2midi(enc) must give
+    the 9-tuple of the fused call, and the memory must equal the oracle's."""
+    import pickle
+    model, g = reduced
+    model.precision = "fp32"
+    spec = torch.from_numpy(g["spec"]).cuda()
+    enc = model.encoder_spec2midi(spec)
+    assert tuple(enc.shape) == (2, 128, 256, 64)
+    orc = ho.Oracle({k: v.cpu() for k, v in model.state_dict().items()}, 2)
+    mem = orc.encoder(torch.from_numpy(g["spec"])).reshape(2, 128, 256, 64)        # oracle returns [B*F, bin, H]
+    assert float((enc.cpu() - mem).abs().max()) <= 1e-4
+    out = model.decoder_spec2midi(enc)
+    full = model(spec)
+    for n, a, b in zip(NAMES, out, full):
+        assert torch.equal(a, b), n
+    _golden_check(out, g, TOL_FP32)
+    # the parent link survives pickling (m_training.py:373 pickles the whole model)
+    clone = pickle.loads(pickle.dumps(model)).cuda()
+    clone.precision = "fp32"
+    assert torch.equal(clone.encoder_spec2midi(spec), enc)
+
+
+def test_workspace_is_released_on_request_and_when_max_batch_drops(golden_dir):
+    """The activation work space grows with max_batch (AMT.transcript raises it to 48 segments per call) and must be returnable."""
+    g = np.load(os.path.join(golden_dir, "hft_paper.npz"))
+    model = hft.build_model(hft.default_config(), 256, 512, 3, 4, seed=1234, device="cuda")
+    spec = torch.from_numpy(g["spec"]).cuda()
+    model.max_batch = 1
+    ref = model(spec)[5].clone()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    model.max_batch = 24
+    assert torch.equal(model(spec)[5], ref)
+    torch.cuda.synchronize()
+    grown = free0 - torch.cuda.mem_get_info()[0]
+    assert grown > 4 << 30                                     # ~7 GB of fp16x3 work space for 24 segments
+    model.release_workspace()
+    assert free0 - torch.cuda.mem_get_info()[0] < 1 << 30
+    assert torch.equal(model(spec)[5], ref)                    # re-allocated on demand
+    model.max_batch = 1                                        # lowering the bound releases as well
+    assert torch.equal(model(spec)[5], ref)
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < 1 << 30

@@ -21,19 +21,9 @@ extern "C" int hostsim_logmel(const float* wav, long n, const float* window, con
     twr[k] = make_float2((float)cos(a), (float)sin(a));
   }
   std::vector<float> melw(kMaxMelW, 0.f);
-  std::vector<uint32_t> melinfo(kNmels);
-  int off = 0;
-  for (int m = 0; m < kNmels; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < kNfreq; ++k)
-      if (fb[(long)k * kNmels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-    int len = lo < 0 ? 0 : hi - lo + 1;
-    if (len > 31 || off + len > kMaxMelW) return 1;
-    for (int i = 0; i < len; ++i) melw[off + i] = fb[(long)(lo + i) * kNmels + m];
-    melinfo[m] = mel_pack(lo < 0 ? 0 : lo, len, off);
-    off += len;
-  }
-  std::vector<float> xs(kNfft), P(kNfreq);
+  std::vector<uint32_t> melinfo(kMelInfo);
+  if (lm_pack_filterbank(fb, melw.data(), melinfo.data())) return 1;
+  std::vector<float> xs(kNfft), P(kNfreq + 64, 0.f);   // taps past a band's end read finite padding
   std::vector<float2> Tt(32 * kTStride), Z(1024);
   for (long t = 0; t < T; ++t) {
     for (int i = 0; i < kNfft; ++i) {
