@@ -47,7 +47,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit"
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
@@ -67,8 +67,17 @@ class ClockSampler(threading.Thread):
         for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
             if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
                 reasons.append(n)
+        def fl(col):
+            v = []
+            for r in self.rows:
+                try:
+                    v.append(float(r[col]))
+                except (IndexError, ValueError):
+                    pass
+            return sorted(v)
+        pw, pl = fl(6), fl(7)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": pl[-1] if pl else None}
 
 
 def host_threads():
