@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhft_sm100.so")
+LIB_PATH = os.environ.get("HFT_LIB_PATH") or os.path.join(_HERE, "lib", "libhft_sm100.so")   # HFT_LIB_PATH: kernel-variant experiments only
 
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x3": 3, "mixed": 4}
 

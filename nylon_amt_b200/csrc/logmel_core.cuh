@@ -70,10 +70,8 @@ inline int lm_pack_filterbank(const float* fb, float* melw, uint32_t* melinfo) {
   return 0;
 }
 
-// Step 1+2+3: lane n1.  xs = this frame's 2048 samples (8-byte aligned), win = Hann[2048],
-// tw2[k2*32 + n1] = W_1024^{n1 k2}.  Writes T[k2*kTStride + n1].
-HFT_HD void lm_rows(int lane, const float* xs, const float* win, const float2* tw2, float2* T) {
-  float2 v[32];
+// Step 1: lane n1 loads its 32 windowed points.  xs = this frame's 2048 samples (8-byte aligned), win = Hann[2048].
+HFT_HD void lm_rows_load(int lane, const float* xs, const float* win, float2 (&v)[32]) {
   const float2* x2 = reinterpret_cast<const float2*>(xs);
   const float2* w2 = reinterpret_cast<const float2*>(win);
 #pragma unroll
@@ -81,18 +79,30 @@ HFT_HD void lm_rows(int lane, const float* xs, const float* win, const float2* t
     float2 a = x2[lane + 32 * n2], w = w2[lane + 32 * n2];
     v[n2] = make_float2(a.x * w.x, a.y * w.y);
   }
-  hft_fft32(v);
+}
+// Step 3: twiddle by tw2[k2*32 + n1] = W_1024^{n1 k2} and write T[k2*kTStride + n1].
+HFT_HD void lm_rows_store(int lane, const float2 (&v)[32], const float2* tw2, float2* T) {
 #pragma unroll
   for (int k2 = 0; k2 < 32; ++k2) {
     float2 y = v[HFT_BITREV5(k2)], w = tw2[k2 * 32 + lane];
     T[k2 * kTStride + lane] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
   }
 }
+// Step 1+2+3 in one call.
+HFT_HD void lm_rows(int lane, const float* xs, const float* win, const float2* tw2, float2* T) {
+  float2 v[32];
+  lm_rows_load(lane, xs, win, v);
+  hft_fft32(v);
+  lm_rows_store(lane, v, tw2, T);
+}
 
 // Step 4a: lane k2 reads its row of the transposed tile and transforms it (result stays in registers).
-HFT_HD void lm_cols_load(int lane, const float2* T, float2 (&u)[32]) {
+HFT_HD void lm_cols_load_raw(int lane, const float2* T, float2 (&u)[32]) {
 #pragma unroll
   for (int n1 = 0; n1 < 32; ++n1) u[n1] = T[lane * kTStride + n1];
+}
+HFT_HD void lm_cols_load(int lane, const float2* T, float2 (&u)[32]) {
+  lm_cols_load_raw(lane, T, u);
   hft_fft32(u);
 }
 
@@ -143,8 +153,19 @@ HFT_HD void lm_power(int lane, const float2* Z, const float2* twr, float* P) {  
 
 // Step 6+7: banded mel sums and log.  Lane handles mel bins lane + 32 j; every bin of a group runs the group's tap count (uniform trip
 // count, no divergence); reads past a band's end meet zero weights (P is followed by finite tile contents).
+#ifndef HFT_LM_FASTLOG
+#define HFT_LM_FASTLOG 1        // log through MUFU.LG2 (__logf, abs error ~1e-6 on the log) instead of the 20-instruction logf
+#endif
+#ifndef HFT_LM_UNROLL_J
+#define HFT_LM_UNROLL_J 0       // 1: the eight bin groups unrolled; 0: a loop -- measured r02: 8.49 vs 8.86 ms per 10 h (the hot loop is ~35 KB of SASS;
+                                // sharing one copy of the FFT between the two passes through a two-trip loop was slower: 8.91 ms)
+#endif
 HFT_HD void lm_mel(int lane, const float* P, const float* melw, const uint32_t* melinfo, float log_offset, float* out_row) {
+#if HFT_LM_UNROLL_J
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int j = 0; j < kMelGroups; ++j) {
     const int m = lane + 32 * j;
     const float* p = P + melinfo[m];
@@ -160,7 +181,11 @@ HFT_HD void lm_mel(int lane, const float* P, const float* melw, const uint32_t* 
     }
     for (; i < n; ++i) acc = fmaf(p[i], w[i * 32], acc);
 #ifdef __CUDA_ARCH__
+#if HFT_LM_FASTLOG
+    out_row[m] = __logf(acc + log_offset);
+#else
     out_row[m] = logf(acc + log_offset);
+#endif
 #else
     out_row[m] = ::logf(acc + log_offset);
 #endif
