@@ -80,6 +80,41 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": pl[-1] if pl else None}
 
 
+_FP32_PEAK = {}
+
+
+def fp32_peak(L, dev):
+    """The chip's fp32 FMA rate measured on this box (hft_probe_fp32_fma timed with CUDA events, best of 3 after a warm-up launch);
+    falls back to the nominal figure if the probe fails.  Returns (TFLOP/s, source string)."""
+    import torch
+    key = str(dev)
+    if key in _FP32_PEAK:
+        return _FP32_PEAK[key]
+    res = (FP32_PEAK_TFLOPS, FP32_PEAK_SRC)
+    try:
+        scratch = torch.zeros(16, device=dev)
+        flop = ctypes.c_double(0.0)
+        stream = torch.cuda.current_stream(dev)
+        best = None
+        for i in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = L.hft_probe_fp32_fma(20000, ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(flop), ctypes.c_void_p(stream.cuda_stream))
+            e1.record(stream)
+            e1.synchronize()
+            if rc != 0:
+                raise RuntimeError("probe failed")
+            ms = e0.elapsed_time(e1)
+            if i > 0:
+                best = ms if best is None else min(best, ms)
+        res = (flop.value / best / 1e9, "measured on this box: hft_probe_fp32_fma (16 independent FMA chains per thread, 8 x 256 threads per SM), "
+                                        "best of 3; nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = %.1f" % FP32_PEAK_TFLOPS)
+    except Exception as e:
+        res = (FP32_PEAK_TFLOPS, FP32_PEAK_SRC + " (probe unavailable: %s)" % e)
+    _FP32_PEAK[key] = res
+    return res
+
+
 def host_threads():
     """Threads the CPU legs use: every core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 when
     nproc-per-node > 1, which would time the reference arm on ONE core (r01: the arm hit the driver's limit at N = 2, 4, 8)."""
@@ -238,6 +273,7 @@ def run_logmel(args, hft, _lib, L, dev, dist, rank, world, hours=None, steps=Non
     audio_s = n_clips * clip / 16000.0
     pk = peaks()
     gbs = n_clips * T * LOGMEL_BYTES_PER_FRAME / ms / 1e6
+    f32_peak, f32_src = fp32_peak(L, dev)
     gflop_frame = LOGMEL_FLOP_PER_FRAME / 1e9
     tf32 = n_clips * T * gflop_frame / ms                       # GFLOP / ms = TFLOP/s of fp32 arithmetic actually issued
     # what a user of the reference gets on this GPU today: the reference's own torchaudio MelSpectrogram + log (cuFFT + dense mel matmul),
@@ -274,8 +310,8 @@ def run_logmel(args, hft, _lib, L, dev, dist, rank, world, hours=None, steps=Non
             "gpu_launches": int(n_launch), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                          "traffic": None, "peak_source": pk["src"], "algorithmic_bytes_per_frame": LOGMEL_BYTES_PER_FRAME,
-                         "fp32": {"achieved": tf32, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf32 / FP32_PEAK_TFLOPS,
-                                  "flop_per_frame": LOGMEL_FLOP_PER_FRAME, "peak_source": FP32_PEAK_SRC},
+                         "fp32": {"achieved": tf32, "peak": f32_peak, "unit": "TFLOP/s", "frac": tf32 / f32_peak,
+                                  "flop_per_frame": LOGMEL_FLOP_PER_FRAME, "peak_source": f32_src},
                          "note": "the kernel is bounded by fp32 issue + shared-memory traffic before HBM (DESIGN.md 5): both fractions are reported"},
             "torchaudio_gpu": None if lib_ms is None else {"ms_per_step_equiv": lib_ms, "value": world * audio_s / (lib_ms / 1e3), "unit": "audio-s/s",
                                                            "what": "reference's torchaudio MelSpectrogram + log in eager PyTorch on the same GPU (cuFFT + dense mel matmul), scaled from a 2 h sample"},
@@ -343,6 +379,7 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world, steps=None, warmup=Non
         _lib.check(L.hft_profile_read(k, ctypes.byref(t), ctypes.byref(c)), "hft_profile_read")
         classes[n] = {"ms": round(t.value, 3), "launches": c.value}
     seg_s = world * B / (ms / 1e3)
+    f32_peak, f32_src = fp32_peak(L, dev)
     gflop = 3 * 16.57 * B                      # forward 16.57 GFLOP / segment, backward ~2x
     cpu = None
     if rank == 0 and world == 1 and cpu_leg and not args.no_cpu_baseline:
@@ -382,8 +419,8 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world, steps=None, warmup=Non
             "allreduce_ms": t_ar[0] / 3, "allreduce_exposed_ms": max(0.0, ms - ms_no_ar), "ms_per_step_without_allreduce": ms_no_ar,
             "allreduce": "NCCL sum of the flat fp32 gradient bucket" if world > 1 else "single process: no collective (world 1)",
             "loss_after": loss, "classes": classes, "gpu_launches": int(n_launch), "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": gflop / ms / FP32_PEAK_TFLOPS, "traffic": None, "peak_source": FP32_PEAK_SRC},
+            "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": f32_peak, "unit": "TFLOP/s",
+                         "frac": gflop / ms / f32_peak, "traffic": None, "peak_source": f32_src},
             "cpu_baseline": cpu}
 
 

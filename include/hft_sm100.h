@@ -189,6 +189,11 @@ int64_t hft_last_launch_count(void);
 #define HFT_KCLASS_HEADS 5
 #define HFT_KCLASS_COUNT 6
 int hft_profile_enable(int on);
+
+/* Measurement probe (bench.py): launches a kernel of independent fp32 FMA chains on every SM (8 CTAs of 256 threads each, 16 chains per
+ * thread, `iters` steps) and reports the flop it issues; timed by the caller with CUDA events it gives the chip's fp32 FMA rate under
+ * the current clocks -- the measured denominator of `roofline.fp32` for the CUDA-core kernels (log-mel, training step). */
+int hft_probe_fp32_fma(int32_t iters, float* scratch_dev, double* flop_out, void* stream);
 int hft_profile_read(int kclass, double* ms, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------------------------

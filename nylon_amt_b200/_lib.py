@@ -86,6 +86,7 @@ SYMBOLS = {
     "hft_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]),
     "hft_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "hft_probe_fp32_fma": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
     "hft_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 }
 

@@ -84,3 +84,35 @@ extern "C" int hft_profile_read(int kclass, double* ms, int64_t* launches) {
   g_recs[kclass].clear();
   return 0;
 }
+
+// ---- measurement probe: the chip's fp32 FMA issue rate (the roofline denominator of the CUDA-core kernels; MEASURED_PEAKS.json holds HBM and
+// bf16 tensor figures only).  Every thread runs 16 independent FMA chains; 2 * 16 * iters flop per thread.
+namespace hft {
+__global__ void __launch_bounds__(256) fp32_fma_probe_kernel(int iters, float seed, float* __restrict__ out) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+  const float m = 0.999f + seed * 1e-9f, c = 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;          // never true: keeps the chains alive
+}
+}  // namespace hft
+
+extern "C" int hft_probe_fp32_fma(int32_t iters, float* scratch_dev, double* flop_out, void* stream) {
+  HFT_REQUIRE(iters >= 1 && scratch_dev && flop_out, HFT_ERR_ARG, "hft_probe_fp32_fma: bad argument");
+  const int sms = hft::num_sms(), blocks = sms * 8;
+  hft::reset_launch_count();
+  {
+    hft::LaunchScope ls(HFT_KCLASS_NORM, stream);
+    hft::fp32_fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, scratch_dev);
+  }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  *flop_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+  return 0;
+}
