@@ -53,6 +53,23 @@ def load():
     return ref_amt, ref_model
 
 
+def load_train():
+    """The reference's training/train.py (train(), valid()) as a module; mir_eval (absent here, used only when valid(metrics=True)) is
+    stubbed the way pretty_midi is."""
+    if not os.path.isfile(os.path.join(REF_CODE, "training", "train.py")):
+        raise RuntimeError("reference training/train.py not present under " + REF_ROOT)
+    if "mir_eval" not in sys.modules:
+        try:
+            import mir_eval  # noqa: F401
+        except Exception:
+            sys.modules["mir_eval"] = types.ModuleType("mir_eval")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hftt_reference_train", os.path.join(REF_CODE, "training", "train.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def config():
     import json
     with open(os.path.join(REF_CODE, "corpus", "config.json"), "r", encoding="utf-8") as f:

@@ -281,3 +281,88 @@ def test_workspace_is_released_on_request_and_when_max_batch_drops(golden_dir):
     assert torch.equal(model(spec)[5], ref)
     torch.cuda.synchronize()
     assert free0 - torch.cuda.mem_get_info()[0] < 1 << 30
+
+
+@pytest.mark.parametrize("T", [0, 1, 127, 128, 129])
+def test_transcript_edge_lengths(reduced, T):
+    """amt.py:66-118 on empty / one-frame / ragged features: output rows = ceil(T / 128) * 128 (the reference pads with len_s rows), values
+    equal to the oracle run on the windows the reference would build (amt.py:70-73,88-89)."""
+    model, g = reduced
+    model.precision = "fp32"
+    cfg = hft.default_config()
+    amt = hft.AMT(cfg, None, batch_size=4)
+    amt.model = model
+    rng = np.random.default_rng(T)
+    feat = (rng.standard_normal((T, 256)) * 2 - 9).astype(np.float32)
+    out = amt.transcript(feat)
+    rows = int(np.ceil(T / 128) * 128)
+    assert len(out) == 8
+    for k, a in enumerate(out):
+        assert a.shape == (rows, 88) and a.dtype == (np.int8 if k in (3, 7) else np.float32), (T, k, a.shape, a.dtype)
+    if T == 0:
+        return
+    spec = ho.segment_feature(feat)
+    orc = ho.Oracle({k: v.cpu() for k, v in model.state_dict().items()}, 2)(spec)
+    for k, i in ((0, 0), (1, 1), (2, 2), (4, 5), (5, 6), (6, 7)):
+        ref = orc[i].reshape(rows, 88).numpy()
+        assert float(np.abs(out[k] - ref).max()) <= TOL_FP32, (T, k)
+    for k, i in ((3, 3), (7, 8)):
+        ref = orc[i].reshape(rows, 88, -1).argmax(2).numpy()
+        assert (out[k] == ref).mean() > 0.999, (T, k)
+
+
+def test_wave2feature_edge_lengths():
+    """amt.py:59-61 on an empty and a sub-hop waveform: torch.stft(center=True) yields 1 + n // 256 frames, all at the log(1e-8) floor for
+    silence."""
+    amt = hft.AMT(hft.default_config(), None, None)
+    for n in (0, 1, 255):
+        f = amt.wave2feature(torch.zeros(n, device="cuda"))
+        assert tuple(f.shape) == (1 + n // 256, 256)
+        assert torch.all(f == float(np.log(np.float32(1e-8))))
+
+
+def test_unmodified_reference_amt_drives_the_mirror_model(golden_dir):
+    """The reference's OWN AMT class (hftt_code/model/amt.py, staged unmodified in oracle/_ref) with `self.model` = the mirror module on
+    cuda: its batch-1 loop (amt.py:88-113: a non-contiguous `.T.unsqueeze(0)` view per segment, `.squeeze(0)`, `.argmax(2)`, `.to('cpu')`)
+    and its mpe2note run against Model_SPEC2MIDI.forward of this repo and reproduce the fixture the all-reference run wrote."""
+    import importlib
+    ref_copy = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_copy, "hftt_code", "model", "amt.py")):
+        pytest.skip("oracle/_ref is not staged (run __graft_entry__.build() where /root/reference exists)")
+    old = os.environ.get("NYLON_REF_ROOT")
+    os.environ["NYLON_REF_ROOT"] = ref_copy
+    try:
+        from oracle import _refload
+        importlib.reload(_refload)
+        ref_amt, _ = _refload.load()
+        cfg = _refload.config()
+    finally:
+        if old is None:
+            os.environ.pop("NYLON_REF_ROOT", None)
+        else:
+            os.environ["NYLON_REF_ROOT"] = old
+    t = np.load(os.path.join(golden_dir, "transcript_reduced.npz"))
+    g = np.load(os.path.join(golden_dir, "hft_reduced.npz"))
+    model = hft.build_model(hft.default_config(), 64, 128, 2, 2, device="cpu")
+    sd = {k[2:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("w:")}
+    for n in ("onset", "offset", "mpe"):
+        for s in ("freq", "time"):
+            sd["decoder_spec2midi.fc_%s_%s.weight" % (n, s)] *= float(t["gain"])
+    model.load_state_dict(sd)
+    A = ref_amt.AMT(cfg, None, None)
+    A.device = "cuda"
+    A.model = model.cuda().eval()
+    names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "onset_B", "offset_B", "mpe_B", "velocity_B"]
+    for precision in ("fp32", "fp16x3"):
+        A.model.precision = precision
+        for prefix, out in (("t_", A.transcript(t["feature"])), ("s_", A.transcript_stride(t["feature"], 32))):
+            for n, a in zip(names, out):
+                ref = t[prefix + n]
+                assert a.shape == ref.shape and a.dtype == ref.dtype, (prefix, n)
+                if n.startswith("velocity"):
+                    assert (a == ref).mean() > 0.999, (precision, prefix, n)
+                else:
+                    assert float(np.abs(a - ref).max()) <= TOL_FP32, (precision, prefix, n)
+        out = A.transcript(t["feature"])
+        notes = A.mpe2note(a_onset=out[4], a_offset=out[5], a_mpe=out[6], a_velocity=out[7])
+        assert len(notes) == len(json.loads(str(t["notes_B"])))

@@ -297,3 +297,37 @@ def test_train_returns_with_module_synced(golden_dir):
     hft.training.train(model, it, opt)
     after = model.decoder_spec2midi.fc_onset_time.bias.detach()
     assert not torch.equal(before, after) and not opt._stale
+
+
+def test_unmodified_reference_train_and_valid_functions_drive_the_mirror(golden_dir):
+    """The reference's OWN train() and valid() (hftt_code/training/train.py:63-160, :168-262, staged unmodified in oracle/_ref by
+    __graft_entry__.build()) called with the mirror module, stock criteria and a stock torch.optim.Adam -- nothing of this repo's
+    training.py on the path.  The fixture batch twice = train.py's epoch over a two-item iterator: epoch loss = (loss + loss2) / 2 of
+    tests/golden/train_reduced.npz."""
+    import importlib
+    ref_copy = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_copy, "hftt_code", "training", "train.py")):
+        pytest.skip("oracle/_ref is not staged (run __graft_entry__.build() where /root/reference exists)")
+    old = os.environ.get("NYLON_REF_ROOT")
+    os.environ["NYLON_REF_ROOT"] = ref_copy
+    try:
+        from oracle import _refload
+        importlib.reload(_refload)
+        ref_train = _refload.load_train()
+    finally:
+        if old is None:
+            os.environ.pop("NYLON_REF_ROOT", None)
+        else:
+            os.environ["NYLON_REF_ROOT"] = old
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    model = _model(golden_dir)
+    batch = tuple(x.cpu() for x in _batch(t))                     # train() moves every item to `device` itself (train.py:73-77)
+    iterator = [batch, batch]
+    optimizer = torch.optim.Adam(model.parameters(), lr=float(t["lr"]))
+    crit = [torch.nn.BCELoss(), torch.nn.BCELoss(), torch.nn.BCELoss(), torch.nn.CrossEntropyLoss()] * 2
+    epoch_loss = ref_train.train(model, iterator, optimizer, *crit, 1.0, 1.0, "cuda", False)
+    want = 0.5 * (float(t["loss"]) + float(t["loss2"]))
+    assert abs(epoch_loss - want) <= 1e-4 * abs(want), (epoch_loss, want)
+    assert model.training
+    total, n = ref_train.valid(model, iterator, *crit, 1.0, 1.0, "cuda", False)
+    assert n == 2 and not model.training and np.isfinite(total) and total / n < float(t["loss"])      # two Adam steps later the loss is lower
