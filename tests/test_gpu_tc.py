@@ -127,27 +127,39 @@ def test_forward_split_fp16_meets_fp32_budget(golden_dir, size):
 
 
 @pytest.mark.parametrize("kind,size", [("fp16", "reduced"), ("bf16", "reduced"), ("fp16", "paper"), ("bf16", "paper")])
-def test_forward_tensor_core_vs_oracle(golden_dir, kind, size):
-    """Full forward on tensor cores.  A heads are held to the north_star 16-bit budget (2e-2 abs); for the B heads the
-    measured error is reported and bounded by the budget the CPU emulation of the same rounding points predicts for
-    seeded random weights (tools/precision_study.py: the time stack amplifies upstream rounding ~10x)."""
+def test_forward_single_product_modes_vs_reference_golden(golden_dir, kind, size):
+    """The single-product tensor-core modes against the REFERENCE goldens on seeded (freshly initialised) weights.  These weights amplify
+    upstream rounding ~20x in the time stack, so only part of the outputs can meet the 16-bit budget (2e-2) here -- the mode
+    that meets it everywhere on this fixture is `mixed` (test below), and on trained-like weights fp16 / bf16 meet it on every output
+    (tests/test_gpu_trained.py).  Asserted: every output finite; the outputs that do meet 2e-2 on this fixture keep meeting it (A-head
+    probabilities, the returned attention, fp16's velocity A and B-head probabilities); the rest is bounded by 1.5x the error the CPU
+    emulation of the same rounding points predicts (tools/precision_study.py), as a regression guard, and printed."""
     hid, pf, L, h = {"reduced": (64, 128, 2, 2), "paper": (256, 512, 3, 4)}[size]
     g = np.load(os.path.join(golden_dir, "hft_%s.npz" % size))
     model = hft.build_model(hft.default_config(), hid, pf, L, h, seed=1234, device="cuda")
-    spec = torch.from_numpy(g["spec"][:1]).cuda()
-    model.precision = "fp32"
-    ref = [t.clone() for t in model(spec)]
     model.precision = kind
-    out = model(spec)
+    out = model(torch.from_numpy(g["spec"]).cuda())
     names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "attention", "onset_B", "offset_B", "mpe_B", "velocity_B"]
-    err = {n: float((a - b).abs().max()) for n, a, b in zip(names, out, ref)}
-    print(kind, size, err)
-    for n in names:
-        assert np.isfinite(err[n]), err
-    assert max(err[n] for n in ("onset_A", "offset_A", "mpe_A")) <= 2e-2, err
-    assert err["attention"] <= 2e-2, err
-    budget_vel_a = {"bf16": 0.15, "fp16": 0.03}[kind]
-    assert err["velocity_A"] <= budget_vel_a, err
+    err = {}
+    for i, n in enumerate(names):
+        o = out[i].cpu()
+        assert torch.isfinite(o).all(), n
+        if n.startswith("velocity"):
+            ref, mine = g[n + "_sub"], o[:, ::8, ::8, :].numpy()
+        elif n == "attention":
+            ref, mine = g["attention_sub"], o[:, ::16, :, ::11, :].numpy()
+        else:
+            ref, mine = g[n], o.numpy()
+        err[n] = float(np.abs(mine - ref).max())
+    print(kind, size, {k: "%.1e" % v for k, v in err.items()})
+    assert max(err[n] for n in ("onset_A", "offset_A", "mpe_A", "attention")) <= 2e-2, err
+    sig_b = max(err[n] for n in ("onset_B", "offset_B", "mpe_B"))
+    if kind == "fp16":
+        assert err["velocity_A"] <= 2e-2 and sig_b <= 2e-2, err
+        assert err["velocity_B"] <= 0.15, err                  # emulation: 0.10 (paper), measured 0.088
+    else:
+        assert err["velocity_A"] <= 6e-2 and sig_b <= 6e-2, err      # emulation: 4.0e-2 / 4e-2, measured 3.7e-2 / 3.8e-2
+        assert err["velocity_B"] <= 0.45, err                  # emulation: 0.31, measured 0.29
 
 
 def _forward_in_subprocess(golden_dir, env, out_path, strided):
