@@ -413,6 +413,7 @@ class _Trainer:
         self.n = int(L.hft_model_param_floats(handle.ptr))
         self.offsets = [int(L.hft_model_param_offset(handle.ptr, i)) for i in range(len(handle.names))]
         self.grads = torch.zeros(self.n, device=device)
+        self.tape_id = 0               # bumped by every train-mode forward: a backward must meet the tape its own forward wrote
 
     def __del__(self):
         try:
@@ -447,14 +448,15 @@ class _TrainForward(torch.autograd.Function):
             _lib.check(L.hft_train_forward(t.ptr, B, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), ctypes.byref(o),
                                            ctypes.c_void_p(stream)), "hft_train_forward")
         ctx.model, ctx.trainer, ctx.x, ctx.handle = model, t, x, h
-        ctx.tape_id = t.__dict__["tape_id"] = t.__dict__.get("tape_id", 0) + 1
+        t.tape_id += 1
+        ctx.tape_id = t.tape_id
         ctx.shapes = [p.shape for p in params]
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts):
         t, x = ctx.trainer, ctx.x
-        if t.__dict__.get("tape_id") != ctx.tape_id:
+        if t.tape_id != ctx.tape_id:
             raise RuntimeError("backward through a train-mode forward whose activation tape was overwritten by a later forward of the same module")
         keep = [None if g is None else (g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()) for g in gouts]
         ptrs = [ctypes.c_void_p(g.data_ptr()) if g is not None else None for g in keep]

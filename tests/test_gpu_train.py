@@ -331,3 +331,20 @@ def test_unmodified_reference_train_and_valid_functions_drive_the_mirror(golden_
     assert model.training
     total, n = ref_train.valid(model, iterator, *crit, 1.0, 1.0, "cuda", False)
     assert n == 2 and not model.training and np.isfinite(total) and total / n < float(t["loss"])      # two Adam steps later the loss is lower
+
+
+def test_backward_through_an_overwritten_tape_fails_loudly(golden_dir):
+    """One activation tape per module: a second train-mode forward overwrites it, so the first graph's backward must raise, not
+    return gradients of the wrong forward."""
+    t = np.load(os.path.join(golden_dir, "train_reduced.npz"))
+    model = _model(golden_dir).train()
+    batch = _batch(t)
+    loss1 = _reference_loop_loss(model, *batch)
+    loss2 = _reference_loop_loss(model, *batch)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        loss1.backward()
+    loss2.backward()                                   # the latest forward still owns the tape
+    assert all(p.grad is not None for p in model.parameters())
+    with torch.no_grad():                              # no graph requested: forward only
+        out = model(batch[0])
+    assert out[4] is None and not out[0].requires_grad
