@@ -301,6 +301,19 @@ int hft_trainer_set_dropout(hft_trainer* trainer, float p, uint32_t seed);
 /* mask_out_dev[i] = kept ? 1 / (1 - p) : 0 for i < n of one site: the multiplier the kernels apply (test / restatement aid). */
 int hft_dropout_mask(float p, uint32_t seed, int32_t site, int64_t n, float* mask_out_dev, void* stream);
 
+/* Component entry: the multi-head attention of the training step alone -- softmax(Q K^T / sqrt(dh)) V with dropout on the
+ * probabilities (MultiHeadAttentionLayer.forward, model_spec2midi.py:342-348) and, when d_ctx_dev is not NULL, its backward
+ * (what loss.backward(), training/train.py:158, runs through that node).  All tensors fp32 on the device:
+ *   q [n_seq * lq, ldq] (q_seq_stride = elements between consecutive sequences; 0 = the same queries for every sequence),
+ *   k, v [n_seq * lk, ldkv]; head h occupies columns h * dh .. of each; ctx, d_ctx [n_seq * lq, heads * dh]; lse, d_buf [n_seq, heads, lq];
+ *   dq [n_seq * lq, lddq], dk, dv [n_seq * lk, lddkv].
+ * use_tc: 1 = the tcgen05 kernels (split-fp16 products, fp32 accumulate; head_dim 32, lq, lk <= 256), 0 = the fp32 CUDA-core kernels,
+ * -1 = what the training step picks (tcgen05 where supported unless HFT_TRAIN_TC=0). */
+int hft_train_attention(int32_t use_tc, int32_t dh, int32_t heads, const float* q_dev, int32_t ldq, int64_t q_seq_stride, const float* k_dev,
+                        const float* v_dev, int32_t ldkv, int64_t n_seq, int32_t lq, int32_t lk, float p_drop, uint32_t seed, int32_t site,
+                        float* ctx_dev, float* lse_dev, const float* d_ctx_dev, float* dq_dev, int32_t lddq, float* dk_dev, float* dv_dev,
+                        int32_t lddkv, float* d_buf_dev, void* stream);
+
 /* torch.optim.Adam (no weight decay, no amsgrad) on flat vectors: grads are multiplied by grad_scale first (1 / world size
  * after a sum all-reduce); step counts from 1. */
 int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,

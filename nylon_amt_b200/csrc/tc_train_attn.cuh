@@ -1,0 +1,466 @@
+// tcgen05 attention for the TRAINING step, head_dim 32 (reduced model, BASELINE configs[4]): forward with the row
+// log-sum-exp, and the backward that recomputes the probabilities (reference MultiHeadAttentionLayer.forward,
+// model_spec2midi.py:342-348, under loss.backward(), training/train.py:158).  Same arguments as the fp32 CUDA-core
+// kernels they replace (attn_f32_r2_kernel, attn_bwd_dq_r2_kernel, attn_bwd_dkv_pair_kernel): fp32 Q | K | V, dO, O in
+// global memory, fp32 results.
+//
+// Arithmetic: every product runs on the tensor cores as THREE fp16 MMAs with fp32 accumulation in TMEM
+// (a.b = a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits), exp2 / dropout / the
+// dS formula in fp32 on the CUDA cores.  Gradients are tiny (loss means over B*128*88 positions), so dO is scaled by a
+// power of two per CTA (its largest magnitude lands in [1, 2)) before the split and the results are scaled back: every
+// output is linear in dO, powers of two are exact.
+//
+// Structure (one CTA = 256 threads = 128 TMEM lanes x 2 column halves, two CTAs per SM, 256 TMEM columns each):
+//   operands are staged by the threads themselves: fp32 rows -> hi | lo fp16 tiles in the K-major 64-byte-swizzled UMMA
+//   layout (a [rows, 32] tile serves as A / B K-major for the score-type products and as B MN-major for the
+//   accumulate-type products, so nothing is transposed);
+//   forward   (seq, head, 128 queries): per 128-key unit S = Q K^T -> each thread owns 64 columns of its row with its own
+//             max / sum (split softmax), writes P (hi | lo, dropout applied) in place over S, O_{unit,half} = P V with A from
+//             TMEM into its own 32 columns; the partial results are merged in the epilogue, lse = max + ln(sum);
+//   dQ kernel (seq, head, 128 queries), thread = query row: per 64-key chunk S = Q K^T, dP = dO V^T -> dS = P (dP - D) c
+//             in place -> dQ += dS K (A from TMEM); also writes D = rowsum(dO . O);
+//   dK/dV kernel (seq, head, 128 keys), thread = key row: per 64-query chunk S^T = K Q^T, dP^T = V dO^T -> P^T (dropped) and
+//             dS^T in place -> dV += P^T dO, dK += dS^T Q.
+//   The transposed pass recomputes S and dP on the tensor cores instead of transposing dS through shared memory: the
+//   score-type products have K = 32 and cost a fifth of the accumulate-type ones.
+#pragma once
+#include "tc_common.cuh"
+#include "tc_attn.cuh"          // ex2_approx
+#include "f32_kernels.cuh"      // Drop, drop_keep
+
+namespace hft {
+namespace tc {
+
+struct TAttnArgs {
+  const float* Q; int ldq; long long q_seq_stride;    // q_seq_stride 0: the same queries for every sequence (decoder layer zero)
+  const float* K; const float* V; int ldkv;
+  int Lq, Lk, heads;
+  float c;                                            // 1 / sqrt(head_dim)
+  float* ctx;                                         // forward out / backward in (O): [S * Lq, ldo]
+  int ldo;
+  float* lse;                                         // [S, heads, Lq]  (forward out / backward in)
+  const float* dO;                                    // [S * Lq, ldo]
+  float* dQ; int lddq;
+  float* dK; float* dV; int lddkv;
+  float* Dbuf;                                        // [S, heads, Lq]: written by the dQ kernel, read by the dK/dV kernel
+  Drop drop;
+};
+
+constexpr int kTThreads = 256;
+constexpr uint32_t kTAtom = 512;                      // 8 rows x 64 bytes: one 64B-swizzle atom of a [rows, 32] fp16 tile
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+// rows [0, n_valid) of an fp32 tensor (32 columns starting at src, row pitch ld) times `scale` -> hi | lo fp16 tiles in the
+// K-major 64B-swizzled UMMA layout (row r at r * 64, 16-byte chunk ch at position ch ^ ((r >> 1) & 3)); rows up to n_pad are zero.
+__device__ __forceinline__ void tstage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long ld, int n_valid, int n_pad, float scale) {
+  for (int i = threadIdx.x; i < n_pad * 4; i += kTThreads) {
+    const int r = i >> 2, ch = i & 3;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r < n_valid) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + (long long)r * ld + ch * 8);
+      a = __ldg(s4);
+      b = __ldg(s4 + 1);
+    }
+    uint32_t h[4], l[4];
+    split_pack<false>(a.x * scale, a.y * scale, h[0], l[0]);
+    split_pack<false>(a.z * scale, a.w * scale, h[1], l[1]);
+    split_pack<false>(b.x * scale, b.y * scale, h[2], l[2]);
+    split_pack<false>(b.z * scale, b.w * scale, h[3], l[3]);
+    const int off = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// largest |x| over n_rows x 32 values -> the power of two that brings it into [1, 2) (1 when everything is zero / denormal)
+__device__ __forceinline__ float tpow2_scale(const float* src, long long ld, int n_rows, float* s_red /*[9]*/) {
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < n_rows * 8; i += kTThreads) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (long long)(i >> 3) * ld + (i & 7) * 4));
+    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < kTThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+    const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
+    s_red[8] = (e == 0u || e >= 253u) ? 1.f : __uint_as_float((254u - e) << 23);
+  }
+  __syncthreads();
+  return s_red[8];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// forward: ctx = dropout(softmax(Q K^T c)) V, lse = logsumexp(Q K^T c)
+// ---------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs p, int lkp /* keys padded to a multiple of 128 */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_q = smem;                                   // hi at 0, lo at 8 KB
+  uint8_t* s_k = s_q + 2 * 128 * 64;                     // hi, lo: lkp * 64 each
+  uint8_t* s_v = s_k + 2 * lkp * 64;
+  float* s_ms = reinterpret_cast<float*>(s_v + 2 * lkp * 64);   // [4 partials][128 rows]
+  float* s_sum = s_ms + 4 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 4 * 128);   // [0] S ready, [1] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int seq = blockIdx.x, head = blockIdx.y, qt = blockIdx.z;
+  const int nu = lkp >> 7;                               // 128-key units
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  {
+    const int qv = min(128, p.Lq - qt * 128);
+    tstage_rows(s_q, s_q + 128 * 64, p.Q + (long long)seq * p.q_seq_stride + (long long)qt * 128 * p.ldq + head * 32, p.ldq, qv, 128, 1.f);
+    tstage_rows(s_k, s_k + lkp * 64, p.K + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp, 1.f);
+    tstage_rows(s_v, s_v + lkp * 64, p.V + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp, 1.f);
+  }
+  fence_proxy_async();                                   // generic-proxy shared-memory writes -> visible to the UMMA (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc_s = make_idesc(128, 128, false, false, false);   // S = Q K^T, both K-major
+  const uint32_t idesc_o = make_idesc(128, 32, false, false, true);     // O = P V, A from TMEM, B = V MN-major
+  const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_k), va = smem_u32(s_v);
+  auto issue_s = [&](int u) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+      const uint32_t qp = qa + (part == 1 ? 128 * 64 : 0), kp = ka + (part == 2 ? lkp * 64 : 0) + u * 128 * 64;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        umma_f16(tmem_base, make_sdesc(qp + k * 32, 16, kTAtom, kSwz64), make_sdesc(kp + k * 32, 16, kTAtom, kSwz64), idesc_s, acc);
+        acc = 1;
+      }
+    }
+  };
+  auto issue_pv = [&](int u) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t vp = va + (part == 2 ? lkp * 64 : 0) + (u * 128 + h * 64) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t pcol = (uint32_t)(h * 64 + (k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
+          umma_f16_ts(tmem_base + 128 + (u * 2 + h) * 32, tmem_base + pcol, make_sdesc(vp + k * 16 * 64, kTAtom, kTAtom, kSwz64), idesc_o, acc);
+          acc = 1;
+        }
+      }
+    }
+  };
+
+  const int r = quarter * 32 + lane;                     // query row inside the tile == TMEM lane
+  const int qrow = qt * 128 + r;
+  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const float c2 = p.c * kLog2e;
+  const long long drop_row = (((long long)seq * p.heads + head) * p.Lq + qrow) * p.Lk;
+
+  for (int u = 0; u < nu; ++u) {
+    if (threadIdx.x == 0) {
+      if (u > 0) issue_pv(u - 1);
+      issue_s(u);                                        // overwrites P of the previous unit: the MMA pipe runs in issue order
+      umma_commit(&bars[0]);
+    }
+    mbar_wait(&bars[0], u & 1);
+    fence_after_sync();
+    const int key0 = u * 128 + half * 64;                // first key of this thread's 64 columns
+    const int kvalid = p.Lk - key0;                      // valid keys among them (<= 0: none)
+    uint32_t v[2][32];
+    tmem_ld32(t_row + half * 64, v[0]);
+    tmem_ld32(t_row + half * 64 + 32, v[1]);
+    tmem_ld_wait();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cc * 32 + j < kvalid) mx = fmaxf(mx, __uint_as_float(v[cc][j]));
+    const float ms = kvalid > 0 ? mx * c2 : 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t pw[32];                                   // [hi 16 | lo 16]
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k0 = cc * 32 + 2 * j;
+        float e0 = k0 < kvalid ? ex2_approx(fmaf(__uint_as_float(v[cc][2 * j]), c2, -ms)) : 0.f;
+        float e1 = k0 + 1 < kvalid ? ex2_approx(fmaf(__uint_as_float(v[cc][2 * j + 1]), c2, -ms)) : 0.f;
+        sum += e0 + e1;
+        if (p.drop.thresh) {                             // dropout on the probabilities: O = (P . mask * scale) V, the sum stays undropped
+          e0 = drop_keep(p.drop, (unsigned long long)(drop_row + key0 + k0)) ? e0 * p.drop.scale : 0.f;
+          e1 = drop_keep(p.drop, (unsigned long long)(drop_row + key0 + k0 + 1)) ? e1 * p.drop.scale : 0.f;
+        }
+        split_pack<false>(e0, e1, pw[j], pw[16 + j]);
+      }
+      tmem_st32(t_row + half * 64 + cc * 32, pw);
+    }
+    s_ms[(u * 2 + half) * 128 + r] = ms;
+    s_sum[(u * 2 + half) * 128 + r] = sum;
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  if (threadIdx.x == 0) {
+    issue_pv(nu - 1);
+    umma_commit(&bars[1]);
+  }
+  // merge the partial softmaxes of the row: 2 * nu (max, sum) pairs
+  float M = -INFINITY;
+  for (int i = 0; i < 2 * nu; ++i)
+    if (s_sum[i * 128 + r] > 0.f) M = fmaxf(M, s_ms[i * 128 + r]);
+  float tot = 0.f;
+  for (int i = 0; i < 2 * nu; ++i)
+    if (s_sum[i * 128 + r] > 0.f) tot += s_sum[i * 128 + r] * ex2_approx(s_ms[i * 128 + r] - M);
+  const float inv = 1.f / tot;
+  mbar_wait(&bars[1], 0);
+  fence_after_sync();
+  if (half == 0) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = 0.f;
+    for (int i = 0; i < 2 * nu; ++i) {
+      uint32_t t[32];
+      tmem_ld32(t_row + 128 + i * 32, t);                // .aligned: every lane loads
+      tmem_ld_wait();
+      const float f = s_sum[i * 128 + r] > 0.f ? ex2_approx(s_ms[i * 128 + r] - M) * inv : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(t[j]), f, o[j]);
+    }
+    if (qrow < p.Lq) {
+      float4* dst = reinterpret_cast<float4*>(p.ctx + ((long long)seq * p.Lq + qrow) * p.ldo + head * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  } else if (qrow < p.Lq) {
+    p.lse[((long long)seq * p.heads + head) * p.Lq + qrow] = (M + log2f(tot)) * kLn2;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// backward.  KEYMAJOR = false: dQ (and D) for one 128-query tile; KEYMAJOR = true: dK and dV for one 128-key tile.
+//   P = exp(Q K^T c - lse), dP = dO V^T (. mask * scale), D_i = dO_i . O_i, dS = P (dP - D) c, dQ = dS K, dK = dS^T Q, dV = (P . mask * scale)^T dO
+// ---------------------------------------------------------------------------------------------------------------------------------
+template <bool KEYMAJOR>
+__global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs p, int lcp /* columns (keys / queries) padded to a multiple of 64 */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // row tile: X (first product) and Y (second) = Q, dO (dQ kernel) / K, V (dK/dV kernel); hi at 0, lo at +8 KB
+  uint8_t* s_x = smem;
+  uint8_t* s_y = s_x + 2 * 128 * 64;
+  // column tensors CX, CY = K, V (dQ kernel) / Q, dO (dK/dV kernel); hi, lo: lcp * 64 each
+  uint8_t* s_cx = s_y + 2 * 128 * 64;
+  uint8_t* s_cy = s_cx + 2 * lcp * 64;
+  float* s_lse2 = reinterpret_cast<float*>(s_cy + 2 * lcp * 64);   // [256] by query (row of the tile / column)
+  float* s_D = s_lse2 + 256;
+  float* s_red = s_D + 256;                                        // [16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 16);        // [0] scores ready, [1] outputs ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int seq = blockIdx.x, head = blockIdx.y, tile = blockIdx.z;
+  const long long sh = (long long)seq * p.heads + head;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+
+  const float* Qb = p.Q + (long long)seq * p.q_seq_stride + head * 32;
+  const float* Kb = p.K + (long long)seq * p.Lk * p.ldkv + head * 32;
+  const float* Vb = p.V + (long long)seq * p.Lk * p.ldkv + head * 32;
+  const float* Gb = p.dO + (long long)seq * p.Lq * p.ldo + head * 32;
+  const float* Ob = p.ctx + (long long)seq * p.Lq * p.ldo + head * 32;
+  float sigma;
+  int ncols;                                             // valid columns
+  if (!KEYMAJOR) {
+    const int q0 = tile * 128, qv = min(128, p.Lq - q0);
+    sigma = tpow2_scale(Gb + (long long)q0 * p.ldo, p.ldo, qv, s_red);
+    tstage_rows(s_x, s_x + 128 * 64, Qb + (long long)q0 * p.ldq, p.ldq, qv, 128, 1.f);
+    tstage_rows(s_y, s_y + 128 * 64, Gb + (long long)q0 * p.ldo, p.ldo, qv, 128, sigma);
+    tstage_rows(s_cx, s_cx + lcp * 64, Kb, p.ldkv, p.Lk, lcp, 1.f);
+    tstage_rows(s_cy, s_cy + lcp * 64, Vb, p.ldkv, p.Lk, lcp, 1.f);
+    ncols = p.Lk;
+    // D = rowsum(dO . O): two threads per row, 16 columns each
+    {
+      const int row = threadIdx.x >> 1, part = threadIdx.x & 1;
+      float d = 0.f;
+      if (row < qv) {
+        const float4* g4 = reinterpret_cast<const float4*>(Gb + (long long)(q0 + row) * p.ldo + part * 16);
+        const float4* o4 = reinterpret_cast<const float4*>(Ob + (long long)(q0 + row) * p.ldo + part * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 g = __ldg(g4 + j), o = __ldg(o4 + j);
+          d = fmaf(g.x, o.x, d); d = fmaf(g.y, o.y, d); d = fmaf(g.z, o.z, d); d = fmaf(g.w, o.w, d);
+        }
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      if (part == 0) {
+        s_D[row] = d * sigma;
+        s_lse2[row] = row < qv ? p.lse[sh * p.Lq + q0 + row] * kLog2e : 0.f;
+        if (row < qv) p.Dbuf[sh * p.Lq + q0 + row] = d;
+      }
+    }
+  } else {
+    const int k0 = tile * 128, kv = min(128, p.Lk - k0);
+    sigma = tpow2_scale(Gb, p.ldo, p.Lq, s_red);
+    tstage_rows(s_x, s_x + 128 * 64, Kb + (long long)k0 * p.ldkv, p.ldkv, kv, 128, 1.f);
+    tstage_rows(s_y, s_y + 128 * 64, Vb + (long long)k0 * p.ldkv, p.ldkv, kv, 128, 1.f);
+    tstage_rows(s_cx, s_cx + lcp * 64, Qb, p.ldq, p.Lq, lcp, 1.f);
+    tstage_rows(s_cy, s_cy + lcp * 64, Gb, p.ldo, p.Lq, lcp, sigma);
+    ncols = p.Lq;
+    for (int i = threadIdx.x; i < 256; i += kTThreads) {
+      s_lse2[i] = i < p.Lq ? p.lse[sh * p.Lq + i] * kLog2e : 0.f;
+      s_D[i] = i < p.Lq ? p.Dbuf[sh * p.Lq + i] * sigma : 0.f;
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc_1 = make_idesc(128, 64, false, false, false);    // scores: both operands K-major
+  const uint32_t idesc_2 = make_idesc(128, 32, false, false, true);     // accumulations: A from TMEM, B MN-major
+  const uint32_t xa = smem_u32(s_x), ya = smem_u32(s_y), cxa = smem_u32(s_cx), cya = smem_u32(s_cy);
+  const uint32_t lo_r = 128 * 64, lo_c = (uint32_t)lcp * 64;
+  auto issue_scores = [&](int ch) {                      // T1[128, 64] = X CX_ch^T (columns 0..63), T2 = Y CY_ch^T (columns 64..127)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t ra = t ? ya : xa, ca = (t ? cya : cxa) + ch * 64 * 64;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t rp = ra + (part == 1 ? lo_r : 0), cp = ca + (part == 2 ? lo_c : 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_f16(tmem_base + t * 64, make_sdesc(rp + k * 32, 16, kTAtom, kSwz64), make_sdesc(cp + k * 32, 16, kTAtom, kSwz64), idesc_1, acc);
+          acc = 1;
+        }
+      }
+    }
+  };
+  auto issue_accum = [&](int ch, uint32_t dcol, uint32_t acol, uint32_t btile) {   // D[128, 32] (+)= A(TMEM columns acol..) B_ch
+    uint32_t acc = ch > 0 ? 1u : 0u;
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+      const uint32_t bp = btile + (part == 2 ? lo_c : 0) + ch * 64 * 64;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t pcol = acol + (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
+        umma_f16_ts(tmem_base + dcol, tmem_base + pcol, make_sdesc(bp + k * 16 * 64, kTAtom, kTAtom, kSwz64), idesc_2, acc);
+        acc = 1;
+      }
+    }
+  };
+
+  const int r = quarter * 32 + lane;                     // row of the tile == TMEM lane (query row / key row)
+  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const float c2 = p.c * kLog2e;
+  const int nch = (ncols + 63) >> 6;
+  const float my_lse2 = KEYMAJOR ? 0.f : s_lse2[r], my_D = KEYMAJOR ? 0.f : s_D[r];
+  const long long drop_base = sh * p.Lq * p.Lk;
+
+  if (threadIdx.x == 0) {
+    issue_scores(0);
+    umma_commit(&bars[0]);
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    mbar_wait(&bars[0], ch & 1);
+    fence_after_sync();
+    uint32_t s[32], g[32];
+    tmem_ld32(t_row + half * 32, s);
+    tmem_ld32(t_row + 64 + half * 32, g);
+    tmem_ld_wait();
+    const int col0 = ch * 64 + half * 32;                // first column (key / query index) of this thread's 32
+    uint32_t w1[32], w2[32];                             // [hi 16 | lo 16] each
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float pd[2], ds[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = col0 + 2 * j + e;
+        const float l2 = KEYMAJOR ? s_lse2[col] : my_lse2, D = KEYMAJOR ? s_D[col] : my_D;
+        const float pr = ex2_approx(fmaf(__uint_as_float(s[2 * j + e]), c2, -l2));
+        float kf = 1.f;
+        if (p.drop.thresh) {
+          const long long qi = KEYMAJOR ? col : tile * 128 + r, ki = KEYMAJOR ? tile * 128 + r : col;
+          kf = drop_keep(p.drop, (unsigned long long)(drop_base + qi * p.Lk + ki)) ? p.drop.scale : 0.f;
+        }
+        pd[e] = pr * kf;
+        ds[e] = pr * (__uint_as_float(g[2 * j + e]) * kf - D) * p.c;
+        if (!KEYMAJOR && col >= p.Lk) ds[e] = 0.f;       // padded keys: P is not bounded there
+      }
+      if (KEYMAJOR) {
+        split_pack<false>(pd[0], pd[1], w1[j], w1[16 + j]);
+        split_pack<false>(ds[0], ds[1], w2[j], w2[16 + j]);
+      } else {
+        split_pack<false>(ds[0], ds[1], w1[j], w1[16 + j]);
+      }
+    }
+    tmem_st32(t_row + half * 32, w1);
+    if (KEYMAJOR) tmem_st32(t_row + 64 + half * 32, w2);
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0) {
+      if (KEYMAJOR) {
+        issue_accum(ch, 128, 0, cya);                    // dV += (P . mask)^T dO
+        issue_accum(ch, 160, 64, cxa);                   // dK += dS^T Q
+      } else {
+        issue_accum(ch, 128, 0, cxa);                    // dQ += dS K
+      }
+      if (ch + 1 < nch) {
+        issue_scores(ch + 1);                            // overwrites T1 / T2: the MMA pipe runs in issue order
+        umma_commit(&bars[0]);
+      } else {
+        umma_commit(&bars[1]);
+      }
+    }
+  }
+  mbar_wait(&bars[1], 0);
+  fence_after_sync();
+  const float inv_sigma = 1.f / sigma;
+  const int row = tile * 128 + r;
+  if (KEYMAJOR || half == 0) {
+    uint32_t t[32];
+    tmem_ld32(t_row + 128 + (KEYMAJOR ? half * 32 : 0), t);
+    tmem_ld_wait();
+    float* dst = nullptr;
+    if (!KEYMAJOR) { if (row < p.Lq) dst = p.dQ + ((long long)seq * p.Lq + row) * p.lddq + head * 32; }
+    else if (row < p.Lk) dst = (half ? p.dK : p.dV) + ((long long)seq * p.Lk + row) * p.lddkv + head * 32;
+    if (dst) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(t[4 * j]) * inv_sigma, __uint_as_float(t[4 * j + 1]) * inv_sigma,
+                                                        __uint_as_float(t[4 * j + 2]) * inv_sigma, __uint_as_float(t[4 * j + 3]) * inv_sigma);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+inline size_t tattn_fwd_smem(int lkp) { return 1024 + 2 * 128 * 64 + 4 * (size_t)lkp * 64 + 2 * 4 * 128 * sizeof(float) + 64; }
+inline size_t tattn_bwd_smem(int lcp) { return 1024 + 4 * 128 * 64 + 4 * (size_t)lcp * 64 + (256 + 256 + 16) * sizeof(float) + 64; }
+
+}  // namespace tc
+}  // namespace hft

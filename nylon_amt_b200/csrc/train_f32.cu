@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "model.h"
 #include "train_kernels.cuh"
+#include "tc_train_attn.cuh"
 
 #include <math.h>
 #include <vector>
@@ -141,65 +142,107 @@ static bool attn_r2_enabled() {                    // HFT_TRAIN_ATTN_R2=0: the o
   return v == 1;
 }
 
-static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
+// tcgen05 attention kernels of the training step (tc_train_attn.cuh: head_dim 32, split-fp16 products, fp32-class results).
+// HFT_TRAIN_TC=0 selects the fp32 CUDA-core kernels instead (experiment switch; hft_train_attention() can force either).
+static int g_train_tc_force = -1;
+static bool train_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return g_train_tc_force >= 0 ? g_train_tc_force == 1 : v == 1;
+}
+struct AttnDims { int dh, heads, H; };
+static bool tattn_ok(const AttnDims& d, int ldq, int ldkv, int Lq, int Lk) {
+  return train_tc_enabled() && d.dh == 32 && Lq >= 1 && Lk >= 1 && Lq <= 256 && Lk <= 256 && ldq % 4 == 0 && ldkv % 4 == 0 && d.H % 4 == 0;
+}
+
+static int attn_fwd(const AttnDims& m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
                     int Lq, int Lk, float* ctx, float* lse, Drop drop = Drop{0, 0, 0, 1.f}) {
-  const int dh = m->dh;
+  const int dh = m.dh;
+  const float inv_scale = 1.f / sqrtf((float)dh);
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  if (tattn_ok(m, ldq, ldkv, Lq, Lk)) {
+    tc::TAttnArgs a{};
+    a.Q = Q; a.ldq = ldq; a.q_seq_stride = q_seq_stride; a.K = K; a.V = V; a.ldkv = ldkv; a.Lq = Lq; a.Lk = Lk; a.heads = m.heads; a.c = inv_scale;
+    a.ctx = ctx; a.ldo = m.H; a.lse = lse; a.drop = drop;
+    const int lkp = (Lk + 127) / 128 * 128;
+    HFT_SET_MAX_SMEM(tc::tattn_fwd_kernel, tc::tattn_fwd_smem(256));
+    tc::tattn_fwd_kernel<<<dim3((unsigned)S, m.heads, (Lq + 127) / 128), tc::kTThreads, tc::tattn_fwd_smem(lkp), s>>>(a, lkp);
+    return HFT_OK;
+  }
   size_t smem = (size_t)2 * Lk * dh * sizeof(float);
   int threads = (Lq + 31) / 32 * 32;
   HFT_REQUIRE(threads <= 256 && smem <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention: Lq=%d Lk=%d unsupported", Lq, Lk);
-  dim3 grid((unsigned)S, m->heads);
-  const float inv_scale = 1.f / sqrtf((float)dh);
-  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  dim3 grid((unsigned)S, m.heads);
   if (dh == 64) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
+    attn_f32_kernel<64><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m.heads, inv_scale, ctx, m.H, nullptr, lse, drop);
   } else if (attn_r2_enabled()) {                    // two query rows per thread, one-pass softmax
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_r2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_f32_r2_kernel<32><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, lse, drop);
+    attn_f32_r2_kernel<32><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m.heads, inv_scale, ctx, m.H, lse, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m->heads, inv_scale, ctx, m->H, nullptr, lse, drop);
+    attn_f32_kernel<32><<<grid, threads, smem, s>>>(Q, ldq, q_seq_stride, K, V, ldkv, Lq, Lk, m.heads, inv_scale, ctx, m.H, nullptr, lse, drop);
   }
   return HFT_OK;
 }
+static int attn_fwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long q_seq_stride, const float* K, const float* V, int ldkv, long long S,
+                    int Lq, int Lk, float* ctx, float* lse, Drop drop = Drop{0, 0, 0, 1.f}) {
+  return attn_fwd(AttnDims{m->dh, m->heads, m->H}, s, Q, ldq, q_seq_stride, K, V, ldkv, S, Lq, Lk, ctx, lse, drop);
+}
 
 template <int DH>
-static int attn_bwd_t(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO,
+static int attn_bwd_t(const AttnDims& m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO,
                       const float* O, const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf,
                       Drop drop) {
   const float c = 1.f / sqrtf((float)DH);
-  dim3 grid((unsigned)S, m->heads);
+  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
+  if (DH == 32 && tattn_ok(m, ldq, ldkv, Lq, Lk) && lddq % 4 == 0 && lddkv % 4 == 0) {
+    tc::TAttnArgs a{};
+    a.Q = Q; a.ldq = ldq; a.q_seq_stride = qss; a.K = K; a.V = V; a.ldkv = ldkv; a.Lq = Lq; a.Lk = Lk; a.heads = m.heads; a.c = c;
+    a.ctx = const_cast<float*>(O); a.ldo = m.H; a.lse = const_cast<float*>(lse); a.dO = dO; a.dQ = dQ; a.lddq = lddq; a.dK = dK; a.dV = dV; a.lddkv = lddkv;
+    a.Dbuf = Dbuf; a.drop = drop;
+    HFT_SET_MAX_SMEM(tc::tattn_bwd_kernel<false>, tc::tattn_bwd_smem(256));
+    HFT_SET_MAX_SMEM(tc::tattn_bwd_kernel<true>, tc::tattn_bwd_smem(256));
+    const int lcp_k = (Lk + 63) / 64 * 64, lcp_q = (Lq + 63) / 64 * 64;
+    tc::tattn_bwd_kernel<false><<<dim3((unsigned)S, m.heads, (Lq + 127) / 128), tc::kTThreads, tc::tattn_bwd_smem(lcp_k), s>>>(a, lcp_k);   // dQ, D
+    tc::tattn_bwd_kernel<true><<<dim3((unsigned)S, m.heads, (Lk + 127) / 128), tc::kTThreads, tc::tattn_bwd_smem(lcp_q), s>>>(a, lcp_q);    // dK, dV
+    return HFT_OK;
+  }
+  dim3 grid((unsigned)S, m.heads);
   const size_t smem1 = (size_t)2 * Lk * DH * sizeof(float);
   const size_t smem2 = ((size_t)2 * Lq * DH + 2 * Lq) * sizeof(float);
   const int t1 = (Lq + 31) / 32 * 32, t2 = (Lk + 31) / 32 * 32;
   HFT_REQUIRE(t1 <= 256 && t2 <= 256 && smem1 <= 200 * 1024 && smem2 <= 200 * 1024, HFT_ERR_UNSUPPORTED, "train attention backward: Lq=%d Lk=%d", Lq, Lk);
-  LaunchScope ls(HFT_KCLASS_ATTENTION, s);
   constexpr int DHR = DH <= 32 ? DH : 32;          // the two-row kernel exists for head_dim <= 32 only
   if (DH <= 32 && attn_r2_enabled() && lddq % 4 == 0) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_r2_kernel<DHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dq_r2_kernel<DHR><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
+    attn_bwd_dq_r2_kernel<DHR><<<grid, ((Lq + 1) / 2 + 31) / 32 * 32, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m.H, lse, Lq, Lk, m.heads, c, dQ, lddq, Dbuf, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m->H, lse, Lq, Lk, m->heads, c, dQ, lddq, Dbuf, drop);
+    attn_bwd_dq_kernel<DH><<<grid, t1, smem1, s>>>(Q, ldq, qss, K, V, ldkv, dO, O, m.H, lse, Lq, Lk, m.heads, c, dQ, lddq, Dbuf, drop);
   }
   if (DH == 32 && attn_r2_enabled() && lddkv % 4 == 0) {        // thread pairs: two keys x half the head dimension each
     HFT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dkv_pair_kernel<<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
+    attn_bwd_dkv_pair_kernel<<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m.H, lse, Dbuf, Lq, Lk, m.heads, c, dK, dV, lddkv, drop);
   } else if (DH <= 32) {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
+    attn_bwd_dkv_kernel<DH, 0><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m.H, lse, Dbuf, Lq, Lk, m.heads, c, dK, dV, lddkv, drop);
   } else {
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HFT_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_kernel<DH, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_dkv_kernel<DH, 1><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
-    attn_bwd_dkv_kernel<DH, 2><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m->H, lse, Dbuf, Lq, Lk, m->heads, c, dK, dV, lddkv, drop);
+    attn_bwd_dkv_kernel<DH, 1><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m.H, lse, Dbuf, Lq, Lk, m.heads, c, dK, dV, lddkv, drop);
+    attn_bwd_dkv_kernel<DH, 2><<<grid, t2, smem2, s>>>(Q, ldq, qss, K, V, ldkv, dO, m.H, lse, Dbuf, Lq, Lk, m.heads, c, dK, dV, lddkv, drop);
   }
   return HFT_OK;
 }
+static int attn_bwd(const AttnDims& m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO, const float* O,
+                    const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf, Drop drop) {
+  if (m.dh == 64) return attn_bwd_t<64>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
+  return attn_bwd_t<32>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
+}
 static int attn_bwd(Model* m, cudaStream_t s, const float* Q, int ldq, long long qss, const float* K, const float* V, int ldkv, const float* dO, const float* O,
                     const float* lse, long long S, int Lq, int Lk, float* dQ, int lddq, float* dK, float* dV, int lddkv, float* Dbuf, Drop drop) {
-  if (m->dh == 64) return attn_bwd_t<64>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
-  return attn_bwd_t<32>(m, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
+  return attn_bwd(AttnDims{m->dh, m->heads, m->H}, s, Q, ldq, qss, K, V, ldkv, dO, O, lse, S, Lq, Lk, dQ, lddq, dK, dV, lddkv, Dbuf, drop);
 }
 
 // gradient slot of a registered parameter inside the flat gradient vector
@@ -666,6 +709,36 @@ extern "C" int hft_adam_step(float* params_dev, const float* grads_dev, float* e
     LaunchScope ls(HFT_KCLASS_NORM, stream);
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev, n, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
   }
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
+// Component entry: the multi-head attention of the training step alone (forward with the row log-sum-exp, optionally the backward),
+// on caller-provided fp32 tensors.  use_tc: 1 = tcgen05 kernels (tc_train_attn.cuh; head_dim 32, Lq, Lk <= 256), 0 = fp32 CUDA-core kernels,
+// -1 = what the training step itself would pick.  Lets the tests compare either implementation with torch autograd on the same operands.
+extern "C" int hft_train_attention(int32_t use_tc, int32_t dh, int32_t heads, const float* q_dev, int32_t ldq, int64_t q_seq_stride, const float* k_dev,
+                                   const float* v_dev, int32_t ldkv, int64_t n_seq, int32_t lq, int32_t lk, float p_drop, uint32_t seed, int32_t site,
+                                   float* ctx_dev, float* lse_dev, const float* d_ctx_dev, float* dq_dev, int32_t lddq, float* dk_dev, float* dv_dev,
+                                   int32_t lddkv, float* d_buf_dev, void* stream) {
+  HFT_REQUIRE(q_dev && k_dev && v_dev && ctx_dev && lse_dev && n_seq >= 1 && lq >= 1 && lk >= 1 && heads >= 1 && (dh == 32 || dh == 64), HFT_ERR_ARG,
+              "hft_train_attention: bad argument");
+  HFT_REQUIRE(p_drop >= 0.f && p_drop < 1.f, HFT_ERR_ARG, "hft_train_attention: p_drop must be in [0, 1)");
+  HFT_REQUIRE(!d_ctx_dev || (dq_dev && dk_dev && dv_dev && d_buf_dev), HFT_ERR_ARG, "hft_train_attention: backward needs dq, dk, dv and d_buf");
+  cudaStream_t s = (cudaStream_t)stream;
+  const AttnDims d{dh, heads, heads * dh};
+  Drop drop{0u, seed, (uint32_t)site, 1.f};
+  if (p_drop > 0.f) { drop.thresh = (uint32_t)((double)p_drop * 4294967296.0); drop.scale = 1.f / (1.f - p_drop); }
+  reset_launch_count();
+  g_train_tc_force = use_tc;
+  if (use_tc == 1 && !tattn_ok(d, ldq, ldkv, lq, lk)) {
+    g_train_tc_force = -1;
+    HFT_REQUIRE(false, HFT_ERR_UNSUPPORTED, "hft_train_attention: the tcgen05 kernels need head_dim 32, Lq, Lk <= 256 and row pitches that are multiples of 4");
+  }
+  int rc = attn_fwd(d, s, q_dev, ldq, q_seq_stride, k_dev, v_dev, ldkv, n_seq, lq, lk, ctx_dev, lse_dev, drop);
+  if (rc == HFT_OK && d_ctx_dev)
+    rc = attn_bwd(d, s, q_dev, ldq, q_seq_stride, k_dev, v_dev, ldkv, d_ctx_dev, ctx_dev, lse_dev, n_seq, lq, lk, dq_dev, lddq, dk_dev, dv_dev, lddkv, d_buf_dev, drop);
+  g_train_tc_force = -1;
+  if (rc != HFT_OK) return rc;
   HFT_CHECK_CUDA(cudaGetLastError());
   return HFT_OK;
 }
