@@ -314,6 +314,15 @@ int hft_train_attention(int32_t use_tc, int32_t dh, int32_t heads, const float* 
                         float* ctx_dev, float* lse_dev, const float* d_ctx_dev, float* dq_dev, int32_t lddq, float* dk_dev, float* dv_dev,
                         int32_t lddkv, float* d_buf_dev, void* stream);
 
+/* Component entry: one Linear of the training step on fp32 device tensors.
+ *   w_kn = 0: c[m, n] = a[m, k] w[n, k]^T + bias (optional ReLU)            -- nn.Linear forward (model_spec2midi.py:322-378)
+ *   w_kn = 1: c[m, n] = a[m, k] w[k, n], then c = mask > 0 ? c * mask_scale : 0 when mask_dev is given   -- its input gradient under loss.backward()
+ * accum != 0 adds the result to c instead of overwriting it.  use_tc: 1 = the tcgen05 kernel (split-fp16 products, fp32 accumulate;
+ * k = 64 or 128, n % 16 == 0, n <= 256), 0 = the fp32 CUDA-core kernels, -1 = what the training step picks. */
+int hft_train_linear(int32_t use_tc, int32_t w_kn, const float* a_dev, int32_t lda, const float* w_dev, int32_t ldw, const float* bias_dev,
+                     float* c_dev, int32_t ldc, int64_t m, int32_t n, int32_t k, int32_t relu, int32_t accum, const float* mask_dev, int32_t ldm,
+                     float mask_scale, void* stream);
+
 /* torch.optim.Adam (no weight decay, no amsgrad) on flat vectors: grads are multiplied by grad_scale first (1 / world size
  * after a sum all-reduce); step counts from 1. */
 int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,

@@ -53,31 +53,48 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 // rows [0, n_valid) of an fp32 tensor (32 columns starting at src, row pitch ld) times `scale` -> hi | lo fp16 tiles in the
 // K-major 64B-swizzled UMMA layout (row r at r * 64, 16-byte chunk ch at position ch ^ ((r >> 1) & 3)); rows up to n_pad are zero.
 __device__ __forceinline__ void tstage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long ld, int n_valid, int n_pad, float scale) {
-  for (int i = threadIdx.x; i < n_pad * 4; i += kTThreads) {
-    const int r = i >> 2, ch = i & 3;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (r < n_valid) {
-      const float4* s4 = reinterpret_cast<const float4*>(src + (long long)r * ld + ch * 8);
-      a = __ldg(s4);
-      b = __ldg(s4 + 1);
+  // n_pad is a multiple of 64, so every thread owns n_pad / 64 chunks; two at a time, all four loads in flight before the first conversion
+  for (int i0 = threadIdx.x; i0 < n_pad * 4; i0 += 2 * kTThreads) {
+    float4 a[2], b[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * kTThreads, r = i >> 2, ch = i & 3;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b[u] = a[u];
+      if (r < n_valid) {                                 // (r >= n_pad when n_pad == 64: skipped below)
+        const float4* s4 = reinterpret_cast<const float4*>(src + (long long)r * ld + ch * 8);
+        a[u] = __ldg(s4);
+        b[u] = __ldg(s4 + 1);
+      }
     }
-    uint32_t h[4], l[4];
-    split_pack<false>(a.x * scale, a.y * scale, h[0], l[0]);
-    split_pack<false>(a.z * scale, a.w * scale, h[1], l[1]);
-    split_pack<false>(b.x * scale, b.y * scale, h[2], l[2]);
-    split_pack<false>(b.z * scale, b.w * scale, h[3], l[3]);
-    const int off = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * kTThreads, r = i >> 2, ch = i & 3;
+      if (r >= n_pad) break;
+      uint32_t h[4], l[4];
+      split_pack<false>(a[u].x * scale, a[u].y * scale, h[0], l[0]);
+      split_pack<false>(a[u].z * scale, a[u].w * scale, h[1], l[1]);
+      split_pack<false>(b[u].x * scale, b[u].y * scale, h[2], l[2]);
+      split_pack<false>(b[u].z * scale, b[u].w * scale, h[3], l[3]);
+      const int off = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 
 // largest |x| over n_rows x 32 values -> the power of two that brings it into [1, 2) (1 when everything is zero / denormal)
 __device__ __forceinline__ float tpow2_scale(const float* src, long long ld, int n_rows, float* s_red /*[9]*/) {
   float mx = 0.f;
-  for (int i = threadIdx.x; i < n_rows * 8; i += kTThreads) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (long long)(i >> 3) * ld + (i & 7) * 4));
-    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+  for (int i0 = threadIdx.x; i0 < n_rows * 8; i0 += 4 * kTThreads) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kTThreads;
+      a[u] = i < n_rows * 8 ? __ldg(reinterpret_cast<const float4*>(src + (long long)(i >> 3) * ld + (i & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a[u].x), fabsf(a[u].y))), fmaxf(fabsf(a[u].z), fabsf(a[u].w)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));

@@ -1,0 +1,228 @@
+// tcgen05 GEMM for the TRAINING step (reduced model, BASELINE configs[4]): the Linear layers of the forward
+// (y = x W^T + b, optional ReLU; reference nn.Linear inside model_spec2midi.py:322-378) and their input gradients
+// (dx = dy W, optional ReLU mask / accumulate; loss.backward(), training/train.py:158) on fp32 tensors.
+// Replaces sgemm_tn_kernel / sgemm_nn_kernel (fp32 CUDA cores, 45 % of the fp32 FMA peak) for K = 64 / 128 and N <= 256:
+// every shape of the model is [rows in the 10^5] x [K <= 128] x [N <= 192], i.e. bound by the HBM traffic of the
+// activations once the products run on the tensor cores.
+//
+// Arithmetic: a.w = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in fp16 with fp32 accumulation in TMEM (22 mantissa bits); every
+// row of A is scaled by the power of two that brings its largest magnitude into [1, 2) before the split (gradients are
+// ~1e-6: fp16 would flush them) and W by one power of two per matrix; the epilogue scales back (exact).
+//
+// Structure: persistent CTAs (two per SM, 256 threads, 256 TMEM columns each).  W is staged once per CTA as hi | lo fp16 in
+// the K-major 128-byte-swizzled UMMA layout (transposed on the way when it is stored [K, N]); per 128-row tile the threads
+// load the fp32 rows (the next tile's loads are issued before the current tile's epilogue and stay in registers), split and
+// store them in the same layout, one thread issues the 3 x K/16 MMAs, and the epilogue (thread = row) adds the bias,
+// applies ReLU, stages 32 x 32 blocks per warp in swizzled shared memory and writes them back with full 128-byte rows
+// (ReLU mask / accumulate applied there with coalesced loads).
+#pragma once
+#include "tc_common.cuh"
+
+namespace hft {
+namespace tc {
+
+struct TGemmArgs {
+  const float* A; int lda;
+  const float* W; int ldw;
+  int w_kn;                    // 0: W is [N, K] (C = A W^T);  1: W is [K, N] (C = A W)
+  const float* bias;           // [N] or NULL
+  float* C; int ldc;
+  long long M; int N, K;
+  int relu, accum;             // C = relu(.) ; C += .
+  const float* mask; int ldm; float mask_scale;   // C = mask > 0 ? . * mask_scale : 0   (before the accumulate)
+};
+
+constexpr int kGThreads = 256;
+
+__device__ __forceinline__ float pow2_inv_of(float mx) {       // power of two s with mx * s in [1, 2); 1 when mx is 0 / denormal / not finite
+  const uint32_t e = (__float_as_uint(mx) >> 23) & 0xffu;
+  return (e == 0u || e >= 253u) ? 1.f : __uint_as_float((254u - e) << 23);
+}
+
+template <int KB>   // K / 64
+__global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) {
+  constexpr int CH = KB * 8;                 // 8-element chunks per row
+  constexpr int TASKS = 128 * CH / kGThreads;   // chunks per thread per tile
+  constexpr int A_PART = KB * 128 * 128;     // bytes of one part (hi or lo) of the A tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;                                        // [hi | lo][KB][128 rows x 128 B]; the epilogue staging overlays it
+  uint8_t* s_w = s_a + 2 * A_PART;                            // [hi | lo][KB][N rows x 128 B]
+  const int w_part = KB * p.N * 128;
+  float* s_bias = reinterpret_cast<float*>(s_w + 2 * w_part); // [256]
+  float* s_inv = s_bias + 256;                                // [128] 1 / row scale of the current tile
+  float* s_red = s_inv + 128;                                 // [16]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N;
+
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+
+  // ---- W: largest magnitude -> one power-of-two scale; hi | lo tiles --------------------------------------------------
+  float sigma_w;
+  {
+    float mx = 0.f;
+    const int rows_w = p.w_kn ? p.K : N, cols_w = p.w_kn ? N : p.K;
+    for (int i = tid; i < rows_w * cols_w; i += kGThreads) mx = fmaxf(mx, fabsf(__ldg(p.W + (long long)(i / cols_w) * p.ldw + i % cols_w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kGThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
+    sigma_w = pow2_inv_of(mx);
+    for (int i = tid; i < N * CH; i += kGThreads) {
+      float v[8];
+      int n, ch;
+      if (p.w_kn) {
+        n = i % N; ch = i / N;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.W + (long long)(ch * 8 + j) * p.ldw + n);
+      } else {
+        n = i / CH; ch = i % CH;
+        const float4* s4 = reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + ch * 8);
+        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_pack<false>(v[2 * j] * sigma_w, v[2 * j + 1] * sigma_w, h[j], l[j]);
+      const int off = (ch >> 3) * N * 128 + n * 128 + (((ch & 7) ^ (n & 7)) << 4);
+      *reinterpret_cast<uint4*>(s_w + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(s_w + w_part + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    for (int i = tid; i < 256; i += kGThreads) s_bias[i] = (p.bias && i < N) ? __ldg(p.bias + i) : 0.f;
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const float inv_sigma_w = 1.f / sigma_w;
+
+  const long long n_tiles = (p.M + 127) >> 7;
+  float4 ra[TASKS][2];
+  auto load_tile = [&](long long tile) {
+#pragma unroll
+    for (int t = 0; t < TASKS; ++t) {
+      const int idx = t * kGThreads + tid, r = idx / CH, ch = idx % CH;
+      const long long row = tile * 128 + r;
+      if (row < p.M) {
+        const float4* s4 = reinterpret_cast<const float4*>(p.A + row * p.lda + ch * 8);
+        ra[t][0] = __ldg(s4);
+        ra[t][1] = __ldg(s4 + 1);
+      } else {
+        ra[t][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ra[t][1] = ra[t][0];
+      }
+    }
+  };
+  const uint32_t idesc = make_idesc(128, N, false, false, false);
+  const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
+  const int q = warp & 3, half = warp >> 2;
+  const int n_chunks = (N + 31) >> 5;
+  uint8_t* stage = s_a + warp * 4096;
+  uint32_t phase = 0;
+
+  long long tile = blockIdx.x;
+  if (tile < n_tiles) load_tile(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    // ---- fp32 rows -> per-row power-of-two scale -> hi | lo tiles ----
+#pragma unroll
+    for (int t = 0; t < TASKS; ++t) {
+      const int idx = t * kGThreads + tid, r = idx / CH, ch = idx % CH;
+      const float4 a = ra[t][0], b = ra[t][1];
+      float mx = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+#pragma unroll
+      for (int o = CH / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // the CH lanes that share the row
+      const float sg = pow2_inv_of(mx);
+      if (ch == 0) s_inv[r] = 1.f / sg;
+      uint32_t h[4], l[4];
+      split_pack<false>(a.x * sg, a.y * sg, h[0], l[0]);
+      split_pack<false>(a.z * sg, a.w * sg, h[1], l[1]);
+      split_pack<false>(b.x * sg, b.y * sg, h[2], l[2]);
+      split_pack<false>(b.z * sg, b.w * sg, h[3], l[3]);
+      const int off = (ch >> 3) * (128 * 128) + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(s_a + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(s_a + A_PART + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t ap = a_addr + (part == 1 ? A_PART : 0), wp = w_addr + (part == 2 ? w_part : 0);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base, make_sdesc(ap + kb * (128 * 128) + k * 32, 16, 1024, kSwz128), make_sdesc(wp + kb * N * 128 + k * 32, 16, 1024, kSwz128), idesc, acc);
+            acc = 1;
+          }
+      }
+      umma_commit(bar);
+    }
+    const long long next = tile + gridDim.x;
+    if (next < n_tiles) load_tile(next);                       // in flight during the MMAs and the epilogue
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+
+    // ---- epilogue: thread = row; 32-column blocks through the warp's swizzled staging block ----
+    const float unscale = s_inv[q * 32 + lane] * inv_sigma_w;
+    for (int c = half; c < n_chunks; c += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[e] = fmaf(__uint_as_float(v[4 * g + e]), unscale, s_bias[c * 32 + 4 * g + e]);
+          if (p.relu) o[e] = fmaxf(o[e], 0.f);
+        }
+        *reinterpret_cast<float4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3), g = lane & 7;
+        float4 x = *reinterpret_cast<const float4*>(stage + rr * 128 + ((g ^ (rr & 7)) << 4));
+        const long long grow = tile * 128 + q * 32 + rr;
+        const int col = c * 32 + g * 4;
+        if (grow < p.M && col < N) {
+          float* cp = p.C + grow * p.ldc + col;
+          if (p.mask) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mask + grow * p.ldm + col));
+            x.x = m4.x > 0.f ? x.x * p.mask_scale : 0.f; x.y = m4.y > 0.f ? x.y * p.mask_scale : 0.f;
+            x.z = m4.z > 0.f ? x.z * p.mask_scale : 0.f; x.w = m4.w > 0.f ? x.w * p.mask_scale : 0.f;
+          }
+          if (p.accum) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cp);
+            x.x += c4.x; x.y += c4.y; x.z += c4.z; x.w += c4.w;
+          }
+          *reinterpret_cast<float4*>(cp) = x;
+        }
+      }
+      __syncwarp();
+    }
+    fence_before_sync();
+    __syncthreads();                                           // staging (overlays the A tile) and the accumulator are free again
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+inline size_t tgemm_smem(int KB, int N) { return 1024 + 2 * (size_t)KB * 128 * 128 + 2 * (size_t)KB * N * 128 + (256 + 128 + 16) * sizeof(float) + 64; }
+
+}  // namespace tc
+}  // namespace hft

@@ -12,6 +12,7 @@
 #include "model.h"
 #include "train_kernels.cuh"
 #include "tc_train_attn.cuh"
+#include "tc_train_gemm.cuh"
 
 #include <math.h>
 #include <vector>
@@ -64,8 +65,43 @@ struct Trainer {
 };
 
 // ---- launch helpers -------------------------------------------------------------------------------------------------
+// tcgen05 kernels of the training step (tc_train_attn.cuh: attention, head_dim 32; tc_train_gemm.cuh: Linear forward / input gradient;
+// split-fp16 products, fp32-class results).  HFT_TRAIN_TC=0 selects the fp32 CUDA-core kernels instead (experiment switch;
+// hft_train_attention() / hft_train_linear() can force either).
+static int g_train_tc_force = -1;
+static bool train_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return g_train_tc_force >= 0 ? g_train_tc_force == 1 : v == 1;
+}
+static bool tgemm_ok(const float* A, int lda, const float* W, int ldw, bool w_kn, const float* C, int ldc, int N, int K, const float* mask, int ldm) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return train_tc_enabled() && (K == 64 || K == 128) && N % 16 == 0 && N >= 16 && N <= 256 && lda % 4 == 0 && ldc % 4 == 0 && (w_kn || ldw % 4 == 0) && al(A) && al(W) &&
+         al(C) && (!mask || (ldm % 4 == 0 && al(mask))) && tc::tgemm_smem(K / 64, N) <= 113 * 1024;
+}
+static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a) {
+  static const int sms = num_sms();
+  const long long tiles = (a.M + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < 2LL * sms ? tiles : 2LL * sms);
+  const size_t smem = tc::tgemm_smem(a.K / 64, a.N);
+  LaunchScope ls(HFT_KCLASS_GEMM, s);
+  if (a.K == 64) {
+    HFT_SET_MAX_SMEM(tc::tgemm_kernel<1>, 113 * 1024);
+    tc::tgemm_kernel<1><<<grid, tc::kGThreads, smem, s>>>(a);
+  } else {
+    HFT_SET_MAX_SMEM(tc::tgemm_kernel<2>, 113 * 1024);
+    tc::tgemm_kernel<2><<<grid, tc::kGThreads, smem, s>>>(a);
+  }
+  return HFT_OK;
+}
+
 static int gemm_tn(cudaStream_t s, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc, long long M, int N, int K,
                    bool relu, bool accum = false) {
+  if (M > 0 && tgemm_ok(A, lda, Wt, ldw, false, C, ldc, N, K, nullptr, 0)) {
+    tc::TGemmArgs a{};
+    a.A = A; a.lda = lda; a.W = Wt; a.ldw = ldw; a.w_kn = 0; a.bias = bias; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.relu = relu; a.accum = accum;
+    return tgemm_launch(s, a);
+  }
   HFT_REQUIRE(K % GBK == 0 && lda % 4 == 0 && ldw % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_tn: K=%d lda=%d ldw=%d", K, lda, ldw);
   const int bn = sgemm_tile_n(N);
   dim3 grid((N + bn - 1) / bn, (unsigned)((M + GBM - 1) / GBM));
@@ -82,6 +118,12 @@ static int gemm_tn(cudaStream_t s, const float* A, int lda, const float* Wt, int
 // C[M,N] (+)= A[M,K] * W[K,N]
 static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int ldb, float* C, int ldc, long long M, int N, int K, bool accum,
                    const float* mask = nullptr, int ldm = 0, float mask_scale = 1.f) {
+  if (M > 0 && tgemm_ok(A, lda, W, ldb, true, C, ldc, N, K, mask, ldm)) {
+    tc::TGemmArgs a{};
+    a.A = A; a.lda = lda; a.W = W; a.ldw = ldb; a.w_kn = 1; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.accum = accum; a.mask = mask; a.ldm = ldm;
+    a.mask_scale = mask_scale;
+    return tgemm_launch(s, a);
+  }
   HFT_REQUIRE(K % GBK == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, HFT_ERR_UNSUPPORTED, "train sgemm_nn: N=%d K=%d lda=%d ldb=%d", N, K, lda, ldb);
   const int bn = sgemm_tile_n(N);
   dim3 grid((N + bn - 1) / bn, (unsigned)((M + GBM - 1) / GBM));
@@ -142,14 +184,6 @@ static bool attn_r2_enabled() {                    // HFT_TRAIN_ATTN_R2=0: the o
   return v == 1;
 }
 
-// tcgen05 attention kernels of the training step (tc_train_attn.cuh: head_dim 32, split-fp16 products, fp32-class results).
-// HFT_TRAIN_TC=0 selects the fp32 CUDA-core kernels instead (experiment switch; hft_train_attention() can force either).
-static int g_train_tc_force = -1;
-static bool train_tc_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC"); v = (e && e[0] == '0') ? 0 : 1; }
-  return g_train_tc_force >= 0 ? g_train_tc_force == 1 : v == 1;
-}
 struct AttnDims { int dh, heads, H; };
 static bool tattn_ok(const AttnDims& d, int ldq, int ldkv, int Lq, int Lk) {
   return train_tc_enabled() && d.dh == 32 && Lq >= 1 && Lk >= 1 && Lq <= 256 && Lk <= 256 && ldq % 4 == 0 && ldkv % 4 == 0 && d.H % 4 == 0;
@@ -737,6 +771,32 @@ extern "C" int hft_train_attention(int32_t use_tc, int32_t dh, int32_t heads, co
   int rc = attn_fwd(d, s, q_dev, ldq, q_seq_stride, k_dev, v_dev, ldkv, n_seq, lq, lk, ctx_dev, lse_dev, drop);
   if (rc == HFT_OK && d_ctx_dev)
     rc = attn_bwd(d, s, q_dev, ldq, q_seq_stride, k_dev, v_dev, ldkv, d_ctx_dev, ctx_dev, lse_dev, n_seq, lq, lk, dq_dev, lddq, dk_dev, dv_dev, lddkv, d_buf_dev, drop);
+  g_train_tc_force = -1;
+  if (rc != HFT_OK) return rc;
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
+// Component entry: one Linear of the training step on fp32 device tensors -- forward y = x W^T + b (w_kn = 0, W [N, K]; optional ReLU) or
+// input gradient dx = dy W (w_kn = 1, W [K, N]; optional ReLU mask: c = mask > 0 ? c * mask_scale : 0) -- optionally accumulated into C.
+// use_tc as in hft_train_attention (tcgen05 kernel: K = 64 / 128, N % 16 == 0, N <= 256).
+extern "C" int hft_train_linear(int32_t use_tc, int32_t w_kn, const float* a_dev, int32_t lda, const float* w_dev, int32_t ldw, const float* bias_dev,
+                                float* c_dev, int32_t ldc, int64_t m, int32_t n, int32_t k, int32_t relu, int32_t accum, const float* mask_dev, int32_t ldm,
+                                float mask_scale, void* stream) {
+  HFT_REQUIRE(a_dev && w_dev && c_dev && m >= 1 && n >= 1 && k >= 1, HFT_ERR_ARG, "hft_train_linear: bad argument");
+  HFT_REQUIRE(!(w_kn && (bias_dev || relu)) && !(!w_kn && mask_dev), HFT_ERR_ARG, "hft_train_linear: bias / ReLU belong to the forward form, the mask to the gradient form");
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_launch_count();
+  g_train_tc_force = use_tc;
+  int rc;
+  if (use_tc == 1 && !tgemm_ok(a_dev, lda, w_dev, ldw, w_kn != 0, c_dev, ldc, n, k, mask_dev, ldm)) {
+    set_error("hft_train_linear: the tcgen05 kernel needs K = 64 or 128, N %% 16 == 0, N <= 256, 16-byte aligned rows");
+    rc = HFT_ERR_UNSUPPORTED;
+  } else if (w_kn) {
+    rc = gemm_nn(s, a_dev, lda, w_dev, ldw, c_dev, ldc, m, n, k, accum != 0, mask_dev, ldm, mask_scale);
+  } else {
+    rc = gemm_tn(s, a_dev, lda, w_dev, ldw, bias_dev, c_dev, ldc, m, n, k, relu != 0, accum != 0);
+  }
   g_train_tc_force = -1;
   if (rc != HFT_OK) return rc;
   HFT_CHECK_CUDA(cudaGetLastError());
