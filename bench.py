@@ -413,15 +413,39 @@ def run_train(args, hft, _lib, L, dev, dist, rank, world, steps=None, warmup=Non
         return None
     return {"metric": "training segments/sec (reduced hFT fwd+loss+bwd+Adam)", "value": seg_s, "unit": "segments/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32 tensors; attention and Linear products as split fp16 (3 MMAs, fp32 accumulate) on tcgen05, fp32-class gradients", "data": "synthetic",
             "config": {"workload": "configs[4]: reduced hFT (hid 64, ff 128, 2+2 layers, 2 heads) training step, batch 8 per GPU, Adam lr 1e-4, dropout %g" % args.dropout,
                        "parallelism": "dp%d, one flat-bucket all-reduce of %d floats per step" % (world, opt.n)},
             "allreduce_ms": t_ar[0] / 3, "allreduce_exposed_ms": max(0.0, ms - ms_no_ar), "ms_per_step_without_allreduce": ms_no_ar,
             "allreduce": "NCCL sum of the flat fp32 gradient bucket" if world > 1 else "single process: no collective (world 1)",
             "loss_after": loss, "classes": classes, "gpu_launches": int(n_launch), "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "training step (CUDA-core fp32)", "achieved": gflop / ms, "peak": f32_peak, "unit": "TFLOP/s",
-                         "frac": gflop / ms / f32_peak, "traffic": None, "peak_source": f32_src},
+            "roofline": train_roofline(gflop, ms, B, f32_peak, f32_src),
             "cpu_baseline": cpu}
+
+
+def train_roofline(gflop, ms, B, f32_peak, f32_src):
+    """Roofline of the training step.  With the attention and the Linear forward / input-gradient products on the tensor cores (split fp16, three
+    MMAs per product) every kernel of the step streams fp32 activations: the bound is HBM.  `achieved` = the step's DRAM traffic (ncu
+    dram__bytes_read + write summed over the launches of one step, profiles/traffic.json `train_step_dram_bytes`, measured at batch 8) / step time;
+    the fp32-equivalent arithmetic rate of the algorithmic count stays in `fp32_equivalent` (it passes what the CUDA cores could do only because
+    the products no longer run there)."""
+    pk = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        t = json.load(open(tp))
+        if "train_step_dram_bytes" in t and B == t.get("train_step_batch", 8):
+            traffic = float(t["train_step_dram_bytes"])
+    out = {"bound": "hbm", "kernel": "training step (attention and Linear forward / input gradient: tcgen05 split-fp16 products; weight gradients, LayerNorm, loss, "
+                                     "Adam: fp32 CUDA cores)",
+           "achieved": (traffic / 1e9) / (ms / 1e3) if traffic else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
+           "frac": (traffic / 1e9) / (ms / 1e3) / pk["hbm_gbs"] if traffic else None, "traffic": traffic,
+           "traffic_source": "profiles/traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum over every launch of one training step at batch 8 "
+                             "(actual traffic, not an algorithmic count: the step has no closed-form byte count)",
+           "peak_source": pk["src"],
+           "fp32_equivalent": {"achieved": gflop / ms, "peak": f32_peak, "unit": "TFLOP/s", "frac": gflop / ms / f32_peak, "peak_source": f32_src,
+                               "what": "3 x 16.57 GFLOP per segment (forward + ~2x backward, SURVEY.md 8) / step time against the measured fp32 FMA rate"}}
+    return out
 
 
 def run_batch(args, hft, _lib, L, dev, dist, rank, world, precision, n_segments=256, steps=3, warmup=3):

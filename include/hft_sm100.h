@@ -323,6 +323,13 @@ int hft_train_linear(int32_t use_tc, int32_t w_kn, const float* a_dev, int32_t l
                      float* c_dev, int32_t ldc, int64_t m, int32_t n, int32_t k, int32_t relu, int32_t accum, const float* mask_dev, int32_t ldm,
                      float mask_scale, void* stream);
 
+/* Component entry: the weight gradient of one Linear of the training step: dw[n, k] += dy[m, n]^T x[m, k], db[n] += sum over m of dy[m, n]
+ * (db_dev may be NULL), on fp32 device tensors (what loss.backward(), training/train.py:158, accumulates into nn.Linear.weight.grad / .bias.grad).
+ * use_tc: 1 = the tcgen05 kernel (three-piece bf16 operands, fp32 accumulate; k = 64 or 128, n % 8 == 0, n + k <= 256), 0 = the fp32 CUDA-core
+ * kernel, -1 = what the training step picks. */
+int hft_train_linear_wgrad(int32_t use_tc, const float* dy_dev, int32_t ldy, const float* x_dev, int32_t ldx, float* dw_dev, int32_t ldw, float* db_dev,
+                           int64_t m, int32_t n, int32_t k, void* stream);
+
 /* torch.optim.Adam (no weight decay, no amsgrad) on flat vectors: grads are multiplied by grad_scale first (1 / world size
  * after a sum all-reduce); step counts from 1. */
 int hft_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr, float beta1, float beta2,

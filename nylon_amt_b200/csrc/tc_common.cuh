@@ -98,6 +98,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
          (1ull << 46) | ((uint64_t)swizzle << 61);
 }
 constexpr uint32_t kSwz128 = 2, kSwz64 = 4, kSwz32 = 6;
+// the descriptor of the same layout `byte_off` bytes further on (byte_off % 16 == 0; shared-memory addresses >> 4 fit the 14-bit field, so no carry
+// leaves it): lets an MMA-issuing thread build its descriptors with one add each from a few bases made outside the loop
+__device__ __forceinline__ uint64_t sdesc_advance(uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); }
 
 // ---- TMA ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

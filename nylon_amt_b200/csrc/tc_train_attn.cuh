@@ -11,9 +11,9 @@
 // output is linear in dO, powers of two are exact.
 //
 // Structure (one CTA = 256 threads = 128 TMEM lanes x 2 column halves, two CTAs per SM, 256 TMEM columns each):
-//   operands are staged by the threads themselves: fp32 rows -> hi | lo fp16 tiles in the K-major 64-byte-swizzled UMMA
-//   layout (a [rows, 32] tile serves as A / B K-major for the score-type products and as B MN-major for the
-//   accumulate-type products, so nothing is transposed);
+//   operands are staged by the threads themselves: raw fp32 rows arrive by cp.async (every tensor of the CTA in flight at once) and
+//   are converted in place to hi | lo fp16 tiles in the K-major 64-byte-swizzled UMMA layout (a [rows, 32] tile serves as A / B
+//   K-major for the score-type products and as B MN-major for the accumulate-type products, so nothing is transposed);
 //   forward   (seq, head, 128 queries): per 128-key unit S = Q K^T -> each thread owns 64 columns of its row with its own
 //             max / sum (split softmax), writes P (hi | lo, dropout applied) in place over S, O_{unit,half} = P V with A from
 //             TMEM into its own 32 columns; the partial results are merged in the epilogue, lse = max + ln(sum);
@@ -50,64 +50,80 @@ constexpr int kTThreads = 256;
 constexpr uint32_t kTAtom = 512;                      // 8 rows x 64 bytes: one 64B-swizzle atom of a [rows, 32] fp16 tile
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
-// rows [0, n_valid) of an fp32 tensor (32 columns starting at src, row pitch ld) times `scale` -> hi | lo fp16 tiles in the
-// K-major 64B-swizzled UMMA layout (row r at r * 64, 16-byte chunk ch at position ch ^ ((r >> 1) & 3)); rows up to n_pad are zero.
-__device__ __forceinline__ void tstage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long ld, int n_valid, int n_pad, float scale) {
-  // n_pad is a multiple of 64, so every thread owns n_pad / 64 chunks; two at a time, all four loads in flight before the first conversion
-  for (int i0 = threadIdx.x; i0 < n_pad * 4; i0 += 2 * kTThreads) {
-    float4 a[2], b[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = i0 + u * kTThreads, r = i >> 2, ch = i & 3;
-      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      b[u] = a[u];
-      if (r < n_valid) {                                 // (r >= n_pad when n_pad == 64: skipped below)
-        const float4* s4 = reinterpret_cast<const float4*>(src + (long long)r * ld + ch * 8);
-        a[u] = __ldg(s4);
-        b[u] = __ldg(s4 + 1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = i0 + u * kTThreads, r = i >> 2, ch = i & 3;
-      if (r >= n_pad) break;
-      uint32_t h[4], l[4];
-      split_pack<false>(a[u].x * scale, a[u].y * scale, h[0], l[0]);
-      split_pack<false>(a[u].z * scale, a[u].w * scale, h[1], l[1]);
-      split_pack<false>(b[u].x * scale, b[u].y * scale, h[2], l[2]);
-      split_pack<false>(b[u].z * scale, b[u].w * scale, h[3], l[3]);
-      const int off = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-    }
+// Staging: every operand tile is fetched ONCE, by cp.async, as raw fp32 rows into the shared-memory region its hi | lo fp16 tiles will
+// occupy (32 floats = 128 bytes per row = the 64 + 64 bytes of the two tiles), all tensors in flight together (one global round trip per
+// CTA instead of one per tensor); the conversion then runs in place: every thread reads its 8-float chunks into registers, the CTA
+// synchronises, and the chunks are written back split, in the K-major 64B-swizzled UMMA layout (row r at r * 64, 16-byte chunk ch at
+// position ch ^ ((r >> 1) & 3); hi tile at the region's start, lo tile n_pad * 64 bytes further on).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// rows [0, n_valid) x 32 floats from src (row pitch ld) -> raw rows at region + r * 128; rows up to n_pad (a multiple of 64) are zero
+__device__ __forceinline__ void traw_issue(uint8_t* region, const float* src, long long ld, int n_valid, int n_pad) {
+  for (int i = threadIdx.x; i < n_pad * 8; i += kTThreads) {
+    const int r = i >> 3, c = i & 7;
+    if (r < n_valid) cp_async_16(region + r * 128 + c * 16, src + (long long)r * ld + c * 4);
+    else *reinterpret_cast<uint4*>(region + r * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
-
-// largest |x| over n_rows x 32 values -> the power of two that brings it into [1, 2) (1 when everything is zero / denormal)
-__device__ __forceinline__ float tpow2_scale(const float* src, long long ld, int n_rows, float* s_red /*[9]*/) {
-  float mx = 0.f;
-  for (int i0 = threadIdx.x; i0 < n_rows * 8; i0 += 4 * kTThreads) {
-    float4 a[4];
+// this thread's chunks of a raw region: task t = chunk (t * 256 + tid) -> row = chunk >> 2, 8 floats at column (chunk & 3) * 8.  T >= n_pad / 64.
+template <int T>
+struct TRaw {
+  float4 a[T], b[T];
+  __device__ __forceinline__ void read(const uint8_t* region, int n_pad) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kTThreads;
-      a[u] = i < n_rows * 8 ? __ldg(reinterpret_cast<const float4*>(src + (long long)(i >> 3) * ld + (i & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const int i = t * kTThreads + threadIdx.x;
+      if (i < n_pad * 4) {
+        const float4* s4 = reinterpret_cast<const float4*>(region + (i >> 2) * 128 + (i & 3) * 32);
+        a[t] = s4[0];
+        b[t] = s4[1];
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a[u].x), fabsf(a[u].y))), fmaxf(fabsf(a[u].z), fabsf(a[u].w)));
   }
+  __device__ __forceinline__ float max_abs(int n_pad) const {
+    float mx = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (t * kTThreads + (int)threadIdx.x < n_pad * 4)
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(a[t].x), fabsf(a[t].y)), fmaxf(fabsf(a[t].z), fabsf(a[t].w))),
+                             fmaxf(fmaxf(fabsf(b[t].x), fabsf(b[t].y)), fmaxf(fabsf(b[t].z), fabsf(b[t].w)))));
+    return mx;
+  }
+  __device__ __forceinline__ void write(uint8_t* region, int n_pad, float scale) const {
+    uint8_t* lo = region + n_pad * 64;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int i = t * kTThreads + threadIdx.x, r = i >> 2, ch = i & 3;
+      if (i < n_pad * 4) {
+        uint32_t h[4], l[4];
+        split_pack<false>(a[t].x * scale, a[t].y * scale, h[0], l[0]);
+        split_pack<false>(a[t].z * scale, a[t].w * scale, h[1], l[1]);
+        split_pack<false>(b[t].x * scale, b[t].y * scale, h[2], l[2]);
+        split_pack<false>(b[t].z * scale, b[t].w * scale, h[3], l[3]);
+        const int off = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(region + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+};
+// block-wide: the power of two that brings the largest of the threads' `mx` into [1, 2) (1 when everything is zero / denormal).
+// Two barriers; s_red[9].
+__device__ __forceinline__ float tpow2_block(float mx, float* s_red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = s_red[0];
-    for (int w = 1; w < kTThreads / 32; ++w) m = fmaxf(m, s_red[w]);
-    const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
-    s_red[8] = (e == 0u || e >= 253u) ? 1.f : __uint_as_float((254u - e) << 23);
-  }
-  __syncthreads();
-  return s_red[8];
+  float m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kTThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+  const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
+  return (e == 0u || e >= 253u) ? 1.f : __uint_as_float((254u - e) << 23);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -136,9 +152,21 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   {
     const int qv = min(128, p.Lq - qt * 128);
-    tstage_rows(s_q, s_q + 128 * 64, p.Q + (long long)seq * p.q_seq_stride + (long long)qt * 128 * p.ldq + head * 32, p.ldq, qv, 128, 1.f);
-    tstage_rows(s_k, s_k + lkp * 64, p.K + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp, 1.f);
-    tstage_rows(s_v, s_v + lkp * 64, p.V + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp, 1.f);
+    traw_issue(s_q, p.Q + (long long)seq * p.q_seq_stride + (long long)qt * 128 * p.ldq + head * 32, p.ldq, qv, 128);
+    traw_issue(s_k, p.K + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp);
+    traw_issue(s_v, p.V + (long long)seq * p.Lk * p.ldkv + head * 32, p.ldkv, p.Lk, lkp);
+    cp_async_wait_all();
+    __syncthreads();
+    TRaw<2> rq;
+    TRaw<4> rk;
+    rq.read(s_q, 128);
+    rk.read(s_k, lkp);
+    __syncthreads();
+    rq.write(s_q, 128, 1.f);
+    rk.write(s_k, lkp, 1.f);
+    rk.read(s_v, lkp);
+    __syncthreads();
+    rk.write(s_v, lkp, 1.f);
   }
   fence_proxy_async();                                   // generic-proxy shared-memory writes -> visible to the UMMA (async proxy)
   fence_before_sync();
@@ -148,15 +176,19 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
 
   const uint32_t idesc_s = make_idesc(128, 128, false, false, false);   // S = Q K^T, both K-major
   const uint32_t idesc_o = make_idesc(128, 32, false, false, true);     // O = P V, A from TMEM, B = V MN-major
-  const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_k), va = smem_u32(s_v);
+  // base descriptors (hi piece, row 0); every MMA's descriptors are one add away
+  const uint64_t dq = make_sdesc(smem_u32(s_q), 16, kTAtom, kSwz64), dk = make_sdesc(smem_u32(s_k), 16, kTAtom, kSwz64);
+  const uint64_t dv = make_sdesc(smem_u32(s_v), kTAtom, kTAtom, kSwz64);
+  const uint32_t kv_lo = (uint32_t)lkp * 64;
   auto issue_s = [&](int u) {
     uint32_t acc = 0;
+    const uint64_t dku = sdesc_advance(dk, u * 128 * 64);
 #pragma unroll
     for (int part = 0; part < 3; ++part) {
-      const uint32_t qp = qa + (part == 1 ? 128 * 64 : 0), kp = ka + (part == 2 ? lkp * 64 : 0) + u * 128 * 64;
+      const uint64_t qp = sdesc_advance(dq, part == 1 ? 128 * 64 : 0), kp = part == 2 ? sdesc_advance(dku, kv_lo) : dku;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        umma_f16(tmem_base, make_sdesc(qp + k * 32, 16, kTAtom, kSwz64), make_sdesc(kp + k * 32, 16, kTAtom, kSwz64), idesc_s, acc);
+        umma_f16(tmem_base, sdesc_advance(qp, k * 32), sdesc_advance(kp, k * 32), idesc_s, acc);
         acc = 1;
       }
     }
@@ -165,13 +197,14 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t acc = 0;
+      const uint64_t dvu = sdesc_advance(dv, (u * 128 + h * 64) * 64);
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
-        const uint32_t vp = va + (part == 2 ? lkp * 64 : 0) + (u * 128 + h * 64) * 64;
+        const uint64_t vp = part == 2 ? sdesc_advance(dvu, kv_lo) : dvu;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t pcol = (uint32_t)(h * 64 + (k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
-          umma_f16_ts(tmem_base + 128 + (u * 2 + h) * 32, tmem_base + pcol, make_sdesc(vp + k * 16 * 64, kTAtom, kTAtom, kSwz64), idesc_o, acc);
+          umma_f16_ts(tmem_base + 128 + (u * 2 + h) * 32, tmem_base + pcol, sdesc_advance(vp, k * 16 * 64), idesc_o, acc);
           acc = 1;
         }
       }
@@ -285,8 +318,8 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
   uint8_t* s_cy = s_cx + 2 * lcp * 64;
   float* s_lse2 = reinterpret_cast<float*>(s_cy + 2 * lcp * 64);   // [256] by query (row of the tile / column)
   float* s_D = s_lse2 + 256;
-  float* s_red = s_D + 256;                                        // [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 16);        // [0] scores ready, [1] outputs ready
+  float* s_red = s_D + 256;                                        // [32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 32);        // [0] scores ready, [1] outputs ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,46 +339,68 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
   const float* Gb = p.dO + (long long)seq * p.Lq * p.ldo + head * 32;
   const float* Ob = p.ctx + (long long)seq * p.Lq * p.ldo + head * 32;
   float sigma;
-  int ncols;                                             // valid columns
-  if (!KEYMAJOR) {
-    const int q0 = tile * 128, qv = min(128, p.Lq - q0);
-    sigma = tpow2_scale(Gb + (long long)q0 * p.ldo, p.ldo, qv, s_red);
-    tstage_rows(s_x, s_x + 128 * 64, Qb + (long long)q0 * p.ldq, p.ldq, qv, 128, 1.f);
-    tstage_rows(s_y, s_y + 128 * 64, Gb + (long long)q0 * p.ldo, p.ldo, qv, 128, sigma);
-    tstage_rows(s_cx, s_cx + lcp * 64, Kb, p.ldkv, p.Lk, lcp, 1.f);
-    tstage_rows(s_cy, s_cy + lcp * 64, Vb, p.ldkv, p.Lk, lcp, 1.f);
-    ncols = p.Lk;
-    // D = rowsum(dO . O): two threads per row, 16 columns each
-    {
-      const int row = threadIdx.x >> 1, part = threadIdx.x & 1;
-      float d = 0.f;
-      if (row < qv) {
-        const float4* g4 = reinterpret_cast<const float4*>(Gb + (long long)(q0 + row) * p.ldo + part * 16);
-        const float4* o4 = reinterpret_cast<const float4*>(Ob + (long long)(q0 + row) * p.ldo + part * 16);
+  const int ncols = KEYMAJOR ? p.Lq : p.Lk;              // valid columns
+  {
+    const int r0 = tile * 128;                           // first row of the tile (query / key)
+    const int rv = min(128, (KEYMAJOR ? p.Lk : p.Lq) - r0);
+    const float* xsrc = KEYMAJOR ? Kb + (long long)r0 * p.ldkv : Qb + (long long)r0 * p.ldq;
+    const float* ysrc = KEYMAJOR ? Vb + (long long)r0 * p.ldkv : Gb + (long long)r0 * p.ldo;
+    traw_issue(s_x, xsrc, KEYMAJOR ? p.ldkv : p.ldq, rv, 128);
+    traw_issue(s_y, ysrc, KEYMAJOR ? p.ldkv : p.ldo, rv, 128);
+    traw_issue(s_cx, KEYMAJOR ? Qb : Kb, KEYMAJOR ? p.ldq : p.ldkv, ncols, lcp);
+    traw_issue(s_cy, KEYMAJOR ? Gb : Vb, KEYMAJOR ? p.ldo : p.ldkv, ncols, lcp);
+    // per-row statistics travel in registers while the tiles are in flight
+    const int drow = threadIdx.x >> 1, dpart = threadIdx.x & 1;      // dQ kernel: D = rowsum(dO . O), two threads per row, 16 columns each
+    float4 o4[4];
+    float st_l = 0.f, st_d = 0.f;
+    if (!KEYMAJOR) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 g = __ldg(g4 + j), o = __ldg(o4 + j);
-          d = fmaf(g.x, o.x, d); d = fmaf(g.y, o.y, d); d = fmaf(g.z, o.z, d); d = fmaf(g.w, o.w, d);
-        }
+      for (int j = 0; j < 4; ++j)
+        o4[j] = drow < rv ? __ldg(reinterpret_cast<const float4*>(Ob + (long long)(r0 + drow) * p.ldo + dpart * 16) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dpart == 0 && drow < rv) st_l = __ldg(p.lse + sh * p.Lq + r0 + drow);
+    } else if ((int)threadIdx.x < p.Lq) {
+      st_l = __ldg(p.lse + sh * p.Lq + threadIdx.x);
+      st_d = __ldg(p.Dbuf + sh * p.Lq + threadIdx.x);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    TRaw<2> rx, ry;
+    TRaw<4> rc;
+    rx.read(s_x, 128);
+    ry.read(s_y, 128);
+    rc.read(s_cx, lcp);
+    float d = 0.f;
+    if (!KEYMAJOR) {                                     // dO . O from the raw dO rows, before they are overwritten
+      const float4* g4 = reinterpret_cast<const float4*>(s_y + drow * 128 + dpart * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 g = g4[j], o = o4[j];
+        d = fmaf(g.x, o.x, d); d = fmaf(g.y, o.y, d); d = fmaf(g.z, o.z, d); d = fmaf(g.w, o.w, d);
       }
       d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (part == 0) {
-        s_D[row] = d * sigma;
-        s_lse2[row] = row < qv ? p.lse[sh * p.Lq + q0 + row] * kLog2e : 0.f;
-        if (row < qv) p.Dbuf[sh * p.Lq + q0 + row] = d;
-      }
+      sigma = tpow2_block(ry.max_abs(128), s_red);       // (barrier inside: every raw read above is complete)
+    } else {
+      __syncthreads();
+      sigma = 1.f;
     }
-  } else {
-    const int k0 = tile * 128, kv = min(128, p.Lk - k0);
-    sigma = tpow2_scale(Gb, p.ldo, p.Lq, s_red);
-    tstage_rows(s_x, s_x + 128 * 64, Kb + (long long)k0 * p.ldkv, p.ldkv, kv, 128, 1.f);
-    tstage_rows(s_y, s_y + 128 * 64, Vb + (long long)k0 * p.ldkv, p.ldkv, kv, 128, 1.f);
-    tstage_rows(s_cx, s_cx + lcp * 64, Qb, p.ldq, p.Lq, lcp, 1.f);
-    tstage_rows(s_cy, s_cy + lcp * 64, Gb, p.ldo, p.Lq, lcp, sigma);
-    ncols = p.Lq;
-    for (int i = threadIdx.x; i < 256; i += kTThreads) {
-      s_lse2[i] = i < p.Lq ? p.lse[sh * p.Lq + i] * kLog2e : 0.f;
-      s_D[i] = i < p.Lq ? p.Dbuf[sh * p.Lq + i] * sigma : 0.f;
+    __syncthreads();
+    rx.write(s_x, 128, 1.f);
+    ry.write(s_y, 128, KEYMAJOR ? 1.f : sigma);
+    rc.write(s_cx, lcp, 1.f);
+    rc.read(s_cy, lcp);
+    if (KEYMAJOR) sigma = tpow2_block(rc.max_abs(lcp), s_red + 16);
+    else __syncthreads();
+    __syncthreads();
+    rc.write(s_cy, lcp, KEYMAJOR ? sigma : 1.f);
+    if (!KEYMAJOR) {
+      if (dpart == 0) {
+        s_D[drow] = d * sigma;
+        s_lse2[drow] = st_l * kLog2e;
+        if (drow < rv) p.Dbuf[sh * p.Lq + r0 + drow] = d;
+      }
+    } else {
+      s_lse2[threadIdx.x] = st_l * kLog2e;
+      s_D[threadIdx.x] = st_d * sigma;
     }
   }
   fence_proxy_async();
@@ -356,33 +411,37 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
 
   const uint32_t idesc_1 = make_idesc(128, 64, false, false, false);    // scores: both operands K-major
   const uint32_t idesc_2 = make_idesc(128, 32, false, false, true);     // accumulations: A from TMEM, B MN-major
-  const uint32_t xa = smem_u32(s_x), ya = smem_u32(s_y), cxa = smem_u32(s_cx), cya = smem_u32(s_cy);
+  // base descriptors (hi piece, row 0): K-major forms for the score-type products, MN-major forms of the column tensors for the accumulations
+  const uint64_t dxk = make_sdesc(smem_u32(s_x), 16, kTAtom, kSwz64), dyk = make_sdesc(smem_u32(s_y), 16, kTAtom, kSwz64);
+  const uint64_t dcxk = make_sdesc(smem_u32(s_cx), 16, kTAtom, kSwz64), dcyk = make_sdesc(smem_u32(s_cy), 16, kTAtom, kSwz64);
+  const uint64_t dcxm = make_sdesc(smem_u32(s_cx), kTAtom, kTAtom, kSwz64), dcym = make_sdesc(smem_u32(s_cy), kTAtom, kTAtom, kSwz64);
   const uint32_t lo_r = 128 * 64, lo_c = (uint32_t)lcp * 64;
   auto issue_scores = [&](int ch) {                      // T1[128, 64] = X CX_ch^T (columns 0..63), T2 = Y CY_ch^T (columns 64..127)
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      const uint32_t ra = t ? ya : xa, ca = (t ? cya : cxa) + ch * 64 * 64;
+      const uint64_t ra = t ? dyk : dxk, ca = sdesc_advance(t ? dcyk : dcxk, ch * 64 * 64);
       uint32_t acc = 0;
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
-        const uint32_t rp = ra + (part == 1 ? lo_r : 0), cp = ca + (part == 2 ? lo_c : 0);
+        const uint64_t rp = sdesc_advance(ra, part == 1 ? lo_r : 0), cp = part == 2 ? sdesc_advance(ca, lo_c) : ca;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          umma_f16(tmem_base + t * 64, make_sdesc(rp + k * 32, 16, kTAtom, kSwz64), make_sdesc(cp + k * 32, 16, kTAtom, kSwz64), idesc_1, acc);
+          umma_f16(tmem_base + t * 64, sdesc_advance(rp, k * 32), sdesc_advance(cp, k * 32), idesc_1, acc);
           acc = 1;
         }
       }
     }
   };
-  auto issue_accum = [&](int ch, uint32_t dcol, uint32_t acol, uint32_t btile) {   // D[128, 32] (+)= A(TMEM columns acol..) B_ch
+  auto issue_accum = [&](int ch, uint32_t dcol, uint32_t acol, uint64_t btile) {   // D[128, 32] (+)= A(TMEM columns acol..) B_ch
     uint32_t acc = ch > 0 ? 1u : 0u;
+    const uint64_t bch = sdesc_advance(btile, ch * 64 * 64);
 #pragma unroll
     for (int part = 0; part < 3; ++part) {
-      const uint32_t bp = btile + (part == 2 ? lo_c : 0) + ch * 64 * 64;
+      const uint64_t bp = part == 2 ? sdesc_advance(bch, lo_c) : bch;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t pcol = acol + (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
-        umma_f16_ts(tmem_base + dcol, tmem_base + pcol, make_sdesc(bp + k * 16 * 64, kTAtom, kTAtom, kSwz64), idesc_2, acc);
+        umma_f16_ts(tmem_base + dcol, tmem_base + pcol, sdesc_advance(bp, k * 16 * 64), idesc_2, acc);
         acc = 1;
       }
     }
@@ -440,10 +499,10 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
     fence_after_sync();
     if (threadIdx.x == 0) {
       if (KEYMAJOR) {
-        issue_accum(ch, 128, 0, cya);                    // dV += (P . mask)^T dO
-        issue_accum(ch, 160, 64, cxa);                   // dK += dS^T Q
+        issue_accum(ch, 128, 0, dcym);                    // dV += (P . mask)^T dO
+        issue_accum(ch, 160, 64, dcxm);                   // dK += dS^T Q
       } else {
-        issue_accum(ch, 128, 0, cxa);                    // dQ += dS K
+        issue_accum(ch, 128, 0, dcxm);                    // dQ += dS K
       }
       if (ch + 1 < nch) {
         issue_scores(ch + 1);                            // overwrites T1 / T2: the MMA pipe runs in issue order
@@ -477,7 +536,7 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
 }
 
 inline size_t tattn_fwd_smem(int lkp) { return 1024 + 2 * 128 * 64 + 4 * (size_t)lkp * 64 + 2 * 4 * 128 * sizeof(float) + 64; }
-inline size_t tattn_bwd_smem(int lcp) { return 1024 + 4 * 128 * 64 + 4 * (size_t)lcp * 64 + (256 + 256 + 16) * sizeof(float) + 64; }
+inline size_t tattn_bwd_smem(int lcp) { return 1024 + 4 * 128 * 64 + 4 * (size_t)lcp * 64 + (256 + 256 + 32) * sizeof(float) + 64; }
 
 }  // namespace tc
 }  // namespace hft

@@ -6,8 +6,8 @@
 // activations once the products run on the tensor cores.
 //
 // Arithmetic: a.w = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in fp16 with fp32 accumulation in TMEM (22 mantissa bits); every
-// row of A is scaled by the power of two that brings its largest magnitude into [1, 2) before the split (gradients are
-// ~1e-6: fp16 would flush them) and W by one power of two per matrix; the epilogue scales back (exact).
+// row of A and every row of W (output feature) is scaled by the power of two that brings its largest magnitude into [1, 2)
+// before the split (gradients are ~1e-6: fp16 would flush them); the epilogue scales back per row and column (exact).
 //
 // Structure: persistent CTAs (two per SM, 256 threads, 256 TMEM columns each).  W is staged once per CTA as hi | lo fp16 in
 // the K-major 128-byte-swizzled UMMA layout (transposed on the way when it is stored [K, N]); per 128-row tile the threads
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   uint8_t* s_w = s_a + 2 * A_PART;                            // [hi | lo][KB][N rows x 128 B]
   const int w_part = KB * p.N * 128;
   float* s_bias = reinterpret_cast<float*>(s_w + 2 * w_part); // [256]
-  float* s_inv = s_bias + 256;                                // [128] 1 / row scale of the current tile
-  float* s_red = s_inv + 128;                                 // [16]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 16);
+  float* s_winv = s_bias + 256;                               // [256] 1 / scale of W row n
+  float* s_inv = s_winv + 256;                                // [128] 1 / row scale of the current tile
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_inv + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -61,39 +61,45 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
 
-  // ---- W: largest magnitude -> one power-of-two scale; hi | lo tiles --------------------------------------------------
-  float sigma_w;
+  // ---- W rows (output features) -> per-row power-of-two scale -> hi | lo tiles; every thread loads all its chunks before converting ----
   {
-    float mx = 0.f;
-    const int rows_w = p.w_kn ? p.K : N, cols_w = p.w_kn ? N : p.K;
-    for (int i = tid; i < rows_w * cols_w; i += kGThreads) mx = fmaxf(mx, fabsf(__ldg(p.W + (long long)(i / cols_w) * p.ldw + i % cols_w)));
+    constexpr int WT = 8;                                      // chunks per thread: N * CH / 256 <= 8 (N <= 256 at K = 64, N <= 128 at K = 128)
+    float v[WT][8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    mx = s_red[0];
+    for (int t = 0; t < WT; ++t) {
+      const int i = t * kGThreads + tid, n = i / CH, ch = i % CH;
+      if (i < N * CH) {
+        if (p.w_kn) {
 #pragma unroll
-    for (int w = 1; w < kGThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
-    sigma_w = pow2_inv_of(mx);
-    for (int i = tid; i < N * CH; i += kGThreads) {
-      float v[8];
-      int n, ch;
-      if (p.w_kn) {
-        n = i % N; ch = i / N;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.W + (long long)(ch * 8 + j) * p.ldw + n);
+          for (int j = 0; j < 8; ++j) v[t][j] = __ldg(p.W + (long long)(ch * 8 + j) * p.ldw + n);
+        } else {
+          const float4* s4 = reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + ch * 8);
+          const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+          v[t][0] = a.x; v[t][1] = a.y; v[t][2] = a.z; v[t][3] = a.w; v[t][4] = b.x; v[t][5] = b.y; v[t][6] = b.z; v[t][7] = b.w;
+        }
       } else {
-        n = i / CH; ch = i % CH;
-        const float4* s4 = reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + ch * 8);
-        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      }
-      uint32_t h[4], l[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack<false>(v[2 * j] * sigma_w, v[2 * j + 1] * sigma_w, h[j], l[j]);
-      const int off = (ch >> 3) * N * 128 + n * 128 + (((ch & 7) ^ (n & 7)) << 4);
-      *reinterpret_cast<uint4*>(s_w + off) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(s_w + w_part + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < WT; ++t) {
+      const int i = t * kGThreads + tid, n = i / CH, ch = i % CH;
+      float mx = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(v[t][j]));
+#pragma unroll
+      for (int o = CH / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // the CH lanes that share the row
+      if (i < N * CH) {
+        const float sg = pow2_inv_of(mx);
+        if (ch == 0) s_winv[n] = 1.f / sg;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_pack<false>(v[t][2 * j] * sg, v[t][2 * j + 1] * sg, h[j], l[j]);
+        const int off = (ch >> 3) * N * 128 + n * 128 + (((ch & 7) ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(s_w + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(s_w + w_part + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
     for (int i = tid; i < 256; i += kGThreads) s_bias[i] = (p.bias && i < N) ? __ldg(p.bias + i) : 0.f;
   }
@@ -102,7 +108,6 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const float inv_sigma_w = 1.f / sigma_w;
 
   const long long n_tiles = (p.M + 127) >> 7;
   float4 ra[TASKS][2];
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
     }
   };
   const uint32_t idesc = make_idesc(128, N, false, false, false);
-  const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
+  const uint64_t da = make_sdesc(smem_u32(s_a), 16, 1024, kSwz128), dw = make_sdesc(smem_u32(s_w), 16, 1024, kSwz128);   // bases: hi piece, K block 0
   const int q = warp & 3, half = warp >> 2;
   const int n_chunks = (N + 31) >> 5;
   uint8_t* stage = s_a + warp * 4096;
@@ -158,14 +163,16 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
       uint32_t acc = 0;
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
-        const uint32_t ap = a_addr + (part == 1 ? A_PART : 0), wp = w_addr + (part == 2 ? w_part : 0);
+        const uint64_t ap = sdesc_advance(da, part == 1 ? A_PART : 0), wp = part == 2 ? sdesc_advance(dw, w_part) : dw;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t wk = sdesc_advance(wp, kb * N * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_base, make_sdesc(ap + kb * (128 * 128) + k * 32, 16, 1024, kSwz128), make_sdesc(wp + kb * N * 128 + k * 32, 16, 1024, kSwz128), idesc, acc);
+            umma_f16(tmem_base, sdesc_advance(ap, kb * (128 * 128) + k * 32), sdesc_advance(wk, k * 32), idesc, acc);
             acc = 1;
           }
+        }
       }
       umma_commit(bar);
     }
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
     fence_after_sync();
 
     // ---- epilogue: thread = row; 32-column blocks through the warp's swizzled staging block ----
-    const float unscale = s_inv[q * 32 + lane] * inv_sigma_w;
+    const float unscale = s_inv[q * 32 + lane];
     for (int c = half; c < n_chunks; c += 2) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          o[e] = fmaf(__uint_as_float(v[4 * g + e]), unscale, s_bias[c * 32 + 4 * g + e]);
+          o[e] = fmaf(__uint_as_float(v[4 * g + e]) * unscale, s_winv[c * 32 + 4 * g + e], s_bias[c * 32 + 4 * g + e]);
           if (p.relu) o[e] = fmaxf(o[e], 0.f);
         }
         *reinterpret_cast<float4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-inline size_t tgemm_smem(int KB, int N) { return 1024 + 2 * (size_t)KB * 128 * 128 + 2 * (size_t)KB * N * 128 + (256 + 128 + 16) * sizeof(float) + 64; }
+inline size_t tgemm_smem(int KB, int N) { return 1024 + 2 * (size_t)KB * 128 * 128 + 2 * (size_t)KB * N * 128 + (256 + 256 + 128) * sizeof(float) + 64; }
 
 }  // namespace tc
 }  // namespace hft

@@ -13,6 +13,7 @@
 #include "train_kernels.cuh"
 #include "tc_train_attn.cuh"
 #include "tc_train_gemm.cuh"
+#include "tc_train_dw.cuh"
 
 #include <math.h>
 #include <vector>
@@ -76,8 +77,32 @@ static bool train_tc_enabled() {
 }
 static bool tgemm_ok(const float* A, int lda, const float* W, int ldw, bool w_kn, const float* C, int ldc, int N, int K, const float* mask, int ldm) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  return train_tc_enabled() && (K == 64 || K == 128) && N % 16 == 0 && N >= 16 && N <= 256 && lda % 4 == 0 && ldc % 4 == 0 && (w_kn || ldw % 4 == 0) && al(A) && al(W) &&
+  return train_tc_enabled() && (K == 64 || K == 128) && N % 16 == 0 && N >= 16 && N * (K / 8) <= 2048 && lda % 4 == 0 && ldc % 4 == 0 && (w_kn || ldw % 4 == 0) && al(A) && al(W) &&
          al(C) && (!mask || (ldm % 4 == 0 && al(mask))) && tc::tgemm_smem(K / 64, N) <= 113 * 1024;
+}
+// stage height and CTAs per SM of the tcgen05 weight-gradient kernel: 32-row stages and three CTAs per SM when they fit (shared memory, 512 TMEM columns)
+static void tdw_plan(int N, int K, int* rows, int* minb, int* tmem_cols) {
+  const int G = ((N + 63) / 64 + 1) / 2, need = G * (K + 32);
+  *tmem_cols = need <= 128 ? 128 : 256;
+  const char* e = getenv("HFT_TRAIN_DW_ROWS");                          // experiment switch: 64 = the two-CTA, 64-row-stage variant where it fits
+  const bool want64 = e && atoi(e) == 64;
+  if (want64 && tc::tdw_smem(K / 64, N, 64) <= 113 * 1024) { *rows = 64; *minb = 2; return; }
+  *rows = 32;
+  *minb = (*tmem_cols == 128 && tc::tdw_smem(K / 64, N, 32) <= 75 * 1024) ? 3 : 2;
+}
+// The tcgen05 weight-gradient kernel is correct (tests/test_gpu_train_linear.py) but, measured, only level with the fp32 CUDA-core kernel
+// (both ~1.7-2.0 TB/s of their operands: the single-buffered stage chain load -> convert -> MMA is latency-bound), so the training step keeps
+// dw_gemm_kernel unless HFT_TRAIN_TC_DW=1; hft_train_linear_wgrad(use_tc = 1) always runs it.
+static bool tdw_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC_DW"); v = (e && e[0] == '1') ? 1 : 0; }
+  return g_train_tc_force >= 0 ? g_train_tc_force == 1 : (v == 1 && train_tc_enabled());
+}
+static bool tdw_ok(const float* dY, int ldy, const float* X, int ldx, int N, int K) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int G = ((N + 63) / 64 + 1) / 2;
+  return tdw_enabled() && (K == 64 || K == 128) && N % 8 == 0 && N >= 8 && N + K <= 256 && G * (K + 32) <= 256 && ldy % 4 == 0 && ldx % 4 == 0 && al(dY) && al(X) &&
+         tc::tdw_smem(K / 64, N, 32) <= 113 * 1024;
 }
 static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a) {
   static const int sms = num_sms();
@@ -135,6 +160,32 @@ static int gemm_nn(cudaStream_t s, const float* A, int lda, const float* W, int 
 // dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)
 static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, long long M, int N, int K) {
   HFT_REQUIRE(ldy % 4 == 0 && ldx % 4 == 0, HFT_ERR_UNSUPPORTED, "train dw gemm: ldy=%d ldx=%d", ldy, ldx);
+  if (M > 0 && tdw_ok(dY, ldy, X, ldx, N, K)) {
+    static const int sms_tc = num_sms();
+    tc::TDwArgs a{};
+    a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.dW = dW; a.ldw = ldw; a.db = db; a.M = M; a.N = N; a.K = K;
+    int R, minb;
+    tdw_plan(N, K, &R, &minb, &a.tmem_cols);
+    long long ctas = (long long)minb * sms_tc;                     // every resident slot one CTA, at least four stages each
+    if (ctas > (M + 4 * R - 1) / (4 * R)) ctas = (M + 4 * R - 1) / (4 * R);
+    a.rows_per_cta = ((M + ctas - 1) / ctas + R - 1) / R * R;
+    ctas = (M + a.rows_per_cta - 1) / a.rows_per_cta;
+    const size_t smem = tc::tdw_smem(K / 64, N, R);
+    LaunchScope ls(HFT_KCLASS_GEMM, s);
+#define HFT_TDW_LAUNCH(KBv, Rv, Bv)                                                                   \
+  do {                                                                                                \
+    HFT_SET_MAX_SMEM((tc::tdw_kernel<KBv, Rv, Bv>), 113 * 1024);                                      \
+    tc::tdw_kernel<KBv, Rv, Bv><<<(unsigned)ctas, tc::kDwThreads, smem, s>>>(a);                      \
+  } while (0)
+    if (K == 64 && R == 64) HFT_TDW_LAUNCH(1, 64, 2);
+    else if (K == 64 && minb == 3) HFT_TDW_LAUNCH(1, 32, 3);
+    else if (K == 64) HFT_TDW_LAUNCH(1, 32, 2);
+    else if (R == 64) HFT_TDW_LAUNCH(2, 64, 2);
+    else if (minb == 3) HFT_TDW_LAUNCH(2, 32, 3);
+    else HFT_TDW_LAUNCH(2, 32, 2);
+#undef HFT_TDW_LAUNCH
+    return HFT_OK;
+  }
   const int gx = (N + DWT - 1) / DWT, gy = (K + DWT - 1) / DWT;
   // split M so that the grid fills the chip two (256-thread, 128-register) CTAs deep (the tile count gx * gy is 1..6 for this model: without the split a
   // [64 x 64] dW ran on 44..128 of the 148 SMs), with at least four stages per CTA so the closing atomics stay the minor part
@@ -575,9 +626,9 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
   HFT_CHECK_CUDA(cudaMemsetAsync(t.g_front_b, 0, (size_t)H * sizeof(float), s));
   {
     LaunchScope ls(HFT_KCLASS_FRONT, s);
-    if (H == 64) front_bwd_kernel<65, 4><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
-    else if (H == 128) front_bwd_kernel<65, 2><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
-    else front_bwd_kernel<65, 1><<<NB, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    if (H == 64) front_bwd_kernel<65, 4><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    else if (H == 128) front_bwd_kernel<65, 2><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    else front_bwd_kernel<65, 1><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
     const int C = m->d.cnn_channel, kw = m->d.cnn_kernel, n_out = m->nproc - (kw - 1);
     const int total = H * C * n_out + H + C * kw + C;
     front_chain_bwd_kernel<<<(total + 127) / 128, 128, 0, s>>>(t.g_front_w, t.g_front_b, m->w[m->tok_w], m->w[m->conv_w], m->w[m->conv_b], H, C, kw, n_out, m->nproc,
@@ -796,6 +847,27 @@ extern "C" int hft_train_linear(int32_t use_tc, int32_t w_kn, const float* a_dev
     rc = gemm_nn(s, a_dev, lda, w_dev, ldw, c_dev, ldc, m, n, k, accum != 0, mask_dev, ldm, mask_scale);
   } else {
     rc = gemm_tn(s, a_dev, lda, w_dev, ldw, bias_dev, c_dev, ldc, m, n, k, relu != 0, accum != 0);
+  }
+  g_train_tc_force = -1;
+  if (rc != HFT_OK) return rc;
+  HFT_CHECK_CUDA(cudaGetLastError());
+  return HFT_OK;
+}
+
+// Component entry: the weight gradient of one Linear of the training step, dW[n, k] += dY[m, n]^T X[m, k] and db[n] += colsum(dY) (db may be NULL),
+// on fp32 device tensors.  use_tc as in hft_train_attention (tcgen05 kernel: k = 64 / 128, n % 8 == 0, n + k <= 256).
+extern "C" int hft_train_linear_wgrad(int32_t use_tc, const float* dy_dev, int32_t ldy, const float* x_dev, int32_t ldx, float* dw_dev, int32_t ldw, float* db_dev,
+                                      int64_t m, int32_t n, int32_t k, void* stream) {
+  HFT_REQUIRE(dy_dev && x_dev && dw_dev && m >= 1 && n >= 1 && k >= 1, HFT_ERR_ARG, "hft_train_linear_wgrad: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_launch_count();
+  g_train_tc_force = use_tc;
+  int rc;
+  if (use_tc == 1 && !tdw_ok(dy_dev, ldy, x_dev, ldx, n, k)) {
+    set_error("hft_train_linear_wgrad: the tcgen05 kernel needs K = 64 or 128, N %% 8 == 0, N + K <= 256, 16-byte aligned rows");
+    rc = HFT_ERR_UNSUPPORTED;
+  } else {
+    rc = gemm_dw(s, dy_dev, ldy, x_dev, ldx, dw_dev, ldw, db_dev, m, n, k);
   }
   g_train_tc_force = -1;
   if (rc != HFT_OK) return rc;

@@ -692,7 +692,8 @@ __global__ void time_relayout_bwd_kernel(const float* __restrict__ gU, float sca
 }
 
 // Front backward: dWc[h, j] += sum_{b,f} dE[(b,f,bin), h] * spec[b, bin, f + j],  dbc[h] += sum dE   (collapsed 65-tap filter).
-// grid (n_bin); threads = G tap groups x H (G * H = 256).  dE = dX * sqrt(H) (the embedding scale).
+// grid (n_bin, batch): one CTA per (bin, segment) -- 2 048 CTAs for the reduced model, where a grid of n_bin alone left the chip at two CTAs per SM --;
+// threads = G tap groups x H (G * H = 256).  dE = dX * sqrt(H) (the embedding scale).
 template <int NPROC, int G>
 __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st, const float* __restrict__ dX,
                                                         float scale, int H, int F, int NB, int B, float* __restrict__ dWc, float* __restrict__ dbc) {
@@ -705,10 +706,11 @@ __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
   float bsum = 0.f;
-  for (int b = 0; b < B; ++b) {
-    __syncthreads();
+  {
+    const int b = blockIdx.y;
     for (int i = threadIdx.x; i < W; i += blockDim.x) s_row[i] = spec[b * sb + bin * sbin + i * st];
     __syncthreads();
+#pragma unroll 4
     for (int f = 0; f < F; ++f) {
       const float e = dX[(((long long)b * F + f) * NB + bin) * H + h] * scale;
       if (g == 0) bsum += e;

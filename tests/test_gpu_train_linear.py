@@ -58,3 +58,31 @@ def test_training_linear_matches_fp64(M, N, K, form, rm, accum, scale):
         errs[use_tc] = float((c[:, :N].double() - ref).abs().max() / ref.abs().max())
     print("relative-to-max error: tcgen05 %.3g | fp32 CUDA cores %.3g" % (errs[1], errs[0]))
     assert errs[1] <= 2e-6 and errs[0] <= 2e-6, errs
+
+
+WG_CASES = [  # (M, N, K)
+    (50000, 192, 64), (30001, 64, 64), (20000, 128, 64), (20000, 64, 128), (9000, 144, 64), (300, 64, 64), (70000, 128, 128), (4097, 8, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", WG_CASES)
+def test_training_linear_weight_gradient_matches_fp64(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    rnd = lambda *shape: torch.randn(*shape, device="cuda", generator=g)
+    ldy, ldx = N + 64, K + 32
+    dy_full, x_full = rnd(M, ldy) * 2e-6, rnd(M, ldx) * 1.3
+    dy_full[::5] *= 1e-2                                   # rows of very different magnitude
+    dy_full[: M // 3] *= 30.0
+    dw0, db0 = rnd(N, K) * 1e-4, rnd(N) * 1e-4             # the kernels accumulate into what is there
+    ref_w = dw0.double() + dy_full[:, :N].double().t() @ x_full[:, :K].double()
+    ref_b = db0.double() + dy_full[:, :N].double().sum(0)
+    errs = {}
+    for use_tc in (1, 0):
+        dw, db = dw0.clone(), db0.clone()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().hft_train_linear_wgrad(use_tc, _ptr(dy_full), ldy, _ptr(x_full), ldx, _ptr(dw), K, _ptr(db), M, N, K, st), "hft_train_linear_wgrad")
+        torch.cuda.synchronize()
+        errs[use_tc] = (float((dw.double() - ref_w).abs().max() / ref_w.abs().max()), float((db.double() - ref_b).abs().max() / ref_b.abs().max()))
+    print("relative-to-max errors (dW, db): tcgen05 %s | fp32 CUDA cores %s" % (errs[1], errs[0]))
+    for use_tc in (1, 0):
+        assert errs[use_tc][0] <= 5e-6 and errs[use_tc][1] <= 5e-6, errs
