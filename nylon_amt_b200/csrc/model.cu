@@ -3,6 +3,7 @@
 // names are the drop-in contract: m_training.py:275 load_state_dict, amt.py:24-25 pickled modules).
 #include "common.cuh"
 #include "model.h"
+#include "hft_internal.h"
 
 #include <math.h>
 
@@ -116,9 +117,20 @@ __global__ void collapse_front_kernel(const float* __restrict__ tok_w, const flo
   }
 }
 
-__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
+// Up to kCopyCap device-to-device slice copies in ONE launch (the fused Q|K|V / K|V / head matrices are re-assembled from the parameter arena
+// after every optimiser step: 54 copies for the reduced model, which as separate launches cost 4 us each).  blockIdx.y = slice.
+constexpr int kCopyCap = 96;
+struct CopyBatch {
+  const float* src[kCopyCap];
+  float* dst[kCopyCap];
+  int n[kCopyCap];
+  int count;
+};
+__global__ void copy_batch_kernel(const __grid_constant__ CopyBatch b) {
+  const int e = blockIdx.y, n = b.n[e];
+  const float* __restrict__ src = b.src[e];
+  float* __restrict__ dst = b.dst[e];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // q0[n][o] = sum_h pos[n][h] W[o][h] + b[o]   (fc_q of the constant pitch queries, model_spec2midi.py:154-155,260)
@@ -132,8 +144,15 @@ __global__ void q0_kernel(const float* __restrict__ pos, const float* __restrict
   q0[idx] = acc + b[o];
 }
 
-static void dcopy(const float* src, float* dst, long long n, cudaStream_t s) {
-  copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+static void copy_flush(CopyBatch& cb, cudaStream_t s) {
+  if (cb.count == 0) return;
+  int mx = 1;
+  for (int i = 0; i < cb.count; ++i) mx = cb.n[i] > mx ? cb.n[i] : mx;
+  int gx = (mx + 1023) / 1024;
+  if (gx > 64) gx = 64;
+  copy_batch_kernel<<<dim3(gx, cb.count), 256, 0, s>>>(cb);
+  count_launch();
+  cb.count = 0;
 }
 
 static int derive_weights(Model* m, cudaStream_t s) {
@@ -145,6 +164,11 @@ static int derive_weights(Model* m, cudaStream_t s) {
                   2 * ((size_t)(3 + V) * H + (3 + V)) + 64 * (8 + 2 * (n_self + n_cross));   // + per-slice alignment slack
   if (!m->derived_arena) HFT_CHECK_CUDA(cudaMalloc(&m->derived_arena, floats * sizeof(float)));
   float* p = m->derived_arena;
+  CopyBatch cb{};
+  auto dcopy = [&](const float* src, float* dst, long long n, cudaStream_t st) {
+    if (cb.count == kCopyCap) copy_flush(cb, st);
+    cb.src[cb.count] = src; cb.dst[cb.count] = dst; cb.n[cb.count] = (int)n; ++cb.count;
+  };
   auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };   // 256-byte aligned slices
   m->front_w = take((size_t)H * m->nproc);
   m->front_b = take(H);
@@ -181,6 +205,7 @@ static int derive_weights(Model* m, cudaStream_t s) {
   };
   fuse_heads(m->head_freq, m->headA_w, m->headA_b);
   fuse_heads(m->head_time, m->headB_w, m->headB_b);
+  copy_flush(cb, s);
   HFT_CHECK_CUDA(cudaGetLastError());
   return HFT_OK;
 }

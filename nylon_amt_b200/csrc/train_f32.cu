@@ -200,10 +200,19 @@ static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int
   dw_gemm_kernel<<<dim3(gx, gy, (unsigned)splits), DWTHREADS, DW_SMEM, s>>>(dY, ldy, X, ldx, dW, ldw, db, M, N, K, rps);
   return HFT_OK;
 }
+static long long ln_grid(long long rows, int rpw) {              // CTAs of 8 warps x rpw rows, at most 16 per SM (grid-stride beyond that)
+  static const int sms = num_sms();
+  const long long need = (rows + 8 * rpw - 1) / (8 * rpw);
+  return need < 16LL * sms ? need : 16LL * sms;
+}
 static void ln_fwd(Model* m, cudaStream_t s, const float* x, const float* r, long long r_rows, const LnW& ln, long long rows, float* y, float* sum_out,
                    Drop drop = Drop{0, 0, 0, 1.f}, bool drop_x = false) {
   LaunchScope ls(HFT_KCLASS_NORM, s);
-  add_ln_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, r, r_rows, m->w[ln.g], m->w[ln.b], m->H, rows, y, sum_out, drop, drop_x);
+  const float *g = m->w[ln.g], *b = m->w[ln.b];
+  if (m->H == 64) add_ln_v8_kernel<8><<<(unsigned)ln_grid(rows, 4), 256, 0, s>>>(x, r, r_rows, g, b, rows, y, sum_out, drop, drop_x);
+  else if (m->H == 128) add_ln_v8_kernel<16><<<(unsigned)ln_grid(rows, 2), 256, 0, s>>>(x, r, r_rows, g, b, rows, y, sum_out, drop, drop_x);
+  else if (m->H == 256) add_ln_v8_kernel<32><<<(unsigned)ln_grid(rows, 1), 256, 0, s>>>(x, r, r_rows, g, b, rows, y, sum_out, drop, drop_x);
+  else add_ln_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, r, r_rows, g, b, m->H, rows, y, sum_out, drop, drop_x);
 }
 // element-wise dropout in place (forward of an embedding / hidden dropout, or the backward of one)
 static void dropout_inplace(cudaStream_t s, float* x, long long n, const Drop& d) {
@@ -220,7 +229,14 @@ static const float* branch_grad(cudaStream_t s, const float* g, float* scratch, 
 }
 static void ln_bwd(Model* m, cudaStream_t s, const float* dy, const float* sum, const LnW& ln, long long rows, float* ds, float* G) {
   LaunchScope ls(HFT_KCLASS_NORM, s);
-  ln_bwd_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(dy, sum, m->w[ln.g], m->H, rows, ds, G + (m->w[ln.g] - m->arena), G + (m->w[ln.b] - m->arena));
+  float *dg = G + (m->w[ln.g] - m->arena), *db = G + (m->w[ln.b] - m->arena);
+  static const int sms = num_sms();
+  // few, long-lived CTAs: every CTA closes with 2 H atomics
+  const unsigned grid = (unsigned)(rows < 4LL * sms * 64 ? (rows + 63) / 64 : 4LL * sms);
+  if (m->H == 64) ln_bwd_v8_kernel<8><<<grid, 256, 0, s>>>(dy, sum, m->w[ln.g], rows, ds, dg, db);
+  else if (m->H == 128) ln_bwd_v8_kernel<16><<<grid, 256, 0, s>>>(dy, sum, m->w[ln.g], rows, ds, dg, db);
+  else if (m->H == 256) ln_bwd_v8_kernel<32><<<grid, 256, 0, s>>>(dy, sum, m->w[ln.g], rows, ds, dg, db);
+  else ln_bwd_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(dy, sum, m->w[ln.g], m->H, rows, ds, dg, db);
 }
 static void colsum(cudaStream_t s, const float* in, long long rows, long long cols, float* out) {
   long long splits = rows >= 64 ? 16 : 1;
@@ -630,7 +646,7 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
     else if (H == 128) front_bwd_kernel<65, 2><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
     else front_bwd_kernel<65, 1><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
     const int C = m->d.cnn_channel, kw = m->d.cnn_kernel, n_out = m->nproc - (kw - 1);
-    const int total = H * C * n_out + H + C * kw + C;
+    const int total = H * C * n_out + H + 32 * (C * kw + C);                     // threads, then one warp per conv_w / conv_b element
     front_chain_bwd_kernel<<<(total + 127) / 128, 128, 0, s>>>(t.g_front_w, t.g_front_b, m->w[m->tok_w], m->w[m->conv_w], m->w[m->conv_b], H, C, kw, n_out, m->nproc,
                                                                 gof(m, G, m->tok_w), gof(m, G, m->tok_b), gof(m, G, m->conv_w), gof(m, G, m->conv_b));
   }

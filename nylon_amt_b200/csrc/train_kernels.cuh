@@ -274,6 +274,139 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// The two LayerNorm kernels of the training step for H = 64 / 128 / 256, eight columns per lane: a row takes LPR = H / 8 lanes (two 16-byte
+// loads per lane and tensor), a warp works on 32 / LPR rows at a time -- for the reduced model four rows per warp instruction where the
+// one-row-per-warp kernels (add_ln_f32_kernel, ln_bwd_kernel) moved 8 bytes per lane and ran at 1.5-2.2 TB/s.  Same arithmetic, same
+// dropout indexing (element row * H + col).
+// ------------------------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// y = LayerNorm(x + r) * g + b (see add_ln_f32_kernel); grid-stride over groups of 8 * (32 / LPR) rows per CTA
+template <int LPR>
+__global__ void __launch_bounds__(256) add_ln_v8_kernel(const float* __restrict__ x, const float* __restrict__ r, long long r_rows, const float* __restrict__ g,
+                                                        const float* __restrict__ b, long long rows, float* __restrict__ y, float* __restrict__ sum_out, Drop drop,
+                                                        bool drop_x) {
+  constexpr int H = LPR * 8, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, c0 = (lane % LPR) * 8;
+  float gg[8], bb[8];
+  ld8(g + c0, gg);
+  ld8(b + c0, bb);
+  const long long stride = (long long)gridDim.x * 8 * RPW;
+  const long long n_iter = (rows + stride - 1) / stride;     // (whole warps stay in the loop for the shuffles)
+  for (long long it = 0; it < n_iter; ++it) {
+    const long long row = it * stride + ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + sub;
+    const bool live = row < rows;
+    float v[8], rv[8];
+    if (live) {
+      ld8(x + row * H + c0, v);
+      ld8(r + (row % r_rows) * H + c0, rv);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = 0.f; rv[i] = 0.f; }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (drop.thresh) {
+        const bool keep = drop_keep(drop, (unsigned long long)(row * H + c0 + i));
+        if (drop_x) v[i] = keep ? v[i] * drop.scale : 0.f; else rv[i] = keep ? rv[i] * drop.scale : 0.f;
+      }
+      v[i] += rv[i];
+      s += v[i];
+    }
+    if (live && sum_out) st8(sum_out + row * H + c0, v);
+    const float mean = group_sum<LPR>(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(group_sum<LPR>(q) / (float)H + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+    if (live) st8(y + row * H + c0, v);
+  }
+}
+
+// LayerNorm backward (see ln_bwd_kernel): ds, and dg / db through per-lane column partials -> shared memory -> one atomicAdd per column and CTA
+template <int LPR>
+__global__ void __launch_bounds__(256) ln_bwd_v8_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ g, long long rows,
+                                                        float* __restrict__ ds, float* __restrict__ dg, float* __restrict__ db) {
+  constexpr int H = LPR * 8, RPW = 32 / LPR;
+  __shared__ float s_dg[8][H], s_db[8][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR, c0 = (lane % LPR) * 8;
+  float gg[8], pg[8], pb[8];
+  ld8(g + c0, gg);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
+  const long long stride = (long long)gridDim.x * 8 * RPW;
+  const long long n_iter = (rows + stride - 1) / stride;
+  for (long long it = 0; it < n_iter; ++it) {
+    const long long row = it * stride + ((long long)blockIdx.x * 8 + warp) * RPW + sub;
+    const bool live = row < rows;
+    float v[8], d[8];
+    if (live) {
+      ld8(s + row * H + c0, v);
+      ld8(dy + row * H + c0, d);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = 0.f; d[i] = 0.f; }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += v[i];
+    const float mean = group_sum<LPR>(sum) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float t = v[i] - mean; q = fmaf(t, t, q); }
+    const float rstd = rsqrtf(group_sum<LPR>(q) / (float)H + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (v[i] - mean) * rstd, dxh = d[i] * gg[i];
+      pg[i] = fmaf(d[i], xh, pg[i]);
+      pb[i] += d[i];
+      v[i] = xh; d[i] = dxh;
+      m1 += dxh; m2 = fmaf(dxh, xh, m2);
+    }
+    m1 = group_sum<LPR>(m1) / (float)H;
+    m2 = group_sum<LPR>(m2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = rstd * (d[i] - m1 - v[i] * m2);
+    if (live) st8(ds + row * H + c0, d);
+  }
+  // the RPW row groups of the warp hold partials for the same columns: fold them, then the eight warps through shared memory
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) { pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], o); pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], o); }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s_dg[warp][c0 + i] = pg[i]; s_db[warp][c0 + i] = pb[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += s_dg[w][c]; bsum += s_db[w][c]; }
+    atomicAdd(dg + c, a);
+    atomicAdd(db + c, bsum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Attention backward for one (sequence, head), scores recomputed from Q, K and the saved row log-sum-exp:
 //   P = exp(Q K^T c - lse),  dP = dO V^T,  D_i = dO_i . O_i,  dS = P (dP - D) c,  dQ = dS K,  dK = dS^T Q,  dV = P^T dO.
 // Pass 1 (one thread per query row): dQ and D.  Pass 2 (one thread per key row): dK and / or dV, no atomics.
@@ -732,6 +865,8 @@ __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict_
 // Chain rule through the collapse Wc[h,j] = sum_{c,i} tok_w[h, c*n_out + (j-i)] conv_w[c,i],  bc[h] = tok_b[h] + sum tok_w conv_b:
 //   d tok_w[h, c*n_out+k] = sum_i dWc[h,k+i] conv_w[c,i] + dbc[h] conv_b[c];   d conv_w[c,i] = sum_{h,k} dWc[h,k+i] tok_w[h,c*n_out+k];
 //   d conv_b[c] = sum_h dbc[h] sum_k tok_w[h,c*n_out+k];   d tok_b = dbc.
+// Work items: one THREAD per element of d tok_w and d tok_b, one WARP per element of d conv_w / d conv_b (sums over H * n_out terms: as single
+// threads those 24 elements were a 225 us serial tail).  Launch with at least n_tok + H + 32 * (C * kw + C) threads.
 __global__ void front_chain_bwd_kernel(const float* __restrict__ dWc, const float* __restrict__ dbc, const float* __restrict__ tok_w,
                                        const float* __restrict__ conv_w, const float* __restrict__ conv_b, int H, int C, int kw, int n_out, int n_proc,
                                        float* __restrict__ g_tok_w, float* __restrict__ g_tok_b, float* __restrict__ g_conv_w, float* __restrict__ g_conv_b) {
@@ -742,23 +877,34 @@ __global__ void front_chain_bwd_kernel(const float* __restrict__ dWc, const floa
     float a = dbc[h] * conv_b[c];
     for (int i = 0; i < kw; ++i) a = fmaf(dWc[h * n_proc + k + i], conv_w[c * kw + i], a);
     g_tok_w[idx] += a;
-  } else if (idx < n_tok + H) {
+    return;
+  }
+  if (idx < n_tok + H) {
     g_tok_b[idx - n_tok] += dbc[idx - n_tok];
-  } else if (idx < n_tok + H + C * kw) {
-    const int e = idx - n_tok - H, c = e / kw, i = e % kw;
-    float a = 0.f;
-    for (int h = 0; h < H; ++h)
-      for (int k = 0; k < n_out; ++k) a = fmaf(dWc[h * n_proc + k + i], tok_w[(long long)h * C * n_out + c * n_out + k], a);
-    g_conv_w[e] += a;
-  } else if (idx < n_tok + H + C * kw + C) {
-    const int c = idx - n_tok - H - C * kw;
-    float a = 0.f;
-    for (int h = 0; h < H; ++h) {
-      float t = 0.f;
-      for (int k = 0; k < n_out; ++k) t += tok_w[(long long)h * C * n_out + c * n_out + k];
-      a = fmaf(dbc[h], t, a);
+    return;
+  }
+  // warp items (n_tok + H is a multiple of 32 whenever H is, so whole warps arrive here together; the shuffles below need that)
+  const int item = (idx - n_tok - H) >> 5, lane = threadIdx.x & 31;
+  if (item >= C * kw + C) return;
+  float a = 0.f;
+  if (item < C * kw) {
+    const int c = item / kw, i = item % kw;
+    for (int t = lane; t < H * n_out; t += 32) {
+      const int h = t / n_out, k = t % n_out;
+      a = fmaf(dWc[h * n_proc + k + i], tok_w[(long long)h * C * n_out + c * n_out + k], a);
     }
-    g_conv_b[c] += a;
+  } else {
+    const int c = item - C * kw;
+    for (int t = lane; t < H * n_out; t += 32) {
+      const int h = t / n_out, k = t % n_out;
+      a = fmaf(dbc[h], tok_w[(long long)h * C * n_out + c * n_out + k], a);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) {
+    if (item < C * kw) g_conv_w[item] += a;
+    else g_conv_b[item - C * kw] += a;
   }
 }
 
