@@ -15,6 +15,7 @@
 #include "tc_train_gemm.cuh"
 #include "tc_train_dw.cuh"
 
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <vector>
 
@@ -80,29 +81,41 @@ static bool tgemm_ok(const float* A, int lda, const float* W, int ldw, bool w_kn
   return train_tc_enabled() && (K == 64 || K == 128) && N % 16 == 0 && N >= 16 && N * (K / 8) <= 2048 && lda % 4 == 0 && ldc % 4 == 0 && (w_kn || ldw % 4 == 0) && al(A) && al(W) &&
          al(C) && (!mask || (ldm % 4 == 0 && al(mask))) && tc::tgemm_smem(K / 64, N) <= 113 * 1024;
 }
-// stage height and CTAs per SM of the tcgen05 weight-gradient kernel: 32-row stages and three CTAs per SM when they fit (shared memory, 512 TMEM columns)
-static void tdw_plan(int N, int K, int* rows, int* minb, int* tmem_cols) {
-  const int G = ((N + 63) / 64 + 1) / 2, need = G * (K + 32);
-  *tmem_cols = need <= 128 ? 128 : 256;
-  const char* e = getenv("HFT_TRAIN_DW_ROWS");                          // experiment switch: 64 = the two-CTA, 64-row-stage variant where it fits
-  const bool want64 = e && atoi(e) == 64;
-  if (want64 && tc::tdw_smem(K / 64, N, 64) <= 113 * 1024) { *rows = 64; *minb = 2; return; }
-  *rows = 32;
-  *minb = (*tmem_cols == 128 && tc::tdw_smem(K / 64, N, 32) <= 75 * 1024) ? 3 : 2;
+static int tdw_raw_stages(int N, int K) {                         // raw-ring depth of the tcgen05 weight-gradient kernel: what fits one CTA per SM, at most 8
+  const long long room = 220 * 1024 - (long long)tc::tdw_smem(K / 64, N, 2, 0);
+  const long long n = room / (long long)tc::tdw_raw_bytes(K / 64, N);
+  return (int)(n > 8 ? 8 : n);
 }
-// The tcgen05 weight-gradient kernel is correct (tests/test_gpu_train_linear.py) but, measured, only level with the fp32 CUDA-core kernel
-// (both ~1.7-2.0 TB/s of their operands: the single-buffered stage chain load -> convert -> MMA is latency-bound), so the training step keeps
-// dw_gemm_kernel unless HFT_TRAIN_TC_DW=1; hft_train_linear_wgrad(use_tc = 1) always runs it.
+// HFT_TRAIN_TC_DW=0: keep the fp32 CUDA-core weight-gradient kernel (experiment switch); hft_train_linear_wgrad(use_tc) forces either.
+// 2-D row-major fp32 tensor [rows, cols] with row pitch ld (floats), box = box_cols x box_rows, no swizzle (the raw operand stages of tdw_kernel)
+static int make_map_f32(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+  }
+  HFT_REQUIRE(enc != nullptr, HFT_ERR_STATE, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HFT_REQUIRE(r == CUDA_SUCCESS, HFT_ERR_STATE, "cuTensorMapEncodeTiled (fp32) failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows);
+  return HFT_OK;
+}
 static bool tdw_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC_DW"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("HFT_TRAIN_TC_DW"); v = (e && e[0] == '0') ? 0 : 1; }
   return g_train_tc_force >= 0 ? g_train_tc_force == 1 : (v == 1 && train_tc_enabled());
 }
 static bool tdw_ok(const float* dY, int ldy, const float* X, int ldx, int N, int K) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int G = ((N + 63) / 64 + 1) / 2;
-  return tdw_enabled() && (K == 64 || K == 128) && N % 8 == 0 && N >= 8 && N + K <= 256 && G * (K + 32) <= 256 && ldy % 4 == 0 && ldx % 4 == 0 && al(dY) && al(X) &&
-         tc::tdw_smem(K / 64, N, 32) <= 113 * 1024;
+  return tdw_enabled() && (K == 64 || K == 128) && N % 8 == 0 && N >= 8 && N + K <= 256 && G * (64 + 3 * K) <= 512 && ldy % 4 == 0 && ldx % 4 == 0 && al(dY) && al(X) &&
+         tdw_raw_stages(N, K) >= 2;
 }
 static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a) {
   static const int sms = num_sms();
@@ -164,25 +177,27 @@ static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int
     static const int sms_tc = num_sms();
     tc::TDwArgs a{};
     a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.dW = dW; a.ldw = ldw; a.db = db; a.M = M; a.N = N; a.K = K;
-    int R, minb;
-    tdw_plan(N, K, &R, &minb, &a.tmem_cols);
-    long long ctas = (long long)minb * sms_tc;                     // every resident slot one CTA, at least four stages each
-    if (ctas > (M + 4 * R - 1) / (4 * R)) ctas = (M + 4 * R - 1) / (4 * R);
-    a.rows_per_cta = ((M + ctas - 1) / ctas + R - 1) / R * R;
+    CUtensorMap map_y, map_x;
+    HFT_TRY(make_map_f32(&map_y, dY, M, N, ldy, N, tc::kDwRows));
+    HFT_TRY(make_map_f32(&map_x, X, M, K, ldx, K, tc::kDwRows));
+    a.n_slots = 2;
+    a.n_raw = tdw_raw_stages(N, K);
+    if (const char* e = getenv("HFT_DW_NR")) { int v = atoi(e); if (v >= 1 && v <= a.n_raw) a.n_raw = v; }   // experiment switch: shallower raw ring
+    long long ctas = sms_tc;                                        // one persistent CTA per SM, at least four 32-row stages each
+    if (ctas > (M + 4 * tc::kDwRows - 1) / (4 * tc::kDwRows)) ctas = (M + 4 * tc::kDwRows - 1) / (4 * tc::kDwRows);
+    a.rows_per_cta = ((M + ctas - 1) / ctas + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
     ctas = (M + a.rows_per_cta - 1) / a.rows_per_cta;
-    const size_t smem = tc::tdw_smem(K / 64, N, R);
+    const size_t smem = tc::tdw_smem(K / 64, N, a.n_slots, a.n_raw);
+    const int tps = (N + K + 127) / 128;                              // 8-float chunks per producer thread and stage (1 or 2)
     LaunchScope ls(HFT_KCLASS_GEMM, s);
-#define HFT_TDW_LAUNCH(KBv, Rv, Bv)                                                                   \
+#define HFT_TDW_LAUNCH(KBv, Tv)                                                                       \
   do {                                                                                                \
-    HFT_SET_MAX_SMEM((tc::tdw_kernel<KBv, Rv, Bv>), 113 * 1024);                                      \
-    tc::tdw_kernel<KBv, Rv, Bv><<<(unsigned)ctas, tc::kDwThreads, smem, s>>>(a);                      \
+    HFT_SET_MAX_SMEM((tc::tdw_kernel<KBv, Tv>), 220 * 1024);                                          \
+    tc::tdw_kernel<KBv, Tv><<<(unsigned)ctas, tc::kDwThreads, smem, s>>>(map_y, map_x, a);                          \
   } while (0)
-    if (K == 64 && R == 64) HFT_TDW_LAUNCH(1, 64, 2);
-    else if (K == 64 && minb == 3) HFT_TDW_LAUNCH(1, 32, 3);
-    else if (K == 64) HFT_TDW_LAUNCH(1, 32, 2);
-    else if (R == 64) HFT_TDW_LAUNCH(2, 64, 2);
-    else if (minb == 3) HFT_TDW_LAUNCH(2, 32, 3);
-    else HFT_TDW_LAUNCH(2, 32, 2);
+    if (K == 64 && tps == 1) HFT_TDW_LAUNCH(1, 1);
+    else if (K == 64) HFT_TDW_LAUNCH(1, 2);
+    else HFT_TDW_LAUNCH(2, 2);
 #undef HFT_TDW_LAUNCH
     return HFT_OK;
   }
