@@ -30,6 +30,7 @@ struct TGemmArgs {
   long long M; int N, K;
   int relu, accum;             // C = relu(.) ; C += .
   const float* mask; int ldm; float mask_scale;   // C = mask > 0 ? . * mask_scale : 0   (before the accumulate)
+  int tmem_cols;               // power of two >= N (32..256)
 };
 
 constexpr int kGThreads = 256;
@@ -39,8 +40,10 @@ __device__ __forceinline__ float pow2_inv_of(float mx) {       // power of two s
   return (e == 0u || e >= 253u) ? 1.f : __uint_as_float((254u - e) << 23);
 }
 
-template <int KB>   // K / 64
-__global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) {
+// KB = K / 64; MINB = CTAs per SM the register budget is cut for (3 for the narrow shapes, whose tiles are too small to hide the
+// per-tile load -> convert -> MMA -> epilogue chain with two CTAs)
+template <int KB, int MINB>
+__global__ void __launch_bounds__(kGThreads, MINB) tgemm_kernel(const TGemmArgs p) {
   constexpr int CH = KB * 8;                 // 8-element chunks per row
   constexpr int TASKS = 128 * CH / kGThreads;   // chunks per thread per tile
   constexpr int A_PART = KB * 128 * 128;     // bytes of one part (hi or lo) of the A tile
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   const int N = p.N;
 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
 
   // ---- W rows (output features) -> per-row power-of-two scale -> hi | lo tiles; every thread loads all its chunks before converting ----
   {
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tgemm_kernel(const TGemmArgs p) 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 inline size_t tgemm_smem(int KB, int N) { return 1024 + 2 * (size_t)KB * 128 * 128 + 2 * (size_t)KB * N * 128 + (256 + 256 + 128) * sizeof(float) + 64; }

@@ -117,19 +117,29 @@ static bool tdw_ok(const float* dY, int ldy, const float* X, int ldx, int N, int
   return tdw_enabled() && (K == 64 || K == 128) && N % 8 == 0 && N >= 8 && N + K <= 256 && G * (64 + 3 * K) <= 512 && ldy % 4 == 0 && ldx % 4 == 0 && al(dY) && al(X) &&
          tdw_raw_stages(N, K) >= 2;
 }
-static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a) {
+static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a0) {
   static const int sms = num_sms();
-  const long long tiles = (a.M + 127) / 128;
-  const unsigned grid = (unsigned)(tiles < 2LL * sms ? tiles : 2LL * sms);
+  tc::TGemmArgs a = a0;
+  a.tmem_cols = a.N <= 32 ? 32 : a.N <= 64 ? 64 : a.N <= 128 ? 128 : 256;
   const size_t smem = tc::tgemm_smem(a.K / 64, a.N);
+  // two CTAs per SM; HFT_TRAIN_GEMM_CTAS=3 cuts the register budget for three where shared memory (<= 75 KB each) and TMEM (<= 128 columns each)
+  // allow it (experiment switch: measured slower, 46.5 against 41.2 us for [262144, 64] x [64, 64] -- the 85-register budget spills)
+  static int max_b = -1;
+  if (max_b < 0) { const char* e = getenv("HFT_TRAIN_GEMM_CTAS"); max_b = (e && atoi(e) == 3) ? 3 : 2; }
+  const int minb = (max_b == 3 && smem <= 75 * 1024 && a.tmem_cols <= 128) ? 3 : 2;
+  const long long tiles = (a.M + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < (long long)minb * sms ? tiles : (long long)minb * sms);
   LaunchScope ls(HFT_KCLASS_GEMM, s);
-  if (a.K == 64) {
-    HFT_SET_MAX_SMEM(tc::tgemm_kernel<1>, 113 * 1024);
-    tc::tgemm_kernel<1><<<grid, tc::kGThreads, smem, s>>>(a);
-  } else {
-    HFT_SET_MAX_SMEM(tc::tgemm_kernel<2>, 113 * 1024);
-    tc::tgemm_kernel<2><<<grid, tc::kGThreads, smem, s>>>(a);
-  }
+#define HFT_TGEMM_LAUNCH(KBv, Bv)                                                  \
+  do {                                                                             \
+    HFT_SET_MAX_SMEM((tc::tgemm_kernel<KBv, Bv>), 113 * 1024);                     \
+    tc::tgemm_kernel<KBv, Bv><<<grid, tc::kGThreads, smem, s>>>(a);                \
+  } while (0)
+  if (a.K == 64 && minb == 3) HFT_TGEMM_LAUNCH(1, 3);
+  else if (a.K == 64) HFT_TGEMM_LAUNCH(1, 2);
+  else if (minb == 3) HFT_TGEMM_LAUNCH(2, 3);
+  else HFT_TGEMM_LAUNCH(2, 2);
+#undef HFT_TGEMM_LAUNCH
   return HFT_OK;
 }
 
