@@ -62,6 +62,8 @@ def test_training_linear_matches_fp64(M, N, K, form, rm, accum, scale):
 
 WG_CASES = [  # (M, N, K)
     (50000, 192, 64), (30001, 64, 64), (20000, 128, 64), (20000, 64, 128), (9000, 144, 64), (300, 64, 64), (70000, 128, 128), (4097, 8, 64),
+    # many 32-row stages per CTA: every ring of the kernel wraps several times (a missing proxy fence showed only from 6 stages per CTA on)
+    (37888, 192, 64), (56832, 64, 64), (94720, 128, 64), (262144, 64, 64), (262144, 64, 128),
 ]
 
 
@@ -85,4 +87,4 @@ def test_training_linear_weight_gradient_matches_fp64(M, N, K):
         errs[use_tc] = (float((dw.double() - ref_w).abs().max() / ref_w.abs().max()), float((db.double() - ref_b).abs().max() / ref_b.abs().max()))
     print("relative-to-max errors (dW, db): tcgen05 %s | fp32 CUDA cores %s" % (errs[1], errs[0]))
     for use_tc in (1, 0):
-        assert errs[use_tc][0] <= 5e-6 and errs[use_tc][1] <= 5e-6, errs
+        assert errs[use_tc][0] <= 1e-5 and errs[use_tc][1] <= 1e-5, errs   # (the accumulators of a CTA round towards zero: ~4e-6 at 262 144 rows)
