@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(128, NKEY, BF16, false, false);   // S = Q K^T, both K-major
       const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);      // O = P V, A from TMEM, B = V MN-major
+      const SDescBase kds = sdesc_base(16, kAtom, kSwz128), kdv = sdesc_base(kAtom, kAtom, kSwz128);   // one add per descriptor in the loops below
       int slot = 0;
       uint32_t ph = 0, qph[2] = {0, 0}, pph[2] = {0, 0};
       auto take = [&]() -> int {
@@ -176,9 +177,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         const int n_prod = (X3 && !p.s_single) ? 3 : 1;
         for (int part = 0; part < n_prod; ++part) {
           const uint32_t qp = qa + (part == 1 ? L::tile_bytes : 0), kp = ka + (part == 2 ? L::tile_bytes : 0);
+          const uint32_t q0 = sdesc_lo(kds, qp), k0 = sdesc_lo(kds, kp);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) {
-            umma_f16(tmem_base + w * 256, make_sdesc(qp + k * 32, 16, kAtom, kSwz128), make_sdesc(kp + k * 32, 16, kAtom, kSwz128), idesc_s, acc);
+            umma_f16_lohi(tmem_base + w * 256, q0 + 2 * k, kds.hi, k0 + 2 * k, kds.hi, idesc_s, acc);
             acc = 1;
           }
         }
@@ -189,12 +191,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         uint32_t acc = 0;
         const int n_prod = (X3 && !p.pv_single) ? 3 : 1;
         for (int part = 0; part < n_prod; ++part) {
-          const uint32_t vp = va + (part == 2 ? L::tile_bytes : 0);
+          const uint32_t v0 = sdesc_lo(kdv, va + (part == 2 ? L::tile_bytes : 0));
 #pragma unroll
           for (int k = 0; k < NKEY / 16; ++k) {
             // P columns: x3 [hi 16 | lo 16] per 32 keys; single product 8 columns per 16 keys
             const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
-            umma_f16_ts(tp + ocol, tp + pcol, make_sdesc(vp + k * 16 * kRowBytes, kAtom, kAtom, kSwz128), idesc_o, acc);
+            umma_f16_ts_lohi(tp + ocol, tp + pcol, v0 + k * (16 * kRowBytes / 16), kdv.hi, idesc_o, acc);
             acc = 1;
           }
         }
@@ -472,6 +474,7 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(128, LK, BF16, false, false);
       const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);
+      const SDescBase kds2 = sdesc_base(16, kAtom, kSwz128), kdv2 = sdesc_base(kAtom, kAtom, kSwz128);
       int slot = 0;
       uint32_t ph = 0, qph = 0, pph = 0, dph = 0;
       auto take = [&]() -> int {
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
           const uint32_t qp = qa + (part == 1 ? 128 * 64 * 2 : 0), kp = ka + (part == 2 ? L::kv_part : 0);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) {
-            umma_f16(tmem_base, make_sdesc(qp + k * 32, 16, kAtom, kSwz128), make_sdesc(kp + k * 32, 16, kAtom, kSwz128), idesc_s, acc);
+            umma_f16_lohi(tmem_base, sdesc_lo(kds2, qp) + 2 * k, kds2.hi, sdesc_lo(kds2, kp) + 2 * k, kds2.hi, idesc_s, acc);
             acc = 1;
           }
         }
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
 #pragma unroll
           for (int k = 0; k < LK / 16; ++k) {
             const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
-            umma_f16_ts(tmem_base + kOCol, tmem_base + pcol, make_sdesc(vp + k * 16 * kRowBytes, kAtom, kAtom, kSwz128), idesc_o, acc);
+            umma_f16_ts_lohi(tmem_base + kOCol, tmem_base + pcol, sdesc_lo(kdv2, vp) + k * (16 * kRowBytes / 16), kdv2.hi, idesc_o, acc);
             acc = 1;
           }
         }

@@ -94,6 +94,43 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_2cta_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_2cta_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // busy-polling wait (no suspend hint): for a thread whose only job is to react to the barrier, e.g. an MMA issuer
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -131,6 +168,13 @@ constexpr uint32_t kSwz128 = 2, kSwz64 = 4, kSwz32 = 6;
 // the descriptor of the same layout `byte_off` bytes further on (byte_off % 16 == 0; shared-memory addresses >> 4 fit the 14-bit field, so no carry
 // leaves it): lets an MMA-issuing thread build its descriptors with one add each from a few bases made outside the loop
 __device__ __forceinline__ uint64_t sdesc_advance(uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); }
+// the two halves of the descriptor of byte address 0 in a layout; a tile's descriptor is then {lo | (address >> 4), hi}
+struct SDescBase { uint32_t lo, hi; };
+__device__ __forceinline__ SDescBase sdesc_base(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+  const uint64_t d = make_sdesc(0u, lbo_bytes, sbo_bytes, swizzle);
+  return SDescBase{(uint32_t)d, (uint32_t)(d >> 32)};
+}
+__device__ __forceinline__ uint32_t sdesc_lo(const SDescBase& b, uint32_t smem_addr) { return b.lo | ((smem_addr & 0x3FFFFu) >> 4); }
 
 // ---- TMA ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -166,10 +166,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         if (++slot == kFfnSlots) { slot = 0; ph ^= 1; }
         return s;
       };
+      const SDescBase kd = sdesc_base(16, 1024, kSwz128);              // the issuing thread pays one add per descriptor (K step = 32 bytes = +2)
       auto ss4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id, uint32_t& acc) {   // 64 K elements: 4 K-steps, both operands in smem
+        const uint32_t a0 = sdesc_lo(kd, a_addr), b0 = sdesc_lo(kd, b_addr);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          umma_f16_2cta(d, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(b_addr + k * 32, 16, 1024, kSwz128), id, acc);
+          umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, acc);
           acc = 1;
         }
       };
@@ -180,23 +182,23 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         const uint32_t tp = tmem_base + kSCol + b * 128;
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           const int sh = take();
-          const uint32_t wh = smem_u32(s_ring + (size_t)sh * kFfnSlot);
+          const uint32_t wh = sdesc_lo(kd, smem_u32(s_ring + (size_t)sh * kFfnSlot));
           for (int part = 0; part < wparts; ++part)                      // Ph W2h, Pl W2h
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int ks = kc2 * 4 + k;
               const uint32_t pcol = p.x3 ? (uint32_t)((ks >> 1) * 32 + part * 16 + (ks & 1) * 8) : (uint32_t)(ks * 8);
-              umma_f16_ts_2cta(tmem_base + kYCol, tp + pcol, make_sdesc(wh + k * 32, 16, 1024, kSwz128), id2, 1u);
+              umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wh + 2 * k, kd.hi, id2, 1u);
             }
           umma_commit_2cta(&rempty[sh]);
           if (x3p) {
             const int sl = take();
-            const uint32_t wl = smem_u32(s_ring + (size_t)sl * kFfnSlot);
+            const uint32_t wl = sdesc_lo(kd, smem_u32(s_ring + (size_t)sl * kFfnSlot));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                                 // Ph W2l
               const int ks = kc2 * 4 + k;
               const uint32_t pcol = (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
-              umma_f16_ts_2cta(tmem_base + kYCol, tp + pcol, make_sdesc(wl + k * 32, 16, 1024, kSwz128), id2, 1u);
+              umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wl + 2 * k, kd.hi, id2, 1u);
             }
             umma_commit_2cta(&rempty[sl]);
           }

@@ -105,10 +105,12 @@ __global__ void __launch_bounds__(kFrontThreads, 1) front_tc_kernel(const __grid
         const uint32_t d = tmem_base + ab * 256;
         const uint32_t ah = smem_u32(sm.a[ab][0]), al = smem_u32(sm.a[ab][1]);
         uint32_t acc = 0;
+        const SDescBase kd = sdesc_base(16, 1024, kSwz128);
         auto mma4 = [&](uint32_t a_addr, uint32_t b_addr) {
+          const uint32_t a0 = sdesc_lo(kd, a_addr), b0 = sdesc_lo(kd, b_addr);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16(d, make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), make_sdesc(b_addr + k * 32, 16, 1024, kSwz128), idesc, acc);
+            umma_f16_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, idesc, acc);
             acc = 1;
           }
         };

@@ -207,11 +207,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       uint32_t pa = 0, pw = 0;
       int it = 0;
       uint32_t first = 1;
+      const SDescBase kd = sdesc_base(16, 1024, kSwz128);              // the issuing thread pays one add per descriptor (K step = 32 bytes = +2)
       auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id) {
+        const uint32_t a0 = sdesc_lo(kd, a_addr), b0 = sdesc_lo(kd, b_addr);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024, kSwz128), db = make_sdesc(b_addr + k * 32, 16, 1024, kSwz128);
-          if (PAIR) umma_f16_2cta(d, da, db, id, first ? 0u : 1u); else umma_f16(d, da, db, id, first ? 0u : 1u);
+          if (PAIR) umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, first ? 0u : 1u);
+          else umma_f16_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, first ? 0u : 1u);
           first = 0;
         }
       };
