@@ -81,10 +81,24 @@ static bool tgemm_ok(const float* A, int lda, const float* W, int ldw, bool w_kn
   return train_tc_enabled() && (K == 64 || K == 128) && N % 16 == 0 && N >= 16 && N * (K / 8) <= 2048 && lda % 4 == 0 && ldc % 4 == 0 && (w_kn || ldw % 4 == 0) && al(A) && al(W) &&
          al(C) && (!mask || (ldm % 4 == 0 && al(mask))) && tc::tgemm_smem(K / 64, N) <= 113 * 1024;
 }
-static int tdw_raw_stages(int N, int K) {                         // raw-ring depth of the tcgen05 weight-gradient kernel: what fits one CTA per SM, at most 8
-  const long long room = 220 * 1024 - (long long)tc::tdw_smem(K / 64, N, 2, 0);
-  const long long n = room / (long long)tc::tdw_raw_bytes(K / 64, N);
-  return (int)(n > 8 ? 8 : n);
+// ring depths of the tcgen05 weight-gradient kernel (one CTA per SM, 220 KB of shared memory): operand slots first (HFT_DW_NS, default 2),
+// the raw fp32 ring takes what is left, at most 8 stages (HFT_DW_NR caps it)
+static int tdw_op_slots() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HFT_DW_NS"); v = e ? atoi(e) : 2; if (v < 2 || v > 4) v = 2; }
+  return v;
+}
+static int tdw_raw_stages(int N, int K, int n_slots) {
+  const long long room = 220 * 1024 - (long long)tc::tdw_smem(K / 64, N, n_slots, 0);
+  long long n = room / (long long)tc::tdw_raw_bytes(K / 64, N);
+  if (n > 8) n = 8;
+  if (const char* e = getenv("HFT_DW_NR")) { int v = atoi(e); if (v >= 1 && v < n) n = v; }
+  return (int)n;
+}
+static void tdw_rings(int N, int K, int* n_slots, int* n_raw) {
+  *n_slots = tdw_op_slots();
+  while (*n_slots > 2 && tdw_raw_stages(N, K, *n_slots) < 3) --*n_slots;
+  *n_raw = tdw_raw_stages(N, K, *n_slots);
 }
 // HFT_TRAIN_TC_DW=0: keep the fp32 CUDA-core weight-gradient kernel (experiment switch); hft_train_linear_wgrad(use_tc) forces either.
 // 2-D row-major fp32 tensor [rows, cols] with row pitch ld (floats), box = box_cols x box_rows, no swizzle (the raw operand stages of tdw_kernel)
@@ -115,7 +129,7 @@ static bool tdw_ok(const float* dY, int ldy, const float* X, int ldx, int N, int
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int G = ((N + 63) / 64 + 1) / 2;
   return tdw_enabled() && (K == 64 || K == 128) && N % 8 == 0 && N >= 8 && N + K <= 256 && G * (64 + 3 * K) <= 512 && ldy % 4 == 0 && ldx % 4 == 0 && al(dY) && al(X) &&
-         tdw_raw_stages(N, K) >= 2;
+         tdw_raw_stages(N, K, 2) >= 2;
 }
 static int tgemm_launch(cudaStream_t s, const tc::TGemmArgs& a0) {
   static const int sms = num_sms();
@@ -190,9 +204,7 @@ static int gemm_dw(cudaStream_t s, const float* dY, int ldy, const float* X, int
     CUtensorMap map_y, map_x;
     HFT_TRY(make_map_f32(&map_y, dY, M, N, ldy, N, tc::kDwRows));
     HFT_TRY(make_map_f32(&map_x, X, M, K, ldx, K, tc::kDwRows));
-    a.n_slots = 2;
-    a.n_raw = tdw_raw_stages(N, K);
-    if (const char* e = getenv("HFT_DW_NR")) { int v = atoi(e); if (v >= 1 && v <= a.n_raw) a.n_raw = v; }   // experiment switch: shallower raw ring
+    tdw_rings(N, K, &a.n_slots, &a.n_raw);
     long long ctas = sms_tc;                                        // one persistent CTA per SM, at least four 32-row stages each
     if (ctas > (M + 4 * tc::kDwRows - 1) / (4 * tc::kDwRows)) ctas = (M + 4 * tc::kDwRows - 1) / (4 * tc::kDwRows);
     a.rows_per_cta = ((M + ctas - 1) / ctas + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
