@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {                                                       // the whole warp runs the loop (uniform control flow); one elected lane issues MMAs and commits
       const uint32_t idesc_s = make_idesc(128, NKEY, BF16, false, false);   // S = Q K^T, both K-major
       const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);      // O = P V, A from TMEM, B = V MN-major
       const SDescBase kds = sdesc_base(16, kAtom, kSwz128), kdv = sdesc_base(kAtom, kAtom, kSwz128);   // one add per descriptor in the loops below
+      auto commit = [&](uint64_t* bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
       int slot = 0;
       uint32_t ph = 0, qph[2] = {0, 0}, pph[2] = {0, 0};
       auto take = [&]() -> int {
@@ -173,33 +174,39 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
       };
       auto issue_s = [&](int w, int kslot) {                                // S(w)[128, NKEY] = Q(w) K^T;  x3: Qh Kh + Ql Kh + Qh Kl
         const uint32_t qa = smem_u32(s_q + (size_t)w * L::q_bytes), ka = smem_u32(s_ring + (size_t)kslot * L::slot_bytes);
-        uint32_t acc = 0;
         const int n_prod = (X3 && !p.s_single) ? 3 : 1;
-        for (int part = 0; part < n_prod; ++part) {
-          const uint32_t qp = qa + (part == 1 ? L::tile_bytes : 0), kp = ka + (part == 2 ? L::tile_bytes : 0);
-          const uint32_t q0 = sdesc_lo(kds, qp), k0 = sdesc_lo(kds, kp);
+        if (elect_one()) {
+          uint32_t acc = 0;
+          for (int part = 0; part < n_prod; ++part) {
+            const uint32_t qp = qa + (part == 1 ? L::tile_bytes : 0), kp = ka + (part == 2 ? L::tile_bytes : 0);
+            const uint32_t q0 = sdesc_lo(kds, qp), k0 = sdesc_lo(kds, kp);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            umma_f16_lohi(tmem_base + w * 256, q0 + 2 * k, kds.hi, k0 + 2 * k, kds.hi, idesc_s, acc);
-            acc = 1;
+            for (int k = 0; k < DH / 16; ++k) {
+              umma_f16_lohi(tmem_base + w * 256, q0 + 2 * k, kds.hi, k0 + 2 * k, kds.hi, idesc_s, acc);
+              acc = 1;
+            }
           }
         }
+        __syncwarp();
       };
       auto issue_pv = [&](int w, uint32_t ocol, int vslot) {                // O_u(w)[128, dh] = P V;  x3: Ph Vh + Pl Vh + Ph Vl
         const uint32_t va = smem_u32(s_ring + (size_t)vslot * L::slot_bytes);
         const uint32_t tp = tmem_base + w * 256;
-        uint32_t acc = 0;
         const int n_prod = (X3 && !p.pv_single) ? 3 : 1;
-        for (int part = 0; part < n_prod; ++part) {
-          const uint32_t v0 = sdesc_lo(kdv, va + (part == 2 ? L::tile_bytes : 0));
+        if (elect_one()) {
+          uint32_t acc = 0;
+          for (int part = 0; part < n_prod; ++part) {
+            const uint32_t v0 = sdesc_lo(kdv, va + (part == 2 ? L::tile_bytes : 0));
 #pragma unroll
-          for (int k = 0; k < NKEY / 16; ++k) {
-            // P columns: x3 [hi 16 | lo 16] per 32 keys; single product 8 columns per 16 keys
-            const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
-            umma_f16_ts_lohi(tp + ocol, tp + pcol, v0 + k * (16 * kRowBytes / 16), kdv.hi, idesc_o, acc);
-            acc = 1;
+            for (int k = 0; k < NKEY / 16; ++k) {
+              // P columns: x3 [hi 16 | lo 16] per 32 keys; single product 8 columns per 16 keys
+              const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
+              umma_f16_ts_lohi(tp + ocol, tp + pcol, v0 + k * (16 * kRowBytes / 16), kdv.hi, idesc_o, acc);
+              acc = 1;
+            }
           }
         }
+        __syncwarp();
       };
       int prev[2] = {-1, -1};
       int held_v = 0, held_k = 0;
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         mbar_wait(&p_ready[w], pph[w]); pph[w] ^= 1;
         fence_after_sync();
         issue_pv(w, NH == 2 ? kOCol + 64 : kOCol, held_v);
-        umma_commit(&o_ready[w]);
-        if (!shared || w == 1) umma_commit(&ring_empty[held_v]);
+        commit(&o_ready[w]);
+        if (!shared || w == 1) commit(&ring_empty[held_v]);
       };
       for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
         int tile[2] = {2 * round, 2 * round + 1 < p.n_items ? 2 * round + 1 : -1};
@@ -220,9 +227,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
             mbar_wait(&q_full[w], qph[w]); qph[w] ^= 1;
             fence_after_sync();
             issue_s(w, held_k);
-            umma_commit(&s_ready[w]);
-            if (NH == 1) umma_commit(&q_empty[w]);
-            if (!shared || w == 1) umma_commit(&ring_empty[held_k]);
+            commit(&s_ready[w]);
+            if (NH == 1) commit(&q_empty[w]);
+            if (!shared || w == 1) commit(&ring_empty[held_k]);
           }
         }
         if (NH == 2) {
@@ -233,9 +240,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
             fence_after_sync();
             issue_pv(w, kOCol, held_v);
             issue_s(w, held_k);                                              // overwrites P_a: the MMA pipe runs in issue order
-            umma_commit(&s_ready[w]);
-            umma_commit(&q_empty[w]);
-            if (!shared || w == 1) { umma_commit(&ring_empty[held_v]); umma_commit(&ring_empty[held_k]); }
+            commit(&s_ready[w]);
+            commit(&q_empty[w]);
+            if (!shared || w == 1) { commit(&ring_empty[held_v]); commit(&ring_empty[held_k]); }
           }
         }
         prev[0] = tile[0]; prev[1] = tile[1];

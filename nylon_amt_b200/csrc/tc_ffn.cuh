@@ -152,7 +152,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && leader) {
+    if (leader) {                                       // whole warp, uniform control flow; one elected lane issues MMAs and commits
       const uint32_t id1 = make_idesc(256, kFfnJB, BF16, false, false);
       const uint32_t id2 = make_idesc(256, kFfnH, BF16, false, false);
       const uint32_t id64 = make_idesc(256, 64, BF16, false, false);
@@ -169,12 +169,15 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
       const SDescBase kd = sdesc_base(16, 1024, kSwz128);              // the issuing thread pays one add per descriptor (K step = 32 bytes = +2)
       auto ss4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id, uint32_t& acc) {   // 64 K elements: 4 K-steps, both operands in smem
         const uint32_t a0 = sdesc_lo(kd, a_addr), b0 = sdesc_lo(kd, b_addr);
+        const uint32_t acc0 = acc;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, acc);
-          acc = 1;
+          for (int k = 0; k < 4; ++k) umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, k ? 1u : acc0);
         }
+        __syncwarp();
+        acc = 1;
       };
+      auto commit = [&](uint64_t* bar) { if (elect_one()) umma_commit_2cta(bar); __syncwarp(); };
       auto gemm2 = [&](int j) {                                          // Y += P_j W2[:, j]^T, A = P_j from TMEM
         const int b = j & 1;
         mbar_wait(&p_ready[b], pph[b]); pph[b] ^= 1;
@@ -183,24 +186,30 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           const int sh = take();
           const uint32_t wh = sdesc_lo(kd, smem_u32(s_ring + (size_t)sh * kFfnSlot));
-          for (int part = 0; part < wparts; ++part)                      // Ph W2h, Pl W2h
+          if (elect_one()) {
+            for (int part = 0; part < wparts; ++part)                    // Ph W2h, Pl W2h
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ks = kc2 * 4 + k;
-              const uint32_t pcol = p.x3 ? (uint32_t)((ks >> 1) * 32 + part * 16 + (ks & 1) * 8) : (uint32_t)(ks * 8);
-              umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wh + 2 * k, kd.hi, id2, 1u);
-            }
-          umma_commit_2cta(&rempty[sh]);
+              for (int k = 0; k < 4; ++k) {
+                const int ks = kc2 * 4 + k;
+                const uint32_t pcol = p.x3 ? (uint32_t)((ks >> 1) * 32 + part * 16 + (ks & 1) * 8) : (uint32_t)(ks * 8);
+                umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wh + 2 * k, kd.hi, id2, 1u);
+              }
+          }
+          __syncwarp();
+          commit(&rempty[sh]);
           if (x3p) {
             const int sl = take();
             const uint32_t wl = sdesc_lo(kd, smem_u32(s_ring + (size_t)sl * kFfnSlot));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                                 // Ph W2l
-              const int ks = kc2 * 4 + k;
-              const uint32_t pcol = (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
-              umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wl + 2 * k, kd.hi, id2, 1u);
+              for (int k = 0; k < 4; ++k) {                               // Ph W2l
+                const int ks = kc2 * 4 + k;
+                const uint32_t pcol = (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
+                umma_f16_ts_2cta_lohi(tmem_base + kYCol, tp + pcol, wl + 2 * k, kd.hi, id2, 1u);
+              }
             }
-            umma_commit_2cta(&rempty[sl]);
+            __syncwarp();
+            commit(&rempty[sl]);
           }
         }
       };
@@ -230,21 +239,21 @@ ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
               ss4(d, smem_u32(s_x + (size_t)kc * kChunkA), wh + h * 8192, id1, acc);                       // xh W1h
               if (x3p) ss4(d, smem_u32(s_x + (size_t)(kFfnKC + kc) * kChunkA), wh + h * 8192, id1, acc);   // xl W1h
             }
-            umma_commit_2cta(&rempty[sh]);
+            commit(&rempty[sh]);
             if (x3p) {
               const int sl = take();
               const uint32_t wl = smem_u32(s_ring + (size_t)sl * kFfnSlot);
               for (int h = 0; h < 2; ++h) ss4(d, smem_u32(s_x + (size_t)(2 * u + h) * kChunkA), wl + h * 8192, id1, acc);   // xh W1l
-              umma_commit_2cta(&rempty[sl]);
+              commit(&rempty[sl]);
             }
           }
-          umma_commit_2cta(&s_ready[j & 1]);
-          if (j == kFfnNJ - 1) umma_commit_2cta(x_empty);                 // x is dead once GEMM1 of the last block has completed
+          commit(&s_ready[j & 1]);
+          if (j == kFfnNJ - 1) commit(x_empty);                 // x is dead once GEMM1 of the last block has completed
           if (j == 1) residual();                                         // after two GEMM1 blocks: the previous tile's epilogue overlaps them
           if (j >= 1) gemm2(j - 1);
         }
         gemm2(kFfnNJ - 1);
-        umma_commit_2cta(y_ready);
+        commit(y_ready);
       }
     }
   } else {

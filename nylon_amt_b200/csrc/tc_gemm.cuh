@@ -197,10 +197,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && leader) {
+    if (leader) {                                       // the whole warp runs the loop (uniform control flow: descriptors stay in uniform registers); one elected lane issues
       const uint32_t idesc = make_idesc(kCtas * kBlockM, n_tile, BF16, false, false);
       const uint32_t idesc64 = make_idesc(kCtas * kBlockM, 64, BF16, false, false);
-      auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_2cta(bar); else umma_commit(bar); };
+      auto commit = [&](uint64_t* bar) { if (elect_one()) { if (PAIR) umma_commit_2cta(bar); else umma_commit(bar); } __syncwarp(); };
       const uint32_t i64_addr = smem_u32(s_i64);
       if (p.w_resident) { mbar_wait(wbar, 0); fence_after_sync(); }
       int sa = 0, sw = 0;
@@ -210,12 +210,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const SDescBase kd = sdesc_base(16, 1024, kSwz128);              // the issuing thread pays one add per descriptor (K step = 32 bytes = +2)
       auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id) {
         const uint32_t a0 = sdesc_lo(kd, a_addr), b0 = sdesc_lo(kd, b_addr);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          if (PAIR) umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, first ? 0u : 1u);
-          else umma_f16_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, first ? 0u : 1u);
-          first = 0;
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (PAIR) umma_f16_2cta_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, k ? 1u : acc0);
+            else umma_f16_lohi(d, a0 + 2 * k, kd.hi, b0 + 2 * k, kd.hi, id, k ? 1u : acc0);
+          }
         }
+        __syncwarp();
+        first = 0;
       };
       auto wait_a = [&]() -> uint32_t {                  // next A-ring slot, filled
         mbar_wait(&full_a[sa], pa);
