@@ -176,38 +176,39 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
 
   const uint32_t idesc_s = make_idesc(128, 128, false, false, false);   // S = Q K^T, both K-major
   const uint32_t idesc_o = make_idesc(128, 32, false, false, true);     // O = P V, A from TMEM, B = V MN-major
-  // base descriptors (hi piece, row 0); every MMA's descriptors are one add away
-  const uint64_t dq = make_sdesc(smem_u32(s_q), 16, kTAtom, kSwz64), dk = make_sdesc(smem_u32(s_k), 16, kTAtom, kSwz64);
-  const uint64_t dv = make_sdesc(smem_u32(s_v), kTAtom, kTAtom, kSwz64);
-  const uint32_t kv_lo = (uint32_t)lkp * 64;
+  // descriptors: constant halves + the low word of a tile (address >> 4); every MMA's descriptors are one 32-bit add away, computed by the whole
+  // (converged) warp 0 so that they live in uniform registers, and the MMAs of a group are issued back to back by one elected lane
+  const SDescBase kdk = sdesc_base(16, kTAtom, kSwz64), kdm = sdesc_base(kTAtom, kTAtom, kSwz64);
+  const uint32_t q_lo16 = sdesc_lo(kdk, smem_u32(s_q)), k_lo16 = sdesc_lo(kdk, smem_u32(s_k)), v_lo16 = sdesc_lo(kdm, smem_u32(s_v));
+  const uint32_t kv_lo = ((uint32_t)lkp * 64) >> 4;      // hi -> lo piece of K / V, in 16-byte units
   auto issue_s = [&](int u) {
-    uint32_t acc = 0;
-    const uint64_t dku = sdesc_advance(dk, u * 128 * 64);
+    const uint32_t ku = k_lo16 + (uint32_t)(u * 128 * 64 >> 4);
+    if (elect_one()) {
 #pragma unroll
-    for (int part = 0; part < 3; ++part) {
-      const uint64_t qp = sdesc_advance(dq, part == 1 ? 128 * 64 : 0), kp = part == 2 ? sdesc_advance(dku, kv_lo) : dku;
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t qp = q_lo16 + (part == 1 ? (128 * 64 >> 4) : 0), kp = ku + (part == 2 ? kv_lo : 0);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        umma_f16(tmem_base, sdesc_advance(qp, k * 32), sdesc_advance(kp, k * 32), idesc_s, acc);
-        acc = 1;
+        for (int k = 0; k < 2; ++k) umma_f16_lohi(tmem_base, qp + 2 * k, kdk.hi, kp + 2 * k, kdk.hi, idesc_s, (part | k) ? 1u : 0u);
       }
     }
+    __syncwarp();
   };
   auto issue_pv = [&](int u) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      uint32_t acc = 0;
-      const uint64_t dvu = sdesc_advance(dv, (u * 128 + h * 64) * 64);
+      const uint32_t vu = v_lo16 + (uint32_t)((u * 128 + h * 64) * 64 >> 4);
+      if (elect_one()) {
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const uint64_t vp = part == 2 ? sdesc_advance(dvu, kv_lo) : dvu;
+        for (int part = 0; part < 3; ++part) {
+          const uint32_t vp = vu + (part == 2 ? kv_lo : 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t pcol = (uint32_t)(h * 64 + (k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
-          umma_f16_ts(tmem_base + 128 + (u * 2 + h) * 32, tmem_base + pcol, sdesc_advance(vp, k * 16 * 64), idesc_o, acc);
-          acc = 1;
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t pcol = (uint32_t)(h * 64 + (k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
+            umma_f16_ts_lohi(tmem_base + 128 + (u * 2 + h) * 32, tmem_base + pcol, vp + k * (16 * 64 >> 4), kdm.hi, idesc_o, (part | k) ? 1u : 0u);
+          }
         }
       }
+      __syncwarp();
     }
   };
 
@@ -218,10 +219,11 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
   const long long drop_row = (((long long)seq * p.heads + head) * p.Lq + qrow) * p.Lk;
 
   for (int u = 0; u < nu; ++u) {
-    if (threadIdx.x == 0) {
+    if (warp == 0) {                                     // whole warp, uniform control flow (descriptors in uniform registers); one elected lane issues
       if (u > 0) issue_pv(u - 1);
       issue_s(u);                                        // overwrites P of the previous unit: the MMA pipe runs in issue order
-      umma_commit(&bars[0]);
+      if (elect_one()) umma_commit(&bars[0]);
+      __syncwarp();
     }
     mbar_wait(&bars[0], u & 1);
     fence_after_sync();
@@ -263,9 +265,10 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_fwd_kernel(const TAttnArgs
     __syncthreads();
     fence_after_sync();
   }
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     issue_pv(nu - 1);
-    umma_commit(&bars[1]);
+    if (elect_one()) umma_commit(&bars[1]);
+    __syncwarp();
   }
   // merge the partial softmaxes of the row: 2 * nu (max, sum) pairs
   float M = -INFINITY;
@@ -411,40 +414,44 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
 
   const uint32_t idesc_1 = make_idesc(128, 64, false, false, false);    // scores: both operands K-major
   const uint32_t idesc_2 = make_idesc(128, 32, false, false, true);     // accumulations: A from TMEM, B MN-major
-  // base descriptors (hi piece, row 0): K-major forms for the score-type products, MN-major forms of the column tensors for the accumulations
-  const uint64_t dxk = make_sdesc(smem_u32(s_x), 16, kTAtom, kSwz64), dyk = make_sdesc(smem_u32(s_y), 16, kTAtom, kSwz64);
-  const uint64_t dcxk = make_sdesc(smem_u32(s_cx), 16, kTAtom, kSwz64), dcyk = make_sdesc(smem_u32(s_cy), 16, kTAtom, kSwz64);
-  const uint64_t dcxm = make_sdesc(smem_u32(s_cx), kTAtom, kTAtom, kSwz64), dcym = make_sdesc(smem_u32(s_cy), kTAtom, kTAtom, kSwz64);
-  const uint32_t lo_r = 128 * 64, lo_c = (uint32_t)lcp * 64;
+  // descriptors: constant halves + the low word of a tile (address >> 4) -- K-major forms for the score-type products, MN-major forms of the
+  // column tensors for the accumulations; computed by the whole (converged) warp 0, the MMAs of a group issued back to back by one elected lane
+  const SDescBase kdk = sdesc_base(16, kTAtom, kSwz64), kdm = sdesc_base(kTAtom, kTAtom, kSwz64);
+  const uint32_t x16 = sdesc_lo(kdk, smem_u32(s_x)), y16 = sdesc_lo(kdk, smem_u32(s_y));
+  const uint32_t cxk16 = sdesc_lo(kdk, smem_u32(s_cx)), cyk16 = sdesc_lo(kdk, smem_u32(s_cy));
+  const uint32_t dcxm = sdesc_lo(kdm, smem_u32(s_cx)), dcym = sdesc_lo(kdm, smem_u32(s_cy));
+  const uint32_t lo_r = (128 * 64) >> 4, lo_c = ((uint32_t)lcp * 64) >> 4;   // hi -> lo piece of a row tile / a column tensor, in 16-byte units
   auto issue_scores = [&](int ch) {                      // T1[128, 64] = X CX_ch^T (columns 0..63), T2 = Y CY_ch^T (columns 64..127)
+    const uint32_t c0 = (uint32_t)(ch * 64 * 64 >> 4);
+    if (elect_one()) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const uint64_t ra = t ? dyk : dxk, ca = sdesc_advance(t ? dcyk : dcxk, ch * 64 * 64);
-      uint32_t acc = 0;
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t ra = t ? y16 : x16, ca = (t ? cyk16 : cxk16) + c0;
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const uint64_t rp = sdesc_advance(ra, part == 1 ? lo_r : 0), cp = part == 2 ? sdesc_advance(ca, lo_c) : ca;
+        for (int part = 0; part < 3; ++part) {
+          const uint32_t rp = ra + (part == 1 ? lo_r : 0), cp = ca + (part == 2 ? lo_c : 0);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          umma_f16(tmem_base + t * 64, sdesc_advance(rp, k * 32), sdesc_advance(cp, k * 32), idesc_1, acc);
-          acc = 1;
+          for (int k = 0; k < 2; ++k) umma_f16_lohi(tmem_base + t * 64, rp + 2 * k, kdk.hi, cp + 2 * k, kdk.hi, idesc_1, (part | k) ? 1u : 0u);
         }
       }
     }
+    __syncwarp();
   };
-  auto issue_accum = [&](int ch, uint32_t dcol, uint32_t acol, uint64_t btile) {   // D[128, 32] (+)= A(TMEM columns acol..) B_ch
-    uint32_t acc = ch > 0 ? 1u : 0u;
-    const uint64_t bch = sdesc_advance(btile, ch * 64 * 64);
+  auto issue_accum = [&](int ch, uint32_t dcol, uint32_t acol, uint32_t btile16) {   // D[128, 32] (+)= A(TMEM columns acol..) B_ch
+    const uint32_t acc0 = ch > 0 ? 1u : 0u;
+    const uint32_t bch = btile16 + (uint32_t)(ch * 64 * 64 >> 4);
+    if (elect_one()) {
 #pragma unroll
-    for (int part = 0; part < 3; ++part) {
-      const uint64_t bp = part == 2 ? sdesc_advance(bch, lo_c) : bch;
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t bp = bch + (part == 2 ? lo_c : 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t pcol = acol + (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
-        umma_f16_ts(tmem_base + dcol, tmem_base + pcol, sdesc_advance(bp, k * 16 * 64), idesc_2, acc);
-        acc = 1;
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t pcol = acol + (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8);
+          umma_f16_ts_lohi(tmem_base + dcol, tmem_base + pcol, bp + k * (16 * 64 >> 4), kdm.hi, idesc_2, (part | k) ? 1u : acc0);
+        }
       }
     }
+    __syncwarp();
   };
 
   const int r = quarter * 32 + lane;                     // row of the tile == TMEM lane (query row / key row)
@@ -454,9 +461,10 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
   const float my_lse2 = KEYMAJOR ? 0.f : s_lse2[r], my_D = KEYMAJOR ? 0.f : s_D[r];
   const long long drop_base = sh * p.Lq * p.Lk;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {                                       // whole warp, uniform control flow (descriptors in uniform registers); one elected lane issues
     issue_scores(0);
-    umma_commit(&bars[0]);
+    if (elect_one()) umma_commit(&bars[0]);
+    __syncwarp();
   }
   for (int ch = 0; ch < nch; ++ch) {
     mbar_wait(&bars[0], ch & 1);
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       if (KEYMAJOR) {
         issue_accum(ch, 128, 0, dcym);                    // dV += (P . mask)^T dO
         issue_accum(ch, 160, 64, dcxm);                   // dK += dS^T Q
@@ -506,10 +514,11 @@ __global__ void __launch_bounds__(kTThreads, 2) tattn_bwd_kernel(const TAttnArgs
       }
       if (ch + 1 < nch) {
         issue_scores(ch + 1);                            // overwrites T1 / T2: the MMA pipe runs in issue order
-        umma_commit(&bars[0]);
+        if (elect_one()) umma_commit(&bars[0]);
       } else {
-        umma_commit(&bars[1]);
+        if (elect_one()) umma_commit(&bars[1]);
       }
+      __syncwarp();
     }
   }
   mbar_wait(&bars[1], 0);

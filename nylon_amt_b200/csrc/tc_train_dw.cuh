@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tdw_kernel(const __grid_constan
         tma_load_2d(dst + raw_y, &map_x, 0, (int)m0, &raw_full[rs]);
       }
     }
-  } else if (lane == 0) {
-    // ===================== MMA issuer =====================
+  } else {
+    // ===================== MMA issuer: the whole warp runs the loop (uniform descriptors), one elected lane issues and commits =====================
     // A = two neighbouring dY blocks of one piece (MN-major, M = 128); B = a run of up to four 64-column atoms of [ones | c0 | c1 | c2]
     // (MN-major, N <= 256).  dY piece q meets the ones column and the X pieces 0 .. 2 - q: the six products that matter
     // (b0c0, b0c1, b0c2, b1c0, b1c1, b2c0) in 3 (K = 64) or 5 (K = 128) wide MMAs per 16 rows instead of 9 narrow ones -- the narrow
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tdw_kernel(const __grid_constan
       fence_after_sync();
       const uint32_t base = ring_lo + slot * slot16;
       const uint32_t acc0 = s > 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if (g < G) {
@@ -215,8 +216,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) tdw_kernel(const __grid_constan
         }
       }
       umma_commit(&empty[slot]);
+      }
+      __syncwarp();
     }
-    umma_commit(done);
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   }
   __syncwarp();
   if (warp < 8 && S > 0) {

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(kGThreads, MINB) tgemm_kernel(const TGemmArgs 
     }
   };
   const uint32_t idesc = make_idesc(128, N, false, false, false);
-  const uint64_t da = make_sdesc(smem_u32(s_a), 16, 1024, kSwz128), dw = make_sdesc(smem_u32(s_w), 16, 1024, kSwz128);   // bases: hi piece, K block 0
+  const SDescBase kd = sdesc_base(16, 1024, kSwz128);
+  const uint32_t a16 = sdesc_lo(kd, smem_u32(s_a)), w16 = sdesc_lo(kd, smem_u32(s_w));   // low descriptor words of the hi pieces, K block 0
   const int q = warp & 3, half = warp >> 2;
   const int n_chunks = (N + 31) >> 5;
   uint8_t* stage = s_a + warp * 4096;
@@ -162,22 +163,22 @@ __global__ void __launch_bounds__(kGThreads, MINB) tgemm_kernel(const TGemmArgs 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {
-      uint32_t acc = 0;
+    if (warp == 0) {                                           // whole warp (uniform descriptors), the MMAs issued back to back by one elected lane
+      if (elect_one()) {
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const uint64_t ap = sdesc_advance(da, part == 1 ? A_PART : 0), wp = part == 2 ? sdesc_advance(dw, w_part) : dw;
+        for (int part = 0; part < 3; ++part) {
+          const uint32_t ap = a16 + (part == 1 ? (A_PART >> 4) : 0), wp = w16 + (part == 2 ? ((uint32_t)w_part >> 4) : 0);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t wk = sdesc_advance(wp, kb * N * 128);
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t wk = wp + ((uint32_t)(kb * N * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_base, sdesc_advance(ap, kb * (128 * 128) + k * 32), sdesc_advance(wk, k * 32), idesc, acc);
-            acc = 1;
+            for (int k = 0; k < 4; ++k)
+              umma_f16_lohi(tmem_base, ap + ((kb * (128 * 128)) >> 4) + 2 * k, kd.hi, wk + 2 * k, kd.hi, idesc, (part | kb | k) ? 1u : 0u);
           }
         }
+        umma_commit(bar);
       }
-      umma_commit(bar);
+      __syncwarp();
     }
     const long long next = tile + gridDim.x;
     if (next < n_tiles) load_tile(next);                       // in flight during the MMAs and the epilogue
