@@ -478,10 +478,11 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                       // whole warp, uniform control flow; one elected lane issues MMAs and commits
       const uint32_t idesc_s = make_idesc(128, LK, BF16, false, false);
       const uint32_t idesc_o = make_idesc(128, DH, BF16, false, true);
       const SDescBase kds2 = sdesc_base(16, kAtom, kSwz128), kdv2 = sdesc_base(kAtom, kAtom, kSwz128);
+      auto commit = [&](uint64_t* bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
       int slot = 0;
       uint32_t ph = 0, qph = 0, pph = 0, dph = 0;
       auto take = [&]() -> int {
@@ -497,35 +498,41 @@ __global__ void __launch_bounds__(kAttnProbsThreads, 1) attn_probs_kernel(const 
         mbar_wait(p_done, dph ^ 1); dph ^= 1;                             // the previous item's probabilities have been read out of P
         fence_after_sync();
         const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_ring + (size_t)ks * L::slot_bytes);
-        uint32_t acc = 0;
         const int s_prod = (X3 && !p.s_single) ? 3 : 1, pv_prod = (X3 && !p.pv_single) ? 3 : 1;
-        for (int part = 0; part < s_prod; ++part) {                       // S = Qh Kh + Ql Kh + Qh Kl
-          const uint32_t qp = qa + (part == 1 ? 128 * 64 * 2 : 0), kp = ka + (part == 2 ? L::kv_part : 0);
+        if (elect_one()) {
+          uint32_t acc = 0;
+          for (int part = 0; part < s_prod; ++part) {                     // S = Qh Kh + Ql Kh + Qh Kl
+            const uint32_t qp = qa + (part == 1 ? 128 * 64 * 2 : 0), kp = ka + (part == 2 ? L::kv_part : 0);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            umma_f16_lohi(tmem_base, sdesc_lo(kds2, qp) + 2 * k, kds2.hi, sdesc_lo(kds2, kp) + 2 * k, kds2.hi, idesc_s, acc);
-            acc = 1;
+            for (int k = 0; k < DH / 16; ++k) {
+              umma_f16_lohi(tmem_base, sdesc_lo(kds2, qp) + 2 * k, kds2.hi, sdesc_lo(kds2, kp) + 2 * k, kds2.hi, idesc_s, acc);
+              acc = 1;
+            }
           }
         }
-        umma_commit(s_ready);
-        umma_commit(q_empty);
-        umma_commit(&ring_empty[ks]);
+        __syncwarp();
+        commit(s_ready);
+        commit(q_empty);
+        commit(&ring_empty[ks]);
         const int vs = take();
         mbar_wait(p_ready, pph); pph ^= 1;
         fence_after_sync();
         const uint32_t va = smem_u32(s_ring + (size_t)vs * L::slot_bytes);
-        acc = 0;
-        for (int part = 0; part < pv_prod; ++part) {                      // O = Ph Vh + Pl Vh + Ph Vl, A = P from TMEM
-          const uint32_t vp = va + (part == 2 ? L::kv_part : 0);
+        if (elect_one()) {
+          uint32_t acc = 0;
+          for (int part = 0; part < pv_prod; ++part) {                    // O = Ph Vh + Pl Vh + Ph Vl, A = P from TMEM
+            const uint32_t vp = va + (part == 2 ? L::kv_part : 0);
 #pragma unroll
-          for (int k = 0; k < LK / 16; ++k) {
-            const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
-            umma_f16_ts_lohi(tmem_base + kOCol, tmem_base + pcol, sdesc_lo(kdv2, vp) + k * (16 * kRowBytes / 16), kdv2.hi, idesc_o, acc);
-            acc = 1;
+            for (int k = 0; k < LK / 16; ++k) {
+              const uint32_t pcol = X3 ? (uint32_t)((k >> 1) * 32 + (part == 1 ? 16 : 0) + (k & 1) * 8) : (uint32_t)(k * 8);
+              umma_f16_ts_lohi(tmem_base + kOCol, tmem_base + pcol, sdesc_lo(kdv2, vp) + k * (16 * kRowBytes / 16), kdv2.hi, idesc_o, acc);
+              acc = 1;
+            }
           }
         }
-        umma_commit(o_ready);
-        umma_commit(&ring_empty[vs]);
+        __syncwarp();
+        commit(o_ready);
+        commit(&ring_empty[vs]);
       }
     }
   } else {
