@@ -830,8 +830,11 @@ __global__ void time_relayout_bwd_kernel(const float* __restrict__ gU, float sca
 template <int NPROC, int G>
 __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st, const float* __restrict__ dX,
                                                         float scale, int H, int F, int NB, int B, float* __restrict__ dWc, float* __restrict__ dbc) {
-  __shared__ float s_row[256];
-  const int bin = blockIdx.x;
+  // Thread (h, g) owns the taps j = g + G a.  Frames are walked in G phases (f = ph, ph + G, ...): inside a phase the spectrogram values a
+  // thread needs slide by ONE tap slot per frame, so a block of 16 frames shares a register window of NA + 15 values (that many shared-memory reads
+  // for 16 x NA FMAs instead of one read per FMA) and its 16 dE values are fetched in one batch (16 loads in flight).  F % (16 G) == 0.
+  __shared__ float s_row[320];
+  const int bin = blockIdx.x, b = blockIdx.y;
   const int W = F + NPROC - 1;
   const int h = threadIdx.x % H, g = threadIdx.x / H;
   constexpr int NA = (NPROC + G - 1) / G;
@@ -839,25 +842,30 @@ __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
   float bsum = 0.f;
-  {
-    const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < W; i += blockDim.x) s_row[i] = spec[b * sb + bin * sbin + i * st];
-    __syncthreads();
-#pragma unroll 4
-    for (int f = 0; f < F; ++f) {
-      const float e = dX[(((long long)b * F + f) * NB + bin) * H + h] * scale;
-      if (g == 0) bsum += e;
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) s_row[i] = i < W ? spec[b * sb + bin * sbin + i * st] : 0.f;
+  __syncthreads();
+  const float* dx = dX + (((long long)b * F) * NB + bin) * H + h;
+  const long long fstride = (long long)NB * H;
+  for (int ph = 0; ph < G; ++ph) {
+    for (int f0 = ph; f0 < F; f0 += 16 * G) {
+      constexpr int WN = NA + 15;                        // window: taps of the first frame + one more slot per further frame
+      float e[16], w[WN];
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        const int j = g + a * G;
-        if (j < NPROC) acc[a] = fmaf(e, s_row[f + j], acc[a]);
+      for (int i = 0; i < 16; ++i) e[i] = __ldg(dx + (long long)(f0 + i * G) * fstride) * scale;
+#pragma unroll
+      for (int m = 0; m < WN; ++m) w[m] = s_row[f0 + g + G * m];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (g == 0) bsum += e[i];
+#pragma unroll
+        for (int a2 = 0; a2 < NA; ++a2) acc[a2] = fmaf(e[i], w[i + a2], acc[a2]);
       }
     }
   }
 #pragma unroll
-  for (int a = 0; a < NA; ++a) {
-    const int j = g + a * G;
-    if (j < NPROC) atomicAdd(dWc + h * NPROC + j, acc[a]);
+  for (int a2 = 0; a2 < NA; ++a2) {
+    const int j = g + a2 * G;
+    if (j < NPROC) atomicAdd(dWc + h * NPROC + j, acc[a2]);
   }
   if (g == 0) atomicAdd(dbc + h, bsum);
 }
