@@ -679,9 +679,12 @@ static int train_backward(Trainer& t, const float* spec, long long sb, long long
   HFT_CHECK_CUDA(cudaMemsetAsync(t.g_front_b, 0, (size_t)H * sizeof(float), s));
   {
     LaunchScope ls(HFT_KCLASS_FRONT, s);
-    if (H == 64) front_bwd_kernel<65, 4><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
-    else if (H == 128) front_bwd_kernel<65, 2><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
-    else front_bwd_kernel<65, 1><<<dim3(NB, B), 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, t.g_front_w, t.g_front_b);
+    static int spc = -1;                               // segments per CTA (HFT_FRONT_BWD_SPC; see the kernel: parallelism against same-address atomics)
+    if (spc < 0) { const char* e = getenv("HFT_FRONT_BWD_SPC"); spc = e ? atoi(e) : 2; if (spc < 1) spc = 1; }
+    const dim3 fgrid(NB, (B + spc - 1) / spc);
+    if (H == 64) front_bwd_kernel<65, 4><<<fgrid, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, spc, t.g_front_w, t.g_front_b);
+    else if (H == 128) front_bwd_kernel<65, 2><<<fgrid, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, spc, t.g_front_w, t.g_front_b);
+    else front_bwd_kernel<65, 1><<<fgrid, 256, 0, s>>>(spec, sb, sbin, st, t.gX, sqrtH, H, F, NB, B, spc, t.g_front_w, t.g_front_b);
     const int C = m->d.cnn_channel, kw = m->d.cnn_kernel, n_out = m->nproc - (kw - 1);
     const int total = H * C * n_out + H + 32 * (C * kw + C);                     // threads, then one warp per conv_w / conv_b element
     front_chain_bwd_kernel<<<(total + 127) / 128, 128, 0, s>>>(t.g_front_w, t.g_front_b, m->w[m->tok_w], m->w[m->conv_w], m->w[m->conv_b], H, C, kw, n_out, m->nproc,

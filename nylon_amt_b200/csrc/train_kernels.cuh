@@ -825,16 +825,16 @@ __global__ void time_relayout_bwd_kernel(const float* __restrict__ gU, float sca
 }
 
 // Front backward: dWc[h, j] += sum_{b,f} dE[(b,f,bin), h] * spec[b, bin, f + j],  dbc[h] += sum dE   (collapsed 65-tap filter).
-// grid (n_bin, batch): one CTA per (bin, segment) -- 2 048 CTAs for the reduced model, where a grid of n_bin alone left the chip at two CTAs per SM --;
+// grid (n_bin, ceil(batch / spc)): one CTA per (bin, spc segments);
 // threads = G tap groups x H (G * H = 256).  dE = dX * sqrt(H) (the embedding scale).
 template <int NPROC, int G>
 __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict__ spec, long long sb, long long sbin, long long st, const float* __restrict__ dX,
-                                                        float scale, int H, int F, int NB, int B, float* __restrict__ dWc, float* __restrict__ dbc) {
+                                                        float scale, int H, int F, int NB, int B, int spc, float* __restrict__ dWc, float* __restrict__ dbc) {
   // Thread (h, g) owns the taps j = g + G a.  Frames are walked in G phases (f = ph, ph + G, ...): inside a phase the spectrogram values a
   // thread needs slide by ONE tap slot per frame, so a block of 16 frames shares a register window of NA + 15 values (that many shared-memory reads
   // for 16 x NA FMAs instead of one read per FMA) and its 16 dE values are fetched in one batch (16 loads in flight).  F % (16 G) == 0.
   __shared__ float s_row[320];
-  const int bin = blockIdx.x, b = blockIdx.y;
+  const int bin = blockIdx.x;
   const int W = F + NPROC - 1;
   const int h = threadIdx.x % H, g = threadIdx.x / H;
   constexpr int NA = (NPROC + G - 1) / G;
@@ -842,23 +842,26 @@ __global__ void __launch_bounds__(256) front_bwd_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
   float bsum = 0.f;
-  for (int i = threadIdx.x; i < 320; i += blockDim.x) s_row[i] = i < W ? spec[b * sb + bin * sbin + i * st] : 0.f;
-  __syncthreads();
-  const float* dx = dX + (((long long)b * F) * NB + bin) * H + h;
   const long long fstride = (long long)NB * H;
-  for (int ph = 0; ph < G; ++ph) {
-    for (int f0 = ph; f0 < F; f0 += 16 * G) {
-      constexpr int WN = NA + 15;                        // window: taps of the first frame + one more slot per further frame
-      float e[16], w[WN];
+  for (int b = blockIdx.y * spc; b < B && b < (int)(blockIdx.y + 1) * spc; ++b) {   // spc segments per CTA: every CTA closes with NPROC * H same-address atomics
+    __syncthreads();
+    for (int i = threadIdx.x; i < 320; i += blockDim.x) s_row[i] = i < W ? spec[b * sb + bin * sbin + i * st] : 0.f;
+    __syncthreads();
+    const float* dx = dX + (((long long)b * F) * NB + bin) * H + h;
+    for (int ph = 0; ph < G; ++ph) {
+      for (int f0 = ph; f0 < F; f0 += 16 * G) {
+        constexpr int WN = NA + 15;                      // window: taps of the first frame + one more slot per further frame
+        float e[16], w[WN];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) e[i] = __ldg(dx + (long long)(f0 + i * G) * fstride) * scale;
+        for (int i = 0; i < 16; ++i) e[i] = __ldg(dx + (long long)(f0 + i * G) * fstride) * scale;
 #pragma unroll
-      for (int m = 0; m < WN; ++m) w[m] = s_row[f0 + g + G * m];
+        for (int m = 0; m < WN; ++m) w[m] = s_row[f0 + g + G * m];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (g == 0) bsum += e[i];
+        for (int i = 0; i < 16; ++i) {
+          if (g == 0) bsum += e[i];
 #pragma unroll
-        for (int a2 = 0; a2 < NA; ++a2) acc[a2] = fmaf(e[i], w[i + a2], acc[a2]);
+          for (int a2 = 0; a2 < NA; ++a2) acc[a2] = fmaf(e[i], w[i + a2], acc[a2]);
+        }
       }
     }
   }
